@@ -1,0 +1,500 @@
+"""Host-side mirror of the reference's R interface for the packed-genotype hot path.
+
+R is not available in the build image, so the host side above the C ABI (include/bsgpu.h) is Python,
+mirroring the reference's operator interface: same function names, argument meaning (1-based
+``ind_row`` / ``ind_col``, ``center`` / ``scale`` per selected column, ``ncores`` accepted and ignored)
+and error behaviour, so the parity tests read like the reference's testthat files.  Reference:
+
+    bed()/bed_light          R/bed-class.R:65-134,176-208      -> class Bed
+    bed_prodVec / cprodVec   R/bed-mult-vec.R:58-75 / :20-37
+    bed_counts / bed_MAF / bed_scaleBinom   R/binom-scaling.R:166-178 / :203-222 / :133-142
+    obj.bed[i, j]            R/bed-mat-acc.R:21-38 (read_bed)
+    bed_cor / snp_cor        R/corr.R:3-57,95-132
+    bed_ld_scores / snp_ld_scores  R/ld-scores.R:3-72
+    bed_tcrossprodSelf       R/bed-tcrossprodSelf.R:21-52
+    bed_randomSVD            R/autoSVD.R:205-219
+
+Everything computes on the GPU through libbsgpu; there is no CPU path here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import BsgError, check, lib
+
+ERROR_DIM = "Incompatibility between dimensions."
+NA_INTEGER = -2147483648
+
+LAYOUT_AUTO, LAYOUT_SNP_MAJOR, LAYOUT_SAMPLE_MAJOR = 0, 1, 2
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _pi(a):
+    return None if a is None else a.ctypes.data_as(_lib.c_int_p)
+
+
+def _pd(a):
+    return None if a is None else a.ctypes.data_as(_lib.c_dbl_p)
+
+
+def _count_lines(path):
+    n = 0
+    with open(path, "rb") as f:
+        for _ in f:
+            n += 1
+    return n
+
+
+class Bed:
+    """A PLINK .bed staged in HBM: the ``bed`` RefClass of the reference (R/bed-class.R:65-134).
+
+    ``Bed(bedfile)`` reads n from the .fam and m from the .bim like ``$nrow`` / ``$ncol`` do, validates
+    the file exactly like ``bedXPtr`` (src/bed-acc-xptr.cpp:14-34) and stages the packed bytes once.
+    ``col_range=(begin, end)`` (0-based, half open) stages only a column shard (multi-GPU).
+    """
+
+    def __init__(self, bedfile=None, nrow=None, ncol=None, device=0, layouts=LAYOUT_AUTO, col_range=None,
+                 _handle=None, _shape=None):
+        self._h = None
+        self.bedfile = None
+        if _handle is not None:
+            self._h = _handle
+            self.nrow, self.ncol = _shape
+            self.bedfile = "<device>"
+            return
+        bedfile = os.path.expanduser(bedfile)
+        self.bedfile = bedfile
+        pre = bedfile[:-4] if bedfile.endswith(".bed") else bedfile
+        for f in (bedfile, pre + ".bim", pre + ".fam"):
+            if (nrow is None or ncol is None) and not os.path.exists(f):
+                raise FileNotFoundError("File '%s' doesn't exist." % f)
+        n = _count_lines(pre + ".fam") if nrow is None else int(nrow)
+        m = _count_lines(pre + ".bim") if ncol is None else int(ncol)
+        b, e = (0, m) if col_range is None else col_range
+        h = C.c_void_p()
+        check(lib().bsg_open_bed(bedfile.encode(), n, m, int(b), int(e), int(device), int(layouts), C.byref(h)))
+        self._h = h
+        self.nrow, self.ncol = n, int(e) - int(b)
+        self.col_offset = int(b)
+
+    # --- alternative constructors -----------------------------------------------------------
+    @classmethod
+    def from_packed(cls, packed, n, m, device=0, layouts=LAYOUT_AUTO):
+        packed = np.ascontiguousarray(packed, dtype=np.uint8).reshape(-1)
+        if packed.size != ((n + 3) // 4) * m:
+            raise BsgError(5, "n or p does not match the dimensions of the file.")
+        h = C.c_void_p()
+        check(lib().bsg_open_packed(packed.ctypes.data_as(_lib.c_u8_p), int(n), int(m), int(device), int(layouts),
+                                    C.byref(h)))
+        return cls(_handle=h, _shape=(int(n), int(m)))
+
+    @classmethod
+    def synthetic(cls, n, m, seed=20250924, na_rate=0.0, col_offset=0, device=0, layouts=LAYOUT_AUTO):
+        h = C.c_void_p()
+        check(lib().bsg_open_synth(int(n), int(m), int(seed), float(na_rate), int(col_offset), int(device),
+                                   int(layouts), C.byref(h)))
+        return cls(_handle=h, _shape=(int(n), int(m)))
+
+    @classmethod
+    def from_fbm(cls, bytes_nm, code256=None, device=0, layouts=LAYOUT_AUTO):
+        """FBM.code256 twin (snp_* functions): n x m raw bytes + the 256-entry code (default CODE_012)."""
+        a = np.asfortranarray(bytes_nm, dtype=np.uint8)
+        n, m = a.shape
+        if code256 is None:
+            code256 = np.full(256, np.nan)
+            code256[:3] = [0, 1, 2]
+        code256 = _f64(code256)
+        h = C.c_void_p()
+        check(lib().bsg_open_fbm256(a.ctypes.data_as(_lib.c_u8_p), n, m, _pd(code256), int(device), int(layouts),
+                                    C.byref(h)))
+        return cls(_handle=h, _shape=(n, m))
+
+    # --- RefClass surface -------------------------------------------------------------------------
+    @property
+    def address(self):
+        return self._h
+
+    @property
+    def light(self):
+        return self
+
+    @property
+    def shape(self):
+        return (self.nrow, self.ncol)
+
+    def __len__(self):
+        return self.nrow * self.ncol
+
+    def __repr__(self):
+        return "A 'bed' object with %d samples and %d variants." % (self.nrow, self.ncol)
+
+    def rows_along(self):
+        return np.arange(1, self.nrow + 1, dtype=np.int32)
+
+    def cols_along(self):
+        return np.arange(1, self.ncol + 1, dtype=np.int32)
+
+    @property
+    def has_na(self):
+        return bool(lib().bsg_has_na(self._h))
+
+    @property
+    def layouts(self):
+        return int(lib().bsg_layouts(self._h))
+
+    @property
+    def packed_bytes(self):
+        return int(lib().bsg_packed_bytes(self._h))
+
+    def export_packed(self):
+        out = np.empty(((self.nrow + 3) // 4) * self.ncol, dtype=np.uint8)
+        check(lib().bsg_export_packed(self._h, out.ctypes.data_as(_lib.c_u8_p)))
+        return out
+
+    def close(self):
+        if self._h is not None:
+            lib().bsg_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # obj.bed[i, j]  (R/bed-mat-acc.R:21-38; 1-based like R, NA -> NA_INTEGER)
+    def __getitem__(self, key):
+        i, j = key
+        ind_row = self.rows_along() if i is None or (isinstance(i, slice) and i == slice(None)) else _i32(np.atleast_1d(i))
+        ind_col = self.cols_along() if j is None or (isinstance(j, slice) and j == slice(None)) else _i32(np.atleast_1d(j))
+        return read_bed(self, ind_row, ind_col)
+
+
+def bed(bedfile, **kw):
+    """Wrapper constructor (R/bed-class.R:146)."""
+    return Bed(bedfile, **kw)
+
+
+def _assert_bed(obj):
+    if not isinstance(obj, Bed):
+        raise TypeError("'obj.bed' is not of class 'bed' or 'bed_light'.")
+
+
+def _ind(obj, ind_row, ind_col):
+    if ind_row is None:
+        raise ValueError("'ind.row' can't be `NULL`.")
+    if ind_col is None:
+        raise ValueError("'ind.col' can't be `NULL`.")
+    return _i32(ind_row), _i32(ind_col)
+
+
+def _dflt(obj, ind_row, ind_col):
+    return (obj.rows_along() if ind_row is ... else ind_row), (obj.cols_along() if ind_col is ... else ind_col)
+
+
+def _assert_lengths(a, b):
+    if len(a) != len(b):
+        raise ValueError(ERROR_DIM)
+
+
+class View:
+    """Device-resident accessor state (ind.row, ind.col, center, scale): bsg_view."""
+
+    def __init__(self, obj, ind_row=..., ind_col=..., center=None, scale=None):
+        _assert_bed(obj)
+        ind_row, ind_col = _dflt(obj, ind_row, ind_col)
+        ind_row, ind_col = _ind(obj, ind_row, ind_col)
+        self.obj = obj
+        self.nr, self.nc = ind_row.size, ind_col.size
+        if (center is None) != (scale is None):
+            raise ValueError("center and scale must be given together")
+        if center is not None:
+            center, scale = _f64(center), _f64(scale)
+            _assert_lengths(center, ind_col)
+            _assert_lengths(scale, ind_col)
+        v = C.c_void_p()
+        check(lib().bsg_view_create(obj._h, _pi(ind_row), self.nr, _pi(ind_col), self.nc, _pd(center), _pd(scale),
+                                    C.byref(v)))
+        self._v = v
+
+    def prodvec(self, y_col):
+        y_col = _f64(y_col)
+        if y_col.size != self.nc:
+            raise ValueError(ERROR_DIM)
+        out = np.empty(self.nr)
+        check(lib().bsg_view_prodvec(self._v, _pd(y_col), _pd(out)))
+        return out
+
+    def cprodvec(self, y_row):
+        y_row = _f64(y_row)
+        if y_row.size != self.nr:
+            raise ValueError(ERROR_DIM)
+        out = np.empty(self.nc)
+        check(lib().bsg_view_cprodvec(self._v, _pd(y_row), _pd(out)))
+        return out
+
+    def prodvec_dev(self, x_ptr, out_ptr, stream=0):
+        check(lib().bsg_view_prodvec_dev(self._v, int(x_ptr), int(out_ptr), int(stream) or None))
+
+    def cprodvec_dev(self, x_ptr, out_ptr, stream=0):
+        check(lib().bsg_view_cprodvec_dev(self._v, int(x_ptr), int(out_ptr), int(stream) or None))
+
+    def close(self):
+        if self._v is not None:
+            lib().bsg_view_destroy(self._v)
+            self._v = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def bed_prodVec(obj_bed, y_col, ind_row=..., ind_col=..., center=None, scale=None, ncores=1):
+    """Product between a "bed" object and a vector (R/bed-mult-vec.R:58-75)."""
+    _assert_bed(obj_bed)
+    ind_row, ind_col = _ind(obj_bed, *_dflt(obj_bed, ind_row, ind_col))
+    y_col = _f64(y_col)
+    _assert_lengths(y_col, ind_col)
+    center = np.zeros(ind_col.size) if center is None else _f64(center)
+    _assert_lengths(center, ind_col)
+    scale = np.ones(ind_col.size) if scale is None else _f64(scale)
+    _assert_lengths(scale, ind_col)
+    out = np.empty(ind_row.size)
+    check(lib().bsg_prodvec(obj_bed._h, _pi(ind_row), ind_row.size, _pi(ind_col), ind_col.size, _pd(center),
+                            _pd(scale), _pd(y_col), _pd(out)))
+    return out
+
+
+def bed_cprodVec(obj_bed, y_row, ind_row=..., ind_col=..., center=None, scale=None, ncores=1):
+    """Cross-product between a "bed" object and a vector (R/bed-mult-vec.R:20-37)."""
+    _assert_bed(obj_bed)
+    ind_row, ind_col = _ind(obj_bed, *_dflt(obj_bed, ind_row, ind_col))
+    y_row = _f64(y_row)
+    _assert_lengths(y_row, ind_row)
+    center = np.zeros(ind_col.size) if center is None else _f64(center)
+    _assert_lengths(center, ind_col)
+    scale = np.ones(ind_col.size) if scale is None else _f64(scale)
+    _assert_lengths(scale, ind_col)
+    out = np.empty(ind_col.size)
+    check(lib().bsg_cprodvec(obj_bed._h, _pi(ind_row), ind_row.size, _pi(ind_col), ind_col.size, _pd(center),
+                             _pd(scale), _pd(y_row), _pd(out)))
+    return out
+
+
+def bed_colstats(obj_bed, ind_row=..., ind_col=..., ncores=1):
+    """src/bed-fun.cpp:9-46 -> dict(sumX, denoX, nb_nona_col); warns like the reference (:40-41)."""
+    _assert_bed(obj_bed)
+    ind_row, ind_col = _ind(obj_bed, *_dflt(obj_bed, ind_row, ind_col))
+    m = ind_col.size
+    sumX, denoX, nb = np.empty(m), np.empty(m), np.empty(m, dtype=np.int32)
+    n_bad = C.c_int(0)
+    check(lib().bsg_colstats(obj_bed._h, _pi(ind_row), ind_row.size, _pi(ind_col), m, _pd(sumX), _pd(denoX), _pi(nb),
+                             C.byref(n_bad)))
+    if n_bad.value > 0:
+        import warnings
+
+        warnings.warn("%d variants have >50%% missing values." % n_bad.value)
+    return {"sumX": sumX, "denoX": denoX, "nb_nona_col": nb}
+
+
+def bed_scaleBinom(obj_bed, ind_row=..., ind_col=..., ncores=1):
+    """Binomial(2, p) scaling (R/binom-scaling.R:133-142)."""
+    st = bed_colstats(obj_bed, ind_row, ind_col, ncores)
+    with np.errstate(all="ignore"):
+        af = st["sumX"] / (2 * st["nb_nona_col"])
+        return {"center": 2 * af, "scale": np.sqrt(2 * af * (1 - af))}
+
+
+def bed_counts(obj_bed, ind_row=..., ind_col=..., byrow=False, ncores=1):
+    """Counts of 0s, 1s, 2s and NAs by variant (or by individual): R/binom-scaling.R:166-178 -> (4, k)."""
+    _assert_bed(obj_bed)
+    ind_row, ind_col = _ind(obj_bed, *_dflt(obj_bed, ind_row, ind_col))
+    k = ind_row.size if byrow else ind_col.size
+    res = np.zeros((k, 4), dtype=np.int32)
+    f = lib().bsg_row_counts if byrow else lib().bsg_col_counts
+    check(f(obj_bed._h, _pi(ind_row), ind_row.size, _pi(ind_col), ind_col.size, _pi(res)))
+    return res.T
+
+
+def bed_MAF(obj_bed, ind_row=..., ind_col=..., ncores=1):
+    """Allele frequencies (R/binom-scaling.R:203-222)."""
+    _assert_bed(obj_bed)
+    ind_row, ind_col = _ind(obj_bed, *_dflt(obj_bed, ind_row, ind_col))
+    counts = bed_counts(obj_bed, ind_row, ind_col, False, ncores).astype(np.int64)
+    ac = counts[1] + 2 * counts[2]
+    nb_nona = ind_row.size - counts[3]
+    with np.errstate(all="ignore"):
+        af = ac / (2 * nb_nona)
+    return {"ac": ac, "mac": np.minimum(ac, 2 * nb_nona - ac), "af": af, "maf": np.minimum(af, 1 - af), "N": nb_nona}
+
+
+def snp_colstats(G, ind_row=..., ind_col=..., ncores=1):
+    """src/colstats.cpp:8-35 on an FBM-backed handle."""
+    ind_row, ind_col = _ind(G, *_dflt(G, ind_row, ind_col))
+    m = ind_col.size
+    sumX, denoX = np.empty(m), np.empty(m)
+    check(lib().bsg_snp_colstats(G._h, _pi(ind_row), ind_row.size, _pi(ind_col), m, _pd(sumX), _pd(denoX)))
+    return {"sumX": sumX, "denoX": denoX}
+
+
+def snp_scaleBinom(nploidy=2):
+    """R/binom-scaling.R:62-77: returns the scaling function."""
+
+    def f(X, ind_row=..., ind_col=..., ncores=1):
+        ind_row2, _ = _dflt(X, ind_row, ind_col)
+        af = snp_colstats(X, ind_row, ind_col, ncores)["sumX"] / (len(ind_row2) * nploidy)
+        with np.errstate(all="ignore"):
+            return {"center": nploidy * af, "scale": np.sqrt(nploidy * af * (1 - af))}
+
+    return f
+
+
+def snp_MAF(G, ind_row=..., ind_col=..., nploidy=2, ncores=1):
+    """R/binom-scaling.R:94-106."""
+    ind_row2, _ = _dflt(G, ind_row, ind_col)
+    af = snp_colstats(G, ind_row, ind_col, ncores)["sumX"] / (len(ind_row2) * nploidy)
+    return np.minimum(af, 1 - af)
+
+
+def read_bed(obj_bed, ind_row, ind_col, na_val=NA_INTEGER):
+    """src/bed-mat-acc.cpp:8-26 -> int32 (nr, nc)."""
+    _assert_bed(obj_bed)
+    ind_row, ind_col = _i32(ind_row), _i32(ind_col)
+    res = np.empty((ind_col.size, ind_row.size), dtype=np.int32)
+    check(lib().bsg_read_bed(obj_bed._h, _pi(ind_row), ind_row.size, _pi(ind_col), ind_col.size, int(na_val), _pi(res)))
+    return res.T
+
+
+def read_bed_scaled(obj_bed, ind_row, ind_col, center, scale):
+    """src/bed-mat-acc.cpp:30-49 -> float64 (nr, nc)."""
+    _assert_bed(obj_bed)
+    ind_row, ind_col = _i32(ind_row), _i32(ind_col)
+    center, scale = _f64(center), _f64(scale)
+    if center.size != ind_col.size or scale.size != ind_col.size:
+        raise ValueError(ERROR_DIM)
+    res = np.empty((ind_col.size, ind_row.size), dtype=np.float64)
+    check(lib().bsg_read_bed_scaled(obj_bed._h, _pi(ind_row), ind_row.size, _pi(ind_col), ind_col.size, _pd(center),
+                                    _pd(scale), _pd(res)))
+    return res.T
+
+
+def cor_thresholds(n_row, alpha=1.0, thr_r2=0.0):
+    """R/corr.R:17-23,29: THR = q / sqrt(k - 2 + q^2) with q = qt(alpha/2, k-2, upper); pmax with sqrt(thr_r2)."""
+    from scipy import stats
+
+    k = np.arange(1, n_row + 1, dtype=np.float64)
+    with np.errstate(all="ignore"):
+        q = stats.t.isf(alpha / 2, df=k - 2)
+        thr = q / np.sqrt(k - 2 + q * q)
+        return np.where(np.isnan(thr), np.nan, np.maximum(thr, np.sqrt(thr_r2)))
+
+
+def corMat(obj, rowInd, colInd, size, thr, pos, fill_diag=True, ncores=1):
+    """src/corr.cpp:102-126 -> CSC pieces (p, i, x); i 0-based ascending, diagonal last."""
+    rowInd, colInd = _i32(rowInd), _i32(colInd)
+    thr, pos = _f64(thr), _f64(pos)
+    if pos.size != colInd.size:
+        raise ValueError(ERROR_DIM)
+    if thr.size != rowInd.size:
+        raise ValueError(ERROR_DIM)
+    p = np.zeros(colInd.size + 1, dtype=np.int64)
+    pi, px = _lib.c_int_p(), _lib.c_dbl_p()
+    check(lib().bsg_cor(obj._h, _pi(rowInd), rowInd.size, _pi(colInd), colInd.size, float(size), _pd(thr), _pd(pos),
+                        int(bool(fill_diag)), p.ctypes.data_as(_lib.c_i64_p), C.byref(pi), C.byref(px)))
+    nnz = int(p[-1])
+    i = np.ctypeslib.as_array(pi, shape=(max(nnz, 1),))[:nnz].copy()
+    x = np.ctypeslib.as_array(px, shape=(max(nnz, 1),))[:nnz].copy()
+    lib().bsg_free(pi)
+    lib().bsg_free(px)
+    return p, i, x
+
+
+def _cor0(obj, ind_row, ind_col, size, alpha, thr_r2, fill_diag, infos_pos, ncores):
+    ind_row, ind_col = _ind(obj, *_dflt(obj, ind_row, ind_col))
+    if infos_pos is None:
+        infos_pos = 1000.0 * np.arange(1, ind_col.size + 1)
+    infos_pos = _f64(infos_pos)
+    _assert_lengths(infos_pos, ind_col)
+    if np.any(np.diff(infos_pos) < 0):
+        raise ValueError("'infos.pos' is not sorted.")
+    thr = cor_thresholds(ind_row.size, alpha, thr_r2)
+    p, i, x = corMat(obj, ind_row, ind_col, size * 1000.0, thr, infos_pos, fill_diag, ncores)
+    if np.isnan(x).any():
+        import warnings
+
+        warnings.warn("NA or NaN values in the resulting correlation matrix.")
+    return p, i, x
+
+
+def bed_cor(obj_bed, ind_row=..., ind_col=..., size=500, alpha=1.0, thr_r2=0.0, fill_diag=True, infos_pos=None, ncores=1):
+    """Correlation matrix (R/corr.R:116-132): CSC (p, i, x) of the upper-triangular dsCMatrix."""
+    _assert_bed(obj_bed)
+    return _cor0(obj_bed, ind_row, ind_col, size, alpha, thr_r2, fill_diag, infos_pos, ncores)
+
+
+snp_cor = bed_cor  # R/corr.R:95-110 (FBM-backed handles share the packed kernels)
+
+
+def bed_ld_scores(obj_bed, ind_row=..., ind_col=..., size=500, infos_pos=None, ncores=1):
+    """LD scores (R/ld-scores.R:59-72)."""
+    _assert_bed(obj_bed)
+    ind_row, ind_col = _ind(obj_bed, *_dflt(obj_bed, ind_row, ind_col))
+    if infos_pos is None:
+        infos_pos = 1000.0 * np.arange(1, ind_col.size + 1)
+    infos_pos = _f64(infos_pos)
+    _assert_lengths(infos_pos, ind_col)
+    if np.any(np.diff(infos_pos) < 0):
+        raise ValueError("'infos.pos' is not sorted.")
+    out = np.empty(ind_col.size)
+    check(lib().bsg_ld_scores(obj_bed._h, _pi(ind_row), ind_row.size, _pi(ind_col), ind_col.size, float(size) * 1000.0,
+                              _pd(infos_pos), _pd(out)))
+    return out
+
+
+snp_ld_scores = bed_ld_scores
+
+
+def bed_tcrossprodSelf(obj_bed, fun_scaling=bed_scaleBinom, ind_row=..., ind_col=..., block_size=None):
+    """tcrossprod / GRM (R/bed-tcrossprodSelf.R:21-52).  The R block loop is one C-ABI call; ``block_size``
+    is accepted for signature compatibility.  Returns (K, center, scale)."""
+    _assert_bed(obj_bed)
+    ind_row, ind_col = _ind(obj_bed, *_dflt(obj_bed, ind_row, ind_col))
+    ms = fun_scaling(obj_bed, ind_row=ind_row, ind_col=ind_col)
+    center, scale = _f64(ms["center"]), _f64(ms["scale"])
+    n = ind_row.size
+    K = np.empty((n, n))
+    check(lib().bsg_tcrossprod(obj_bed._h, _pi(ind_row), n, _pi(ind_col), ind_col.size, _pd(center), _pd(scale), _pd(K)))
+    return K, center, scale
+
+
+def bed_randomSVD(obj_bed, fun_scaling=bed_scaleBinom, ind_row=..., ind_col=..., k=10, tol=1e-4, verbose=False,
+                  ncores=1, maxit=1000):
+    """Randomized partial SVD (R/autoSVD.R:205-219) -> dict(d, u, v, niter, nops, center, scale)."""
+    _assert_bed(obj_bed)
+    ind_row, ind_col = _ind(obj_bed, *_dflt(obj_bed, ind_row, ind_col))
+    n, m = ind_row.size, ind_col.size
+    center = scale = None
+    if fun_scaling is not bed_scaleBinom:
+        ms = fun_scaling(obj_bed, ind_row=ind_row, ind_col=ind_col)
+        center, scale = _f64(ms["center"]), _f64(ms["scale"])
+    d = np.empty(k)
+    u = np.empty((k, n))
+    v = np.empty((k, m))
+    c_out, s_out = np.empty(m), np.empty(m)
+    niter, nops = C.c_int(0), C.c_int(0)
+    check(lib().bsg_randomsvd(obj_bed._h, _pi(ind_row), n, _pi(ind_col), m, _pd(center), _pd(scale), int(k), float(tol),
+                              int(maxit), _pd(d), _pd(u), _pd(v), _pd(c_out), _pd(s_out), C.byref(niter), C.byref(nops)))
+    return {"d": d, "u": u.T, "v": v.T, "niter": niter.value, "nops": nops.value, "center": c_out, "scale": s_out}

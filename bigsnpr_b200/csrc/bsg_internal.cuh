@@ -1,0 +1,123 @@
+// bsg_internal.cuh -- shared declarations of libbsgpu (not part of the public ABI).
+//
+// HBM layout of a staged genotype matrix (see DESIGN.md "Data layout"):
+//   * "staged code": 2 bits per genotype, value = genotype for 0/1/2 and 3 for missing.  It is a
+//     bijective recode of the .bed code of the reference (src/bed-acc.h:22-37: 00->2, 01->NA,
+//     10->1, 11->0), done once at staging, so that the packed value IS the number the kernels
+//     multiply with.  Padding slots (samples >= n of the last byte, bytes up to the line stride)
+//     hold code 0: they add nothing to any sum and are never missing.
+//   * copy A (SNP-major): line j = SNP column j, n codes, lowest bits = first sample -- the .bed
+//     orientation.  Line stride = round_up(ceil(n/4), 128) bytes.
+//   * copy B (sample-major): line i = sample i, m codes.  Line stride = round_up(ceil(m/4), 128).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "bsgpu.h"
+
+#define BSG_KIND_BED 0
+#define BSG_KIND_FBM 1
+
+namespace bsg {
+
+extern thread_local std::string g_err;
+int fail(int code, const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+void count_launch(int n = 1);
+
+#define BSG_CUDA(call)                                   \
+  do {                                                   \
+    cudaError_t e__ = (call);                            \
+    if (e__ != cudaSuccess) return bsg::cuda_fail(e__, #call); \
+  } while (0)
+
+#define BSG_TRY(call)        \
+  do {                       \
+    int rc__ = (call);       \
+    if (rc__) return rc__;   \
+  } while (0)
+
+inline int64_t round_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+// growable device scratch buffer
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes);
+  void release();
+  template <class T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+}  // namespace bsg
+
+struct bsg_bed {
+  int kind = BSG_KIND_BED;
+  int device = 0;
+  int n = 0, m = 0;          // samples, SNP columns held by this handle
+  int64_t n_byte = 0;        // ceil(n/4): bytes per column in the .bed file
+  int64_t strideA = 0, strideB = 0;
+  uint8_t *A = nullptr;      // m lines of strideA bytes
+  uint8_t *B = nullptr;      // n lines of strideB bytes (may be null)
+  int layouts = 0;
+  int has_na = 0;
+  int32_t *cntA = nullptr;   // [m][4] counts of codes 0,1,2,3 per SNP over all n samples
+  int32_t *cntB = nullptr;   // [n][4] counts per sample over all m SNPs (only with copy B)
+  uint8_t *naA = nullptr;    // [m] 1 if the SNP line has a missing value
+  uint8_t *naB = nullptr;    // [n]
+  double code256[256];       // FBM handles: value of each raw byte code (bigstatsr code256)
+  int fbm_generic = 0;       // FBM whose codes are not {0,1,2,NA}: only 0/1/2/NA repack is supported
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // view cached for the 9-argument drop-in matvec calls (bsg_prodvec / bsg_cprodvec)
+  struct bsg_view *cv = nullptr;
+  std::vector<int> cv_row, cv_col;
+  // scratch reused across calls
+  bsg::DevBuf w_idx_row, w_idx_col, w_center, w_scale, w_x, w_out, w_tmp0, w_tmp1, w_tmp2, w_tmp3,
+      w_part, w_dig1, w_dig2, w_misc;
+};
+
+namespace bsg {
+
+// ---- bsg_core.cu -----------------------------------------------------------------------------
+int stage_finish(bsg_bed *h);  // builds copy B (if requested), counts and NA flags from copy A
+int bind_device(const bsg_bed *h);
+
+// ---- index helpers (bsg_core.cu) -------------------------------------------------------------
+// validates 1-based host indices against `limit` (src/bed-acc.h:64-65) and uploads them 0-based.
+// ind == NULL -> identity of length `len` is implied, *dev = nullptr.
+int upload_index(bsg_bed *h, const int *ind, int len, int limit, DevBuf &buf, const int **dev);
+
+// ---- bsg_simple.cu: generic accessor-style kernels (any index multiset) ----------------------
+int simple_prodvec(bsg_bed *h, const int *d_row, int nr, const int *d_col, int nc, const double *d_center,
+                   const double *d_scale, const double *d_x, double *d_out, cudaStream_t s);
+int simple_cprodvec(bsg_bed *h, const int *d_row, int nr, const int *d_col, int nc, const double *d_center,
+                    const double *d_scale, const double *d_x, double *d_out, cudaStream_t s);
+int counts_cols(bsg_bed *h, const int *d_row, int nr, const int *d_col, int nc, int32_t *d_out4, cudaStream_t s);
+int counts_rows(bsg_bed *h, const int *d_row, int nr, const int *d_col, int nc, int32_t *d_out4, cudaStream_t s);
+int read_dense(bsg_bed *h, const int *d_row, int nr, const int *d_col, int nc, int na_val, int *d_out, cudaStream_t s);
+int read_dense_scaled(bsg_bed *h, const int *d_row, int nr, const int *d_col, int nc, const double *d_center,
+                      const double *d_scale, double *d_out, cudaStream_t s);
+
+// ---- bsg_pmv.cu: packed matrix x vector on the integer tensor pipe ----------------------------
+struct PmvPlan;  // opaque, owned by a view
+}  // namespace bsg
+
+struct bsg_view {
+  bsg_bed *h = nullptr;
+  int nr = 0, nc = 0;
+  int row_identity = 1, col_identity = 1;
+  int row_maxmult = 1, col_maxmult = 1;
+  int has_scaling = 0;       // center/scale given (else 0 / 1)
+  // device arrays (owned)
+  int *d_row = nullptr;      // [nr] 0-based rows (null if identity)
+  int *d_col = nullptr;      // [nc] 0-based cols (null if identity)
+  double *d_center = nullptr, *d_scale = nullptr;  // [nc] (null if !has_scaling)
+  // prodvec over copy B: distinct rows to compute and the gather map back to ind_row order
+  int *d_rows_unique = nullptr;  // [nru] sorted distinct rows (null if identity)
+  int *d_row_gather = nullptr;   // [nr] position of each requested row in d_rows_unique
+  int nru = 0;
+  // scratch owned by the view (so device-pointer calls are allocation free)
+  bsg::DevBuf s_vec0, s_vec1, s_vec2, s_q0, s_q1, s_dig1, s_dig2, s_part, s_scal, s_full;
+};

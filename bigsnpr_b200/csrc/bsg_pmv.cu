@@ -1,0 +1,886 @@
+// bsg_pmv.cu -- X.y and Xt.y over the packed genotypes: bed_pMatVec4 / bed_cpMatVec4
+// (src/bed-prod-vec.cpp:15-54, :59-97) re-designed for sm_100a.
+//
+// Why not one-thread-per-genotype: at 2 bits per genotype the HBM roofline is 4 genotypes per byte
+// (2.6e13 genotypes/s at the measured 6.57 TB/s), more than the SIMT pipes can issue as
+// extract + table lookup + DFMA (SURVEY.md section 7 "Hard parts").  So the per-genotype multiply-add is
+// moved to the integer tensor pipe and made EXACT:
+//
+//   * the vector is quantised once per call to 61-bit fixed point, Q_k = rint(y_k * 2^e) with
+//     |Q_k| < 2^60, and split into 8 signed base-256 digits (int8).  Digit s of every element is
+//     column s of an int8 "B" operand with N = 8.
+//   * the staged 2-bit code of a genotype is its value (0/1/2, 3 = missing), so masking a packed
+//     32-bit word with 0x03030303 / 0x30303030 (and the same after >> 2) yields four uint8 "A"
+//     fragments holding 16 genotypes with NO unpack arithmetic beyond 1 shift + 4 ANDs: the fields
+//     left in place at bit 4 are simply worth 16x and accumulate in a second accumulator.
+//   * mma.sync.m16n8k32.u8.s8.s32 accumulates sum_k code_k * digit_k exactly in int32; the 8 slices
+//     are recombined in fp64 only at the very end.  A second plane ([code == 3]) gives the sum of
+//     the vector over missing entries, which turns "NA -> 0 after centering" into algebra:
+//         sum_i (g-c)/s * y_i  over non-missing  =  (R - 3N - c (Y - N)) / s,
+//         R = sum code*y, N = sum [NA]*y, Y = sum y.
+//   * integer partial sums make the result independent of the work split and of the GPU count.
+//
+// Data movement: each CTA streams 256 lines x 128 B per stage with cp.async.bulk (UBLKCP) into a
+// 4-stage shared-memory ring (mbarrier full/empty), one producer warp, 8 consumer warps that read
+// their fragments with conflict-free LDS.128 (line pitch 144 B) straight into IMMA operands.
+#include <algorithm>
+#include <math.h>
+#include <string.h>
+
+#include "bsg_internal.cuh"
+
+namespace bsg {
+namespace pmv {
+
+constexpr int CW = 8;                 // consumer warps
+constexpr int GROUP = 256;            // lines per work item (32 per consumer warp)
+constexpr int SEG = 128;              // bytes per line per stage = 512 codes
+constexpr int PITCH = 144;            // smem line pitch: odd multiple of 16 B -> conflict-free LDS.128
+constexpr int CODES = 512;            // codes per line per stage
+constexpr int DIG = 4096;             // digit bytes per stage per plane (512 codes x 8 slices)
+constexpr int STAGES = 4;
+constexpr int GENO_BYTES = GROUP * PITCH;            // 36864
+constexpr int STAGE_BYTES = GENO_BYTES + 2 * DIG;    // 45056
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 128;
+constexpr int THREADS = (CW + 1) * 32;
+constexpr int MAX_CHUNKS_PER_ITEM = 512;  // 262144 codes: |acc16| <= 262144*48*128 < 2^31
+
+struct Args {
+  const uint8_t *P;
+  int64_t stride;
+  const int *lines;      // physical line per logical line (null = identity)
+  int nlines;
+  int nlines_pad;        // multiple of GROUP
+  int nchunks;           // 128-byte chunks per line
+  int chunks_per_split;
+  int ksplit;
+  const uint8_t *dig1;   // [nchunks][DIG]
+  const uint8_t *dig2;   // NA-plane digits (null = same as dig1)
+  const uint8_t *na_flags;  // per physical line (null = assume missing values anywhere)
+  int use_na;            // 0: matrix has no missing value, skip the NA plane
+  long long *part;       // [ksplit][nlines_pad][16]: 8 raw-plane slices, 8 NA-plane slices
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mma_u8s8(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                         uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
+// One 16-line sub-tile x one stage.  wA / wB: the 8 packed words (128 codes) of lines g and g+8 owned
+// by this lane; b[w][c]: digits of slice g for the 4 codes 4r+c (r = byte) of word w.
+template <bool NA>
+__device__ __forceinline__ void tile_stage(const uint32_t (&wA)[8], const uint32_t (&wB)[8], const uint4 (&b1)[8],
+                                           const uint4 (&b2)[8], int (&acc1)[4], int (&acc16)[4], int (&accn1)[4],
+                                           int (&accn16)[4]) {
+#pragma unroll
+  for (int w = 0; w < 8; w++) {
+    const uint32_t a = wA[w], bq = wB[w];
+    const uint32_t at = a >> 2, bt = bq >> 2;
+    // codes 4r (x1) and 4r+1 (x1) | codes 4r+2 (x16) and 4r+3 (x16)
+    mma_u8s8(acc1, a & 0x03030303u, bq & 0x03030303u, at & 0x03030303u, bt & 0x03030303u, b1[w].x, b1[w].y);
+    mma_u8s8(acc16, a & 0x30303030u, bq & 0x30303030u, at & 0x30303030u, bt & 0x30303030u, b1[w].z, b1[w].w);
+    if (NA) {
+      const uint32_t an = a & (a >> 1), bn = bq & (bq >> 1);      // bit 2p set iff code p == 3
+      const uint32_t ant = at & (at >> 1), bnt = bt & (bt >> 1);
+      mma_u8s8(accn1, an & 0x01010101u, bn & 0x01010101u, ant & 0x01010101u, bnt & 0x01010101u, b2[w].x, b2[w].y);
+      mma_u8s8(accn16, an & 0x10101010u, bn & 0x10101010u, ant & 0x10101010u, bnt & 0x10101010u, b2[w].z, b2[w].w);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(THREADS, 1) k_pmv(const Args a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;  // full[s] at +8s, empty[s] at +8(STAGES+s)
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(bar_base + 8 * s, 1);
+      mbar_init(bar_base + 8 * (STAGES + s), CW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int ngroups = a.nlines_pad / GROUP;
+  const int nitems = ngroups * a.ksplit;
+  const bool two_dig = a.use_na && a.dig2 != nullptr;
+  const uint32_t stage_tx = GROUP * SEG + DIG + (two_dig ? DIG : 0);
+
+  int stage = 0;
+  uint32_t phase = 0;
+
+  if (warp == CW) {
+    // ===================== producer warp: bulk copies global -> shared =====================
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      const int group = item / a.ksplit, ks = item - group * a.ksplit;
+      const int c0 = ks * a.chunks_per_split;
+      const int c1 = min(a.nchunks, c0 + a.chunks_per_split);
+      const uint8_t *src[8];
+#pragma unroll
+      for (int t = 0; t < 8; t++) {
+        int l = group * GROUP + lane * 8 + t;
+        l = min(l, a.nlines - 1);
+        const int phys = a.lines ? a.lines[l] : l;
+        src[t] = a.P + (int64_t)phys * a.stride;
+      }
+      for (int c = c0; c < c1; c++) {
+        const uint32_t full = bar_base + 8 * stage, empty = bar_base + 8 * (STAGES + stage);
+        mbar_wait(empty, phase ^ 1);
+        if (lane == 0) mbar_expect_tx(full, stage_tx);
+        __syncwarp();
+        const uint32_t dst = smem_base + stage * STAGE_BYTES;
+#pragma unroll
+        for (int t = 0; t < 8; t++)
+          bulk_g2s(dst + (lane * 8 + t) * PITCH, src[t] + (int64_t)c * SEG, SEG, full);
+        if (lane == 0) bulk_g2s(dst + GENO_BYTES, a.dig1 + (int64_t)c * DIG, DIG, full);
+        if (lane == 1 && two_dig) bulk_g2s(dst + GENO_BYTES + DIG, a.dig2 + (int64_t)c * DIG, DIG, full);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================== consumer warps: LDS.128 -> IMMA ================================
+    const int g = lane >> 2, q = lane & 3;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      const int group = item / a.ksplit, ks = item - group * a.ksplit;
+      const int c0 = ks * a.chunks_per_split;
+      const int c1 = min(a.nchunks, c0 + a.chunks_per_split);
+      // does any of this warp's 32 lines hold a missing value?  (warp-uniform)
+      bool tile_na = false;
+      if (a.use_na) {
+        if (a.na_flags) {
+          int l = min(group * GROUP + warp * 32 + lane, a.nlines - 1);
+          const int phys = a.lines ? a.lines[l] : l;
+          tile_na = __any_sync(0xffffffffu, a.na_flags[phys] != 0);
+        } else {
+          tile_na = true;
+        }
+      }
+      int acc1[2][4], acc16[2][4], accn1[2][4], accn16[2][4];
+#pragma unroll
+      for (int u = 0; u < 2; u++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) acc1[u][k] = acc16[u][k] = accn1[u][k] = accn16[u][k] = 0;
+
+      for (int c = c0; c < c1; c++) {
+        const uint32_t full = bar_base + 8 * stage, empty = bar_base + 8 * (STAGES + stage);
+        mbar_wait(full, phase);
+        const uint32_t sbase = smem_base + stage * STAGE_BYTES;
+        const uint32_t dbase = sbase + GENO_BYTES + (g * 4 + q) * 16;
+        uint4 b1[8], b2[8];
+#pragma unroll
+        for (int w = 0; w < 8; w++) b1[w] = lds128(dbase + w * 512);
+        if (tile_na) {
+          if (two_dig) {
+#pragma unroll
+            for (int w = 0; w < 8; w++) b2[w] = lds128(dbase + DIG + w * 512);
+          } else {
+#pragma unroll
+            for (int w = 0; w < 8; w++) b2[w] = b1[w];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          const uint32_t la = sbase + (warp * 32 + u * 16 + g) * PITCH + q * 32;
+          const uint32_t lb = la + 8 * PITCH;
+          uint4 x0 = lds128(la), x1 = lds128(la + 16), y0 = lds128(lb), y1 = lds128(lb + 16);
+          const uint32_t wA[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+          const uint32_t wB[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+          if (tile_na)
+            tile_stage<true>(wA, wB, b1, b2, acc1[u], acc16[u], accn1[u], accn16[u]);
+          else
+            tile_stage<false>(wA, wB, b1, b1, acc1[u], acc16[u], accn1[u], accn16[u]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      // ---- item epilogue: exact recombination of the x1 / x16 accumulators, 16 B stores ----
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+#pragma unroll
+        for (int hrow = 0; hrow < 2; hrow++) {
+          const int row = group * GROUP + warp * 32 + u * 16 + g + 8 * hrow;
+          long long *dst = a.part + ((int64_t)ks * a.nlines_pad + row) * 16 + 2 * q;
+          longlong2 v, vn;
+          v.x = (long long)acc1[u][2 * hrow] + (long long)(acc16[u][2 * hrow] >> 4);
+          v.y = (long long)acc1[u][2 * hrow + 1] + (long long)(acc16[u][2 * hrow + 1] >> 4);
+          vn.x = (long long)accn1[u][2 * hrow] + (long long)(accn16[u][2 * hrow] >> 4);
+          vn.y = (long long)accn1[u][2 * hrow + 1] + (long long)(accn16[u][2 * hrow + 1] >> 4);
+          *reinterpret_cast<longlong2 *>(dst) = v;
+          *reinterpret_cast<longlong2 *>(dst + 8) = vn;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// vector preparation: max |v| + finiteness, quantisation, digit layout, exact sums
+// ---------------------------------------------------------------------------------------------
+struct Scal {          // device-resident scalars of one call
+  double maxabs[2];    // [0] raw-plane vector, [1] NA-plane vector
+  int nonfinite;
+  int e[2];            // Q = rint(v * 2^e)
+  double Y;            // sum of the (scattered) vector, for Xt.y
+  double C;            // sum_k c_k z_k, for X.y
+  long long sum_hi, sum_lo;
+};
+
+// mode 0: v0 = x                      (Xt.y, identity scaling handled in finish)
+// mode 1: v0 = x / s, v1 = (c - 3) * x / s   (X.y with scaling)
+__device__ __forceinline__ void make_vals(int mode, const double *x, const double *center, const double *scale, int k,
+                                          double &v0, double &v1) {
+  if (mode == 0) {
+    v0 = x[k];
+    v1 = 0;
+  } else {
+    double z = x[k] / scale[k];
+    v0 = z;
+    v1 = (center[k] - 3.0) * z;
+  }
+}
+
+__global__ void k_scal_reset(Scal *sc) {
+  sc->maxabs[0] = sc->maxabs[1] = 0;
+  sc->nonfinite = 0;
+  sc->e[0] = sc->e[1] = 0;
+  sc->Y = 0;
+  sc->C = 0;
+  sc->sum_hi = sc->sum_lo = 0;
+}
+
+__global__ void k_maxabs(int mode, const double *__restrict__ x, const double *__restrict__ center,
+                         const double *__restrict__ scale, int len, Scal *sc) {
+  double m0 = 0, m1 = 0;
+  int bad = 0;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < len; k += gridDim.x * blockDim.x) {
+    double v0, v1;
+    make_vals(mode, x, center, scale, k, v0, v1);
+    if (!isfinite(v0) || !isfinite(v1)) bad = 1;
+    m0 = fmax(m0, fabs(v0));
+    m1 = fmax(m1, fabs(v1));
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    m0 = fmax(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+    m1 = fmax(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+    bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    // non-negative doubles order like their bit patterns
+    atomicMax(reinterpret_cast<unsigned long long *>(&sc->maxabs[0]), (unsigned long long)__double_as_longlong(m0));
+    atomicMax(reinterpret_cast<unsigned long long *>(&sc->maxabs[1]), (unsigned long long)__double_as_longlong(m1));
+    if (bad) atomicOr(&sc->nonfinite, 1);
+  }
+}
+
+// e = 60 - exponent(maxabs) - headroom_bits, so that |sum of <= 2^headroom quantised values| < 2^60
+__global__ void k_pick_exp(Scal *sc, int headroom_bits) {
+  for (int p = 0; p < 2; p++) {
+    double m = sc->maxabs[p];
+    int ex = 0;
+    if (m > 0 && isfinite(m)) {
+      frexp(m, &ex);
+      sc->e[p] = 60 - ex - headroom_bits;
+    } else {
+      sc->e[p] = 0;
+    }
+  }
+}
+
+// Q[idx ? idx[k] : k] (+)= rint(v * 2^e).  With idx the destination is pre-zeroed and duplicates add
+// up in integers (order independent) -- the scatter side of `ind.row` / `ind.col` multisets.
+__global__ void k_quantise(int mode, const double *__restrict__ x, const double *__restrict__ center,
+                           const double *__restrict__ scale, int len, const int *__restrict__ idx, const Scal *sc,
+                           long long *__restrict__ Q0, long long *__restrict__ Q1) {
+  const int e0 = sc->e[0], e1 = sc->e[1];
+  const bool bad = sc->nonfinite != 0;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < len; k += gridDim.x * blockDim.x) {
+    double v0, v1;
+    make_vals(mode, x, center, scale, k, v0, v1);
+    long long q0 = bad ? 0 : __double2ll_rn(scalbn(v0, e0));
+    long long q1 = (bad || !Q1) ? 0 : __double2ll_rn(scalbn(v1, e1));
+    if (idx) {
+      atomicAdd(reinterpret_cast<unsigned long long *>(Q0 + idx[k]), (unsigned long long)q0);
+      if (Q1) atomicAdd(reinterpret_cast<unsigned long long *>(Q1 + idx[k]), (unsigned long long)q1);
+    } else {
+      Q0[k] = q0;
+      if (Q1) Q1[k] = q1;
+    }
+  }
+}
+
+// digits: one thread per 16-byte unit (chunk, w, s, q) -> 16 int8 digits of slice s for the codes
+// t = 128 q + 16 w + 4 r + c of the chunk, stored at byte c*4 + r  (see tile_stage).
+__global__ void k_digits(const long long *__restrict__ Q, int len, int nchunks, uint8_t *__restrict__ dig) {
+  int64_t total = (int64_t)nchunks * 256;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    int chunk = (int)(t >> 8), unit = (int)(t & 255);
+    int q = unit & 3, s = (unit >> 2) & 7, w = unit >> 5;
+    uint32_t out[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        int64_t k = (int64_t)chunk * CODES + 128 * q + 16 * w + 4 * r + c;
+        long long v = k < len ? Q[k] : 0;
+        // signed base-256 digit s: peel s digits
+        int d = 0;
+        for (int i = 0; i <= s; i++) {
+          d = (int)(signed char)(v & 0xFF);
+          v = (v - d) >> 8;
+        }
+        out[c] |= (uint32_t)(d & 0xFF) << (8 * r);
+      }
+    }
+    reinterpret_cast<uint4 *>(dig)[t] = make_uint4(out[0], out[1], out[2], out[3]);
+  }
+}
+
+// exact integer sum of Q (split in 32-bit halves), then Y = sum * 2^-e     (single block)
+__global__ void k_sum_q(const long long *__restrict__ Q, int len, Scal *sc) {
+  __shared__ long long sh[64], sl[64];
+  long long hi = 0, lo = 0;
+  for (int k = threadIdx.x; k < len; k += blockDim.x) {
+    long long v = Q[k];
+    hi += v >> 32;
+    lo += (long long)(unsigned int)(v & 0xFFFFFFFFll);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    hi += __shfl_xor_sync(0xffffffffu, hi, o);
+    lo += __shfl_xor_sync(0xffffffffu, lo, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sh[threadIdx.x >> 5] = hi;
+    sl[threadIdx.x >> 5] = lo;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long H = 0, L = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) {
+      H += sh[w];
+      L += sl[w];
+    }
+    sc->sum_hi = H;
+    sc->sum_lo = L;
+    sc->Y = scalbn((double)H, 32 - sc->e[0]) + scalbn((double)L, -sc->e[0]);
+  }
+}
+
+// C = sum_k c_k * (x_k / s_k), fixed-shape tree (single block) -> deterministic
+__global__ void k_sum_cz(const double *__restrict__ x, const double *__restrict__ center,
+                         const double *__restrict__ scale, int len, Scal *sc) {
+  __shared__ double sh[32];
+  double acc = 0;
+  for (int k = threadIdx.x; k < len; k += blockDim.x) acc += center[k] * (x[k] / scale[k]);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += sh[w];
+    sc->C = t;
+  }
+}
+
+__device__ __forceinline__ double combine8(const long long *__restrict__ part, int64_t line, int plane, int ksplit,
+                                           int64_t nlines_pad, int e) {
+  double acc = 0;
+#pragma unroll
+  for (int s = 7; s >= 0; s--) {
+    long long v = 0;
+    for (int ks = 0; ks < ksplit; ks++) v += part[((int64_t)ks * nlines_pad + line) * 16 + plane * 8 + s];
+    acc += scalbn((double)v, 8 * s - e);
+  }
+  return acc;
+}
+
+// Xt.y:  out_j = ((R - 3N) - c_j (Y - N)) / s_j        (bedAccScaled semantics, src/bed-acc.h:98-111)
+__global__ void k_finish_cprod(const long long *__restrict__ part, int ksplit, int64_t nlines_pad, int nlines,
+                               const Scal *sc, const double *__restrict__ center, const double *__restrict__ scale,
+                               int use_na, double *__restrict__ out) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nlines) return;
+  if (sc->nonfinite) {
+    out[j] = nan("");
+    return;
+  }
+  const int e = sc->e[0];
+  double R = combine8(part, j, 0, ksplit, nlines_pad, e);
+  double N = use_na ? combine8(part, j, 1, ksplit, nlines_pad, e) : 0.0;
+  double G = R - 3.0 * N;
+  if (center) {
+    out[j] = (G - center[j] * (sc->Y - N)) / scale[j];
+  } else {
+    out[j] = G;
+  }
+}
+
+// X.y:  full_l = R + Nw - C   with Nw the NA-plane sum against w = (c - 3) z;  without scaling
+// full_l = R - 3 N.   out[i] = full[gather[i]].
+__global__ void k_finish_prod(const long long *__restrict__ part, int ksplit, int64_t nlines_pad, int nlines,
+                              const Scal *sc, int has_scaling, int use_na, double *__restrict__ full) {
+  int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= nlines) return;
+  if (sc->nonfinite) {
+    full[l] = nan("");
+    return;
+  }
+  double R = combine8(part, l, 0, ksplit, nlines_pad, sc->e[0]);
+  if (has_scaling) {
+    double Nw = use_na ? combine8(part, l, 1, ksplit, nlines_pad, sc->e[1]) : 0.0;
+    full[l] = (R + Nw) - sc->C;
+  } else {
+    double N = use_na ? combine8(part, l, 1, ksplit, nlines_pad, sc->e[0]) : 0.0;
+    full[l] = R - 3.0 * N;
+  }
+}
+
+__global__ void k_gather(const double *__restrict__ full, const int *__restrict__ idx, int len, double *__restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < len) out[i] = full[idx[i]];
+}
+
+// CUDA-event timing of k_pmv on the launching stream: a ring of event pairs, read back lazily
+constexpr int EV_POOL = 128;
+static cudaEvent_t g_ev0[EV_POOL], g_ev1[EV_POOL];
+static bool g_ev_ready = false;
+static bool g_timing = false;
+static int g_ev_n = 0;  // launches recorded since the last reset (ring overwrites beyond EV_POOL)
+
+static int launch_cap(int64_t work, int block, int cap) {
+  int64_t g = (work + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (int)g;
+}
+
+static int hb_bits(int maxmult) {
+  int b = 0;
+  while ((1 << b) < maxmult) b++;
+  return b;
+}
+
+// shared launcher of the tensor-pipe kernel + scratch sizing
+static int run_pmv(bsg_view *v, const uint8_t *P, int64_t stride, int L, const int *lines, int nlines,
+                   const uint8_t *dig1, const uint8_t *dig2, const uint8_t *na_flags, int use_na, Args *out_args,
+                   cudaStream_t s) {
+  Args a;
+  a.P = P;
+  a.stride = stride;
+  a.lines = lines;
+  a.nlines = nlines;
+  a.nlines_pad = (int)round_up(nlines, GROUP);
+  a.nchunks = (int)(round_up(((int64_t)L + 3) / 4, SEG) / SEG);
+  int ngroups = a.nlines_pad / GROUP;
+  int target_items = 24 * 148;
+  int ks = (target_items + ngroups - 1) / ngroups;
+  int ks_max = std::max(1, a.nchunks / 16);
+  int ks_min = (a.nchunks + MAX_CHUNKS_PER_ITEM - 1) / MAX_CHUNKS_PER_ITEM;
+  ks = std::min(ks, ks_max);
+  ks = std::max(ks, ks_min);
+  ks = std::max(ks, 1);
+  a.chunks_per_split = (a.nchunks + ks - 1) / ks;
+  a.ksplit = (a.nchunks + a.chunks_per_split - 1) / a.chunks_per_split;
+  a.dig1 = dig1;
+  a.dig2 = dig2;
+  a.na_flags = na_flags;
+  a.use_na = use_na;
+  BSG_TRY(v->s_part.ensure((size_t)a.ksplit * a.nlines_pad * 16 * sizeof(long long)));
+  a.part = v->s_part.as<long long>();
+  BSG_CUDA(cudaFuncSetAttribute(k_pmv, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, v->h->device);
+  int nitems = ngroups * a.ksplit;
+  int grid = std::min(nitems, nsm);
+  if (g_timing) cudaEventRecord(g_ev0[g_ev_n % EV_POOL], s);
+  k_pmv<<<grid, THREADS, SMEM_BYTES, s>>>(a);
+  if (g_timing) {
+    cudaEventRecord(g_ev1[g_ev_n % EV_POOL], s);
+    g_ev_n++;
+  }
+  count_launch();
+  BSG_CUDA(cudaGetLastError());
+  *out_args = a;
+  return BSG_OK;
+}
+
+}  // namespace pmv
+
+// =============================================================================================
+// views
+// =============================================================================================
+static int dev_copy(void **dst, const void *src, size_t bytes, cudaStream_t s) {
+  BSG_CUDA(cudaMalloc(dst, bytes ? bytes : 16));
+  if (bytes) BSG_CUDA(cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, s));
+  return BSG_OK;
+}
+
+static bool is_identity(const int *ind, int len, int limit) {
+  if (!ind) return true;
+  if (len != limit) return false;
+  for (int i = 0; i < len; i++)
+    if (ind[i] != i + 1) return false;
+  return true;
+}
+
+static int max_mult(std::vector<int> z) {
+  if (z.empty()) return 1;
+  std::sort(z.begin(), z.end());
+  int best = 1, run = 1;
+  for (size_t i = 1; i < z.size(); i++) {
+    run = (z[i] == z[i - 1]) ? run + 1 : 1;
+    best = std::max(best, run);
+  }
+  return best;
+}
+
+}  // namespace bsg
+
+using namespace bsg;
+
+extern "C" {
+
+int bsg_view_create(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, const double *center,
+                    const double *scale, bsg_view **out) {
+  if (!h || !out) return fail(BSG_ERR_ARG, "null argument");
+  *out = nullptr;
+  BSG_TRY(bind_device(h));
+  if (!ind_row) nr = h->n;
+  if (!ind_col) nc = h->m;
+  if (nr < 0 || nc < 0) return fail(BSG_ERR_ARG, "negative length");
+  if ((center == nullptr) != (scale == nullptr)) return fail(BSG_ERR_ARG, "center and scale must be given together");
+  bsg_view *v = new bsg_view();
+  v->h = h;
+  v->nr = nr;
+  v->nc = nc;
+  v->row_identity = is_identity(ind_row, nr, h->n);
+  v->col_identity = is_identity(ind_col, nc, h->m);
+  v->has_scaling = center != nullptr;
+  cudaStream_t s = h->stream;
+  int rc = BSG_OK;
+  std::vector<int> zr, zc, uniq, gat;
+  if (!v->row_identity) {
+    zr.resize(nr);
+    for (int i = 0; i < nr && !rc; i++) {
+      long long t = (long long)ind_row[i] - 1;
+      if (t < 0 || t >= h->n) rc = fail(BSG_ERR_BOUNDS, "Tested subscript out of bounds (row %d not in 1..%d).", ind_row[i], h->n);
+      zr[i] = (int)t;
+    }
+    if (!rc) {
+      v->row_maxmult = max_mult(zr);
+      uniq = zr;
+      std::sort(uniq.begin(), uniq.end());
+      uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+      gat.resize(nr);
+      for (int i = 0; i < nr; i++) gat[i] = (int)(std::lower_bound(uniq.begin(), uniq.end(), zr[i]) - uniq.begin());
+      v->nru = (int)uniq.size();
+      rc = dev_copy((void **)&v->d_row, zr.data(), (size_t)nr * sizeof(int), s);
+      if (!rc) rc = dev_copy((void **)&v->d_rows_unique, uniq.data(), uniq.size() * sizeof(int), s);
+      if (!rc) rc = dev_copy((void **)&v->d_row_gather, gat.data(), (size_t)nr * sizeof(int), s);
+    }
+  } else {
+    v->nru = h->n;
+  }
+  if (!rc && !v->col_identity) {
+    zc.resize(nc);
+    for (int j = 0; j < nc && !rc; j++) {
+      long long t = (long long)ind_col[j] - 1;
+      if (t < 0 || t >= h->m) rc = fail(BSG_ERR_BOUNDS, "Tested subscript out of bounds (column %d not in 1..%d).", ind_col[j], h->m);
+      zc[j] = (int)t;
+    }
+    if (!rc) {
+      v->col_maxmult = max_mult(zc);
+      rc = dev_copy((void **)&v->d_col, zc.data(), (size_t)nc * sizeof(int), s);
+    }
+  }
+  if (!rc && v->has_scaling) {
+    rc = dev_copy((void **)&v->d_center, center, (size_t)nc * sizeof(double), s);
+    if (!rc) rc = dev_copy((void **)&v->d_scale, scale, (size_t)nc * sizeof(double), s);
+  }
+  if (!rc) rc = v->s_scal.ensure(sizeof(pmv::Scal));
+  cudaError_t e = cudaStreamSynchronize(s);  // host vectors go out of scope
+  if (!rc && e != cudaSuccess) rc = cuda_fail(e, "view upload");
+  if (rc) {
+    bsg_view_destroy(v);
+    return rc;
+  }
+  *out = v;
+  return BSG_OK;
+}
+
+void bsg_view_destroy(bsg_view *v) {
+  if (!v) return;
+  cudaSetDevice(v->h->device);
+  cudaStreamSynchronize(v->h->stream);
+  void *ptrs[] = {v->d_row, v->d_col, v->d_center, v->d_scale, v->d_rows_unique, v->d_row_gather};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  DevBuf *bufs[] = {&v->s_vec0, &v->s_vec1, &v->s_vec2, &v->s_q0, &v->s_q1, &v->s_dig1,
+                    &v->s_dig2, &v->s_part, &v->s_scal, &v->s_full};
+  for (DevBuf *b : bufs) b->release();
+  delete v;
+}
+
+// t(X~) x : lines = SNP columns of copy A, contraction over samples
+int bsg_view_cprodvec_dev(bsg_view *v, const double *x_dev, double *out_dev, void *stream) {
+  if (!v || !x_dev || !out_dev) return fail(BSG_ERR_ARG, "null argument");
+  bsg_bed *h = v->h;
+  BSG_TRY(bind_device(h));
+  cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+  if (v->nc == 0) return BSG_OK;
+  using namespace pmv;
+  Scal *sc = v->s_scal.as<Scal>();
+  const int n = h->n;
+  int nchunks = (int)(h->strideA / SEG);
+  BSG_TRY(v->s_q0.ensure((size_t)n * sizeof(long long)));
+  BSG_TRY(v->s_dig1.ensure((size_t)nchunks * DIG));
+  long long *Q = v->s_q0.as<long long>();
+  k_scal_reset<<<1, 1, 0, s>>>(sc);
+  k_maxabs<<<launch_cap(v->nr, 256, 592), 256, 0, s>>>(0, x_dev, nullptr, nullptr, v->nr, sc);
+  k_pick_exp<<<1, 1, 0, s>>>(sc, hb_bits(v->row_maxmult));
+  if (!v->row_identity) BSG_CUDA(cudaMemsetAsync(Q, 0, (size_t)n * sizeof(long long), s));
+  k_quantise<<<launch_cap(v->nr, 256, 592), 256, 0, s>>>(0, x_dev, nullptr, nullptr, v->nr, v->d_row, sc, Q, nullptr);
+  k_digits<<<launch_cap((int64_t)nchunks * 256, 256, 1184), 256, 0, s>>>(Q, n, nchunks, v->s_dig1.as<uint8_t>());
+  k_sum_q<<<1, 1024, 0, s>>>(Q, n, sc);
+  count_launch(6);
+  Args a;
+  BSG_TRY(run_pmv(v, h->A, h->strideA, n, v->d_col, v->nc, v->s_dig1.as<uint8_t>(), nullptr, h->naA, h->has_na, &a, s));
+  k_finish_cprod<<<(v->nc + 255) / 256, 256, 0, s>>>(a.part, a.ksplit, a.nlines_pad, v->nc, sc, v->d_center, v->d_scale,
+                                                      h->has_na, out_dev);
+  count_launch();
+  BSG_CUDA(cudaGetLastError());
+  return BSG_OK;
+}
+
+// X~ x : lines = samples of copy B, contraction over SNP columns
+int bsg_view_prodvec_dev(bsg_view *v, const double *x_dev, double *out_dev, void *stream) {
+  if (!v || !x_dev || !out_dev) return fail(BSG_ERR_ARG, "null argument");
+  bsg_bed *h = v->h;
+  BSG_TRY(bind_device(h));
+  cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+  if (v->nr == 0) return BSG_OK;
+  if (!h->B) {
+    // no sample-major copy resident: generic accessor kernel over copy A
+    return simple_prodvec(h, v->d_row, v->nr, v->d_col, v->nc, v->d_center, v->d_scale, x_dev, out_dev, s);
+  }
+  using namespace pmv;
+  Scal *sc = v->s_scal.as<Scal>();
+  const int m = h->m;
+  int nchunks = (int)(h->strideB / SEG);
+  const int mode = v->has_scaling ? 1 : 0;
+  const bool two = v->has_scaling && h->has_na;
+  BSG_TRY(v->s_q0.ensure((size_t)m * sizeof(long long)));
+  BSG_TRY(v->s_dig1.ensure((size_t)nchunks * DIG));
+  if (two) {
+    BSG_TRY(v->s_q1.ensure((size_t)m * sizeof(long long)));
+    BSG_TRY(v->s_dig2.ensure((size_t)nchunks * DIG));
+  }
+  long long *Q0 = v->s_q0.as<long long>();
+  long long *Q1 = two ? v->s_q1.as<long long>() : nullptr;
+  k_scal_reset<<<1, 1, 0, s>>>(sc);
+  k_maxabs<<<launch_cap(v->nc, 256, 592), 256, 0, s>>>(mode, x_dev, v->d_center, v->d_scale, v->nc, sc);
+  k_pick_exp<<<1, 1, 0, s>>>(sc, hb_bits(v->col_maxmult));
+  if (!v->col_identity) {
+    BSG_CUDA(cudaMemsetAsync(Q0, 0, (size_t)m * sizeof(long long), s));
+    if (Q1) BSG_CUDA(cudaMemsetAsync(Q1, 0, (size_t)m * sizeof(long long), s));
+  }
+  k_quantise<<<launch_cap(v->nc, 256, 592), 256, 0, s>>>(mode, x_dev, v->d_center, v->d_scale, v->nc, v->d_col, sc, Q0, Q1);
+  k_digits<<<launch_cap((int64_t)nchunks * 256, 256, 1184), 256, 0, s>>>(Q0, m, nchunks, v->s_dig1.as<uint8_t>());
+  if (Q1) k_digits<<<launch_cap((int64_t)nchunks * 256, 256, 1184), 256, 0, s>>>(Q1, m, nchunks, v->s_dig2.as<uint8_t>());
+  if (v->has_scaling) k_sum_cz<<<1, 1024, 0, s>>>(x_dev, v->d_center, v->d_scale, v->nc, sc);
+  count_launch(5 + (Q1 ? 1 : 0) + (v->has_scaling ? 1 : 0));
+  Args a;
+  const int nlines = v->row_identity ? h->n : v->nru;
+  BSG_TRY(run_pmv(v, h->B, h->strideB, m, v->d_rows_unique, nlines, v->s_dig1.as<uint8_t>(),
+                  two ? v->s_dig2.as<uint8_t>() : nullptr, h->naB, h->has_na, &a, s));
+  double *full = out_dev;
+  if (!v->row_identity) {
+    BSG_TRY(v->s_full.ensure((size_t)nlines * sizeof(double)));
+    full = v->s_full.as<double>();
+  }
+  k_finish_prod<<<(nlines + 255) / 256, 256, 0, s>>>(a.part, a.ksplit, a.nlines_pad, nlines, sc, v->has_scaling,
+                                                     h->has_na, full);
+  count_launch();
+  if (!v->row_identity) {
+    k_gather<<<(v->nr + 255) / 256, 256, 0, s>>>(full, v->d_row_gather, v->nr, out_dev);
+    count_launch();
+  }
+  BSG_CUDA(cudaGetLastError());
+  return BSG_OK;
+}
+
+// host-vector front ends: H2D of x, the product, D2H of the result; non-finite input falls back to the
+// accessor kernel, which propagates Inf / NaN exactly like the reference's table arithmetic.
+static int view_host_call(bsg_view *v, const double *x, double *out, bool cprod) {
+  if (!v || !x || !out) return fail(BSG_ERR_ARG, "null argument");
+  bsg_bed *h = v->h;
+  BSG_TRY(bind_device(h));
+  cudaStream_t s = h->stream;
+  const int nin = cprod ? v->nr : v->nc, nout = cprod ? v->nc : v->nr;
+  BSG_TRY(v->s_vec0.ensure((size_t)std::max(nin, 1) * sizeof(double)));
+  BSG_TRY(v->s_vec1.ensure((size_t)std::max(nout, 1) * sizeof(double)));
+  double *dx = v->s_vec0.as<double>(), *dout = v->s_vec1.as<double>();
+  BSG_CUDA(cudaMemcpyAsync(dx, x, (size_t)nin * sizeof(double), cudaMemcpyHostToDevice, s));
+  BSG_TRY(cprod ? bsg_view_cprodvec_dev(v, dx, dout, s) : bsg_view_prodvec_dev(v, dx, dout, s));
+  int bad = 0;
+  const bool fast = cprod || h->B != nullptr;
+  if (fast && nout > 0)
+    BSG_CUDA(cudaMemcpyAsync(&bad, &v->s_scal.as<pmv::Scal>()->nonfinite, sizeof(int), cudaMemcpyDeviceToHost, s));
+  BSG_CUDA(cudaMemcpyAsync(out, dout, (size_t)nout * sizeof(double), cudaMemcpyDeviceToHost, s));
+  BSG_CUDA(cudaStreamSynchronize(s));
+  if (bad) {
+    BSG_TRY(cprod ? simple_cprodvec(h, v->d_row, v->nr, v->d_col, v->nc, v->d_center, v->d_scale, dx, dout, s)
+                  : simple_prodvec(h, v->d_row, v->nr, v->d_col, v->nc, v->d_center, v->d_scale, dx, dout, s));
+    BSG_CUDA(cudaMemcpyAsync(out, dout, (size_t)nout * sizeof(double), cudaMemcpyDeviceToHost, s));
+    BSG_CUDA(cudaStreamSynchronize(s));
+  }
+  return BSG_OK;
+}
+
+int bsg_view_prodvec(bsg_view *v, const double *x, double *out) { return view_host_call(v, x, out, false); }
+int bsg_view_cprodvec(bsg_view *v, const double *x, double *out) { return view_host_call(v, x, out, true); }
+
+// The 9-argument drop-in calls (the .Call twins).  The reference rebuilds its accessor on every call
+// (src/bed-prod-vec.cpp:22-23); here the accessor state lives in a view cached on the handle: it is
+// reused while the index vectors are unchanged (compared by content), and only center / scale / x are
+// re-uploaded, so a Lanczos loop calling through the old interface does no per-call allocation.
+static int cached_view(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, const double *center,
+                       const double *scale, bsg_view **out) {
+  if (!h) return fail(BSG_ERR_ARG, "null handle");
+  if (!ind_row) nr = h->n;
+  if (!ind_col) nc = h->m;
+  if (nr < 0 || nc < 0) return fail(BSG_ERR_ARG, "negative length");
+  if ((center == nullptr) != (scale == nullptr)) return fail(BSG_ERR_ARG, "center and scale must be given together");
+  bool hit = h->cv != nullptr && h->cv->nr == nr && h->cv->nc == nc && (h->cv->has_scaling != 0) == (center != nullptr);
+  if (hit) {
+    hit = (ind_row == nullptr) == h->cv_row.empty() || (ind_row && (int)h->cv_row.size() == nr);
+    if (hit && ind_row) hit = (int)h->cv_row.size() == nr && memcmp(h->cv_row.data(), ind_row, (size_t)nr * sizeof(int)) == 0;
+    if (hit && !ind_row) hit = h->cv_row.empty();
+    if (hit && ind_col) hit = (int)h->cv_col.size() == nc && memcmp(h->cv_col.data(), ind_col, (size_t)nc * sizeof(int)) == 0;
+    if (hit && !ind_col) hit = h->cv_col.empty();
+  }
+  if (!hit) {
+    if (h->cv) bsg_view_destroy(h->cv);
+    h->cv = nullptr;
+    bsg_view *v = nullptr;
+    BSG_TRY(bsg_view_create(h, ind_row, nr, ind_col, nc, center, scale, &v));
+    h->cv = v;
+    h->cv_row.assign(ind_row ? ind_row : nullptr, ind_row ? ind_row + nr : nullptr);
+    h->cv_col.assign(ind_col ? ind_col : nullptr, ind_col ? ind_col + nc : nullptr);
+  } else if (center) {
+    BSG_TRY(bind_device(h));
+    BSG_CUDA(cudaMemcpyAsync(h->cv->d_center, center, (size_t)nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    BSG_CUDA(cudaMemcpyAsync(h->cv->d_scale, scale, (size_t)nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  }
+  *out = h->cv;
+  return BSG_OK;
+}
+
+int bsg_prodvec(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, const double *center,
+                const double *scale, const double *x, double *out) {
+  bsg_view *v = nullptr;
+  BSG_TRY(cached_view(h, ind_row, nr, ind_col, nc, center, scale, &v));
+  return bsg_view_prodvec(v, x, out);
+}
+
+int bsg_cprodvec(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, const double *center,
+                 const double *scale, const double *x, double *out) {
+  bsg_view *v = nullptr;
+  BSG_TRY(cached_view(h, ind_row, nr, ind_col, nc, center, scale, &v));
+  return bsg_view_cprodvec(v, x, out);
+}
+
+double bsg_last_kernel_ms(void) {
+  using namespace pmv;
+  if (!g_ev_ready || g_ev_n == 0) return 0.0;
+  float ms = 0;
+  int k = (g_ev_n - 1) % EV_POOL;
+  if (cudaEventElapsedTime(&ms, g_ev0[k], g_ev1[k]) != cudaSuccess) {
+    cudaGetLastError();
+    return 0.0;
+  }
+  return (double)ms;
+}
+
+// enable (and reset) / disable CUDA-event timing of the tensor-pipe kernel; events are recorded on the
+// launching stream around every k_pmv launch.
+int bsg_set_kernel_timing(int on) {
+  using namespace pmv;
+  if (on && !g_ev_ready) {
+    for (int k = 0; k < EV_POOL; k++) {
+      BSG_CUDA(cudaEventCreate(&g_ev0[k]));
+      BSG_CUDA(cudaEventCreate(&g_ev1[k]));
+    }
+    g_ev_ready = true;
+  }
+  g_timing = on != 0;
+  g_ev_n = 0;
+  return BSG_OK;
+}
+
+// launches timed since the last bsg_set_kernel_timing(1) and their summed device time (ms).  Call after
+// synchronising the stream(s).  At most the last 128 launches are kept.
+int bsg_kernel_time_stats(int *count, double *total_ms) {
+  using namespace pmv;
+  int n = g_ev_n < EV_POOL ? g_ev_n : EV_POOL;
+  double tot = 0;
+  for (int k = 0; k < n; k++) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, g_ev0[k], g_ev1[k]) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(BSG_ERR_CUDA, "kernel timing events not complete: synchronise first");
+    }
+    tot += ms;
+  }
+  if (count) *count = n;
+  if (total_ms) *total_ms = tot;
+  return BSG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,209 @@
+// bsg_stats.cu -- column / row statistics and dense decodes behind the C ABI.
+//   bed_colstats        src/bed-fun.cpp:9-46
+//   bed_col_counts_cpp  src/bed-fun.cpp:51-69     bed_row_counts_cpp  src/bed-fun.cpp:72-98
+//   read_bed            src/bed-mat-acc.cpp:8-26  read_bed_scaled     src/bed-mat-acc.cpp:30-49
+//   snp_colstats        src/colstats.cpp:8-35
+// All sums here are sums of small integers, so they are exact and order independent: results are
+// bit-identical to the reference's scalar loops.
+#include <vector>
+
+#include "bsg_internal.cuh"
+
+namespace bsg {
+
+__global__ void k_gather_counts(const int32_t *__restrict__ cnt, const int *__restrict__ idx, int len,
+                                int32_t *__restrict__ out) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= len) return;
+  int src = idx ? idx[j] : j;
+  reinterpret_cast<int4 *>(out)[j] = reinterpret_cast<const int4 *>(cnt)[src];
+}
+
+// sumX = c1 + 2 c2, xxSum = c1 + 4 c2, c = nr - c3, denoX = xxSum - sumX * sumX / c  (src/bed-fun.cpp:36-38)
+__global__ void k_colstats_from_counts(const int32_t *__restrict__ cnt, int len, int nr, double *__restrict__ sumX,
+                                       double *__restrict__ denoX, int *__restrict__ nona, int *__restrict__ n_bad) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  int bad = 0;
+  if (j < len) {
+    int c1 = cnt[4 * j + 1], c2 = cnt[4 * j + 2], c3 = cnt[4 * j + 3];
+    double xSum = (double)c1 + 2.0 * (double)c2;
+    double xxSum = (double)c1 + 4.0 * (double)c2;
+    int c = nr - c3;
+    sumX[j] = xSum;
+    denoX[j] = xxSum - xSum * xSum / c;
+    nona[j] = c;
+    bad = (2 * (long long)c < nr);
+  }
+  unsigned b = __ballot_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(n_bad, __popc(b));
+}
+
+// FBM twin, no NA handling (src/colstats.cpp:24-31): x = code256[byte]; NA codes poison the sums like in R
+__global__ void k_snp_colstats_from_counts(const int32_t *__restrict__ cnt, int len, int nr, double *__restrict__ sumX,
+                                           double *__restrict__ denoX) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= len) return;
+  int c1 = cnt[4 * j + 1], c2 = cnt[4 * j + 2], c3 = cnt[4 * j + 3];
+  double xSum = (double)c1 + 2.0 * (double)c2;
+  double xxSum = (double)c1 + 4.0 * (double)c2;
+  if (c3 > 0) xSum = xxSum = nan("");
+  sumX[j] = xSum;
+  denoX[j] = xxSum - xSum * xSum / nr;
+}
+
+static bool host_identity(const int *ind, int len, int limit) {
+  if (!ind) return true;
+  if (len != limit) return false;
+  for (int i = 0; i < len; i++)
+    if (ind[i] != i + 1) return false;
+  return true;
+}
+
+// counts for (ind_row, ind_col) into d_out4 [4 x nc]; uses the counts cached at staging when all rows are taken
+static int col_counts_dev(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, int32_t **d_out) {
+  cudaStream_t s = h->stream;
+  const int *d_row = nullptr, *d_col = nullptr;
+  BSG_TRY(upload_index(h, ind_col, nc, h->m, h->w_idx_col, &d_col));
+  BSG_TRY(h->w_tmp0.ensure((size_t)(nc > 0 ? nc : 1) * 4 * sizeof(int32_t)));
+  int32_t *out = h->w_tmp0.as<int32_t>();
+  if (host_identity(ind_row, nr, h->n)) {
+    if (nc > 0) {
+      k_gather_counts<<<(nc + 255) / 256, 256, 0, s>>>(h->cntA, d_col, nc, out);
+      count_launch();
+    }
+  } else {
+    BSG_TRY(upload_index(h, ind_row, nr, h->n, h->w_idx_row, &d_row));
+    BSG_TRY(counts_cols(h, d_row, nr, d_col, nc, out, s));
+  }
+  BSG_CUDA(cudaGetLastError());
+  *d_out = out;
+  return BSG_OK;
+}
+
+}  // namespace bsg
+
+using namespace bsg;
+
+#define FIX_DIMS()                         \
+  if (!h) return fail(BSG_ERR_ARG, "null handle"); \
+  BSG_TRY(bind_device(h));                 \
+  if (!ind_row) nr = h->n;                 \
+  if (!ind_col) nc = h->m;                 \
+  if (nr < 0 || nc < 0) return fail(BSG_ERR_ARG, "negative length");
+
+extern "C" {
+
+int bsg_col_counts(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, int *out) {
+  FIX_DIMS();
+  int32_t *d = nullptr;
+  BSG_TRY(col_counts_dev(h, ind_row, nr, ind_col, nc, &d));
+  BSG_CUDA(cudaMemcpyAsync(out, d, (size_t)nc * 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  BSG_CUDA(cudaStreamSynchronize(h->stream));
+  return BSG_OK;
+}
+
+int bsg_row_counts(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, int *out) {
+  FIX_DIMS();
+  cudaStream_t s = h->stream;
+  const int *d_row = nullptr, *d_col = nullptr;
+  BSG_TRY(upload_index(h, ind_row, nr, h->n, h->w_idx_row, &d_row));
+  BSG_TRY(h->w_tmp0.ensure((size_t)(nr > 0 ? nr : 1) * 4 * sizeof(int32_t)));
+  int32_t *d = h->w_tmp0.as<int32_t>();
+  if (host_identity(ind_col, nc, h->m) && h->cntB) {
+    if (nr > 0) {
+      k_gather_counts<<<(nr + 255) / 256, 256, 0, s>>>(h->cntB, d_row, nr, d);
+      count_launch();
+    }
+  } else {
+    BSG_TRY(upload_index(h, ind_col, nc, h->m, h->w_idx_col, &d_col));
+    BSG_TRY(counts_rows(h, d_row, nr, d_col, nc, d, s));
+  }
+  BSG_CUDA(cudaMemcpyAsync(out, d, (size_t)nr * 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  BSG_CUDA(cudaStreamSynchronize(s));
+  return BSG_OK;
+}
+
+int bsg_colstats(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, double *sumX, double *denoX,
+                 int *nb_nona_col, int *n_bad) {
+  FIX_DIMS();
+  cudaStream_t s = h->stream;
+  int32_t *d = nullptr;
+  BSG_TRY(col_counts_dev(h, ind_row, nr, ind_col, nc, &d));
+  size_t nn = (size_t)(nc > 0 ? nc : 1);
+  BSG_TRY(h->w_tmp1.ensure(nn * sizeof(double)));
+  BSG_TRY(h->w_tmp2.ensure(nn * sizeof(double)));
+  BSG_TRY(h->w_tmp3.ensure(nn * sizeof(int) + 16));
+  int *d_nona = h->w_tmp3.as<int>();
+  int *d_bad = d_nona + nn;
+  BSG_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), s));
+  if (nc > 0) {
+    k_colstats_from_counts<<<(nc + 255) / 256, 256, 0, s>>>(d, nc, nr, h->w_tmp1.as<double>(), h->w_tmp2.as<double>(),
+                                                          d_nona, d_bad);
+    count_launch();
+  }
+  int bad = 0;
+  BSG_CUDA(cudaMemcpyAsync(sumX, h->w_tmp1.p, (size_t)nc * sizeof(double), cudaMemcpyDeviceToHost, s));
+  BSG_CUDA(cudaMemcpyAsync(denoX, h->w_tmp2.p, (size_t)nc * sizeof(double), cudaMemcpyDeviceToHost, s));
+  BSG_CUDA(cudaMemcpyAsync(nb_nona_col, d_nona, (size_t)nc * sizeof(int), cudaMemcpyDeviceToHost, s));
+  BSG_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, s));
+  BSG_CUDA(cudaStreamSynchronize(s));
+  if (n_bad) *n_bad = bad;
+  return BSG_OK;
+}
+
+int bsg_snp_colstats(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, double *sumX, double *denoX) {
+  FIX_DIMS();
+  cudaStream_t s = h->stream;
+  int32_t *d = nullptr;
+  BSG_TRY(col_counts_dev(h, ind_row, nr, ind_col, nc, &d));
+  size_t nn = (size_t)(nc > 0 ? nc : 1);
+  BSG_TRY(h->w_tmp1.ensure(nn * sizeof(double)));
+  BSG_TRY(h->w_tmp2.ensure(nn * sizeof(double)));
+  if (nc > 0) {
+    k_snp_colstats_from_counts<<<(nc + 255) / 256, 256, 0, s>>>(d, nc, nr, h->w_tmp1.as<double>(),
+                                                              h->w_tmp2.as<double>());
+    count_launch();
+  }
+  BSG_CUDA(cudaMemcpyAsync(sumX, h->w_tmp1.p, (size_t)nc * sizeof(double), cudaMemcpyDeviceToHost, s));
+  BSG_CUDA(cudaMemcpyAsync(denoX, h->w_tmp2.p, (size_t)nc * sizeof(double), cudaMemcpyDeviceToHost, s));
+  BSG_CUDA(cudaStreamSynchronize(s));
+  return BSG_OK;
+}
+
+int bsg_read_bed(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, int na_val, int *out) {
+  FIX_DIMS();
+  cudaStream_t s = h->stream;
+  const int *d_row = nullptr, *d_col = nullptr;
+  BSG_TRY(upload_index(h, ind_row, nr, h->n, h->w_idx_row, &d_row));
+  BSG_TRY(upload_index(h, ind_col, nc, h->m, h->w_idx_col, &d_col));
+  size_t tot = (size_t)nr * nc;
+  BSG_TRY(h->w_out.ensure((tot ? tot : 1) * sizeof(int)));
+  BSG_TRY(read_dense(h, d_row, nr, d_col, nc, na_val, h->w_out.as<int>(), s));
+  BSG_CUDA(cudaMemcpyAsync(out, h->w_out.p, tot * sizeof(int), cudaMemcpyDeviceToHost, s));
+  BSG_CUDA(cudaStreamSynchronize(s));
+  return BSG_OK;
+}
+
+int bsg_read_bed_scaled(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, const double *center,
+                        const double *scale, double *out) {
+  FIX_DIMS();
+  if (!center || !scale) return fail(BSG_ERR_DIM, "Incompatibility between dimensions.");
+  cudaStream_t s = h->stream;
+  const int *d_row = nullptr, *d_col = nullptr;
+  BSG_TRY(upload_index(h, ind_row, nr, h->n, h->w_idx_row, &d_row));
+  BSG_TRY(upload_index(h, ind_col, nc, h->m, h->w_idx_col, &d_col));
+  size_t nn = (size_t)(nc > 0 ? nc : 1);
+  BSG_TRY(h->w_center.ensure(nn * sizeof(double)));
+  BSG_TRY(h->w_scale.ensure(nn * sizeof(double)));
+  BSG_CUDA(cudaMemcpyAsync(h->w_center.p, center, (size_t)nc * sizeof(double), cudaMemcpyHostToDevice, s));
+  BSG_CUDA(cudaMemcpyAsync(h->w_scale.p, scale, (size_t)nc * sizeof(double), cudaMemcpyHostToDevice, s));
+  size_t tot = (size_t)nr * nc;
+  BSG_TRY(h->w_out.ensure((tot ? tot : 1) * sizeof(double)));
+  BSG_TRY(read_dense_scaled(h, d_row, nr, d_col, nc, h->w_center.as<double>(), h->w_scale.as<double>(),
+                            h->w_out.as<double>(), s));
+  BSG_CUDA(cudaMemcpyAsync(out, h->w_out.p, tot * sizeof(double), cudaMemcpyDeviceToHost, s));
+  BSG_CUDA(cudaStreamSynchronize(s));
+  return BSG_OK;
+}
+
+}  // extern "C"

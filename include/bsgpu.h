@@ -1,0 +1,160 @@
+/*
+ * bsgpu.h -- C ABI of libbsgpu, the B200 (sm_100a) engine for bigsnpr's packed-genotype hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no R / torch types.  Every entry point
+ * replaces one `.Call` target of privefl/bigsnpr 1.12.21 (file:line under /root/reference cited per
+ * function); the R-side shim that binds them under the original `_bigsnpr_*` names is r_shim/ and
+ * is documented in INTEGRATION.md.
+ *
+ * Conventions (kept from the reference so the shim is a pass-through):
+ *   - ind_row / ind_col are 1-based int32 (R integer vectors); duplicates and any order are allowed
+ *     (src/bed-acc.h:64-65).  NULL means "all rows" / "all columns" (rows_along / cols_along).
+ *   - matrices are column-major; vectors are double (REALSXP) or int32 (INTSXP).
+ *   - all pointers are HOST pointers unless the name ends in _dev.
+ *   - every function returns 0 on success, else a BSG_ERR_* code; bsg_last_error() returns the message
+ *     (the text the reference raises, e.g. "Incompatibility between dimensions.").
+ *   - `ncores` of the reference is accepted by the shim and ignored: the GPU path has no thread knob.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     BSG_ERR_CUDA.
+ */
+#ifndef BSGPU_H
+#define BSGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSG_OK 0
+#define BSG_ERR_DIM 1     /* "Incompatibility between dimensions."  src/bed-acc.h:95-96 */
+#define BSG_ERR_BOUNDS 2  /* subscript out of bounds                  src/bed-acc.h:64-65 */
+#define BSG_ERR_MAGIC 3   /* "File is not a binary PED file."         src/bed-acc-xptr.cpp:21-22 */
+#define BSG_ERR_MODE 4    /* "Variant-major is the only mode supported."  src/bed-acc-xptr.cpp:29-30 */
+#define BSG_ERR_SIZE 5    /* "n or p does not match the dimensions of the file."  :33-34 */
+#define BSG_ERR_IO 6      /* "Error when mapping file"                 src/bed-acc-xptr.cpp:19 */
+#define BSG_ERR_ALLOC 7
+#define BSG_ERR_CUDA 8
+#define BSG_ERR_ARG 9
+#define BSG_ERR_TYPE 10   /* "Unknown object type."                    src/corr.cpp:124 */
+
+/* layouts kept resident in HBM (bit mask) */
+#define BSG_LAYOUT_SNP_MAJOR 1    /* variant-major, the .bed orientation: serves Xt.y, stats, LD, decode */
+#define BSG_LAYOUT_SAMPLE_MAJOR 2 /* transposed copy: serves X.y at the same speed as Xt.y */
+#define BSG_LAYOUT_AUTO 0         /* both when they fit in free HBM, else SNP-major only */
+
+typedef struct bsg_bed bsg_bed;   /* replaces class bed + XPtr<bed>: src/bed-acc.h:18-48, src/bed-acc-xptr.cpp:40-55 */
+typedef struct bsg_view bsg_view; /* replaces bedAccScaled: (ind_row, ind_col, center, scale) resident on device, src/bed-acc.h:86-115 */
+
+const char *bsg_last_error(void);
+int bsg_version(void);
+int bsg_device_count(void);
+
+/* ---- handles ------------------------------------------------------------------------------ */
+/* bedXPtr(path, n, p): src/bed-acc-xptr.cpp:14-55.  Validates the header and size exactly as the
+ * reference, then stages the packed bytes to HBM once (columns [col_begin, col_end), 0-based; pass
+ * 0, m for the whole file -- the range is how SNP columns are sharded across GPUs / ranks). */
+int bsg_open_bed(const char *path, int n, int m, int col_begin, int col_end, int device, int layouts,
+                 bsg_bed **out);
+/* same, from packed bytes in host memory (m * ceil(n/4) bytes, .bed bit layout, no header) */
+int bsg_open_packed(const uint8_t *packed, int n, int m, int device, int layouts, bsg_bed **out);
+/* synthetic .bed generated on the device: per-SNP maf ~ U(0.02,0.5),
+ * g ~ Binomial(2, maf), missing with probability na_rate; counter-based RNG keyed by (seed, global
+ * column = col_offset + j), so column shards of one matrix are reproducible on any rank. */
+int bsg_open_synth(int n, int m, uint64_t seed, double na_rate, int64_t col_offset, int device,
+                   int layouts, bsg_bed **out);
+/* FBM.code256 (bigstatsr, R/bigSNP-class.R:7,13): n x m bytes column-major + 256 doubles.  Codes
+ * that round to 0/1/2/NA are repacked to 2 bits at staging and share every kernel (snp_* twins:
+ * src/colstats.cpp:8-35, src/corr.cpp:113-118, src/ld-scores.cpp:93-96). */
+int bsg_open_fbm256(const uint8_t *bytes, int n, int m, const double *code256, int device, int layouts,
+                    bsg_bed **out);
+void bsg_close(bsg_bed *h);
+int bsg_nrow(const bsg_bed *h);
+int bsg_ncol(const bsg_bed *h);
+int bsg_layouts(const bsg_bed *h);
+int bsg_has_na(const bsg_bed *h);
+/* bytes of packed genotypes one full pass reads (ceil(n/4) * m): the roofline numerator */
+int64_t bsg_packed_bytes(const bsg_bed *h);
+/* copy the staged matrix back in .bed bit layout (m * ceil(n/4) bytes): round-trip check */
+int bsg_export_packed(const bsg_bed *h, uint8_t *out);
+
+/* ---- X.y and Xt.y ---------------------------------------------------------------------------- */
+/* bed_pMatVec4: src/bed-prod-vec.cpp:15-54.  out[nr] = X~[ind_row, ind_col] %*% x[nc] */
+int bsg_prodvec(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc,
+                const double *center, const double *scale, const double *x, double *out);
+/* bed_cpMatVec4: src/bed-prod-vec.cpp:59-97.  out[nc] = t(X~[ind_row, ind_col]) %*% x[nr] */
+int bsg_cprodvec(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc,
+                 const double *center, const double *scale, const double *x, double *out);
+
+/* views: the accessor state of bedAccScaled kept on the device across calls (what big_randomSVD's
+ * closures re-create on every operator call in the reference, R/autoSVD.R:216-218) */
+int bsg_view_create(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc,
+                    const double *center, const double *scale, bsg_view **out);
+void bsg_view_destroy(bsg_view *v);
+int bsg_view_prodvec(bsg_view *v, const double *x, double *out);   /* host vectors */
+int bsg_view_cprodvec(bsg_view *v, const double *x, double *out);  /* host vectors */
+/* device-resident vectors, enqueued on `stream` (a cudaStream_t; NULL = default stream); no sync */
+int bsg_view_prodvec_dev(bsg_view *v, const double *x_dev, double *out_dev, void *stream);
+int bsg_view_cprodvec_dev(bsg_view *v, const double *x_dev, double *out_dev, void *stream);
+
+/* ---- column / row statistics ------------------------------------------------------------------ */
+/* bed_colstats: src/bed-fun.cpp:9-46.  n_bad = count behind the ">50% missing values" warning */
+int bsg_colstats(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, double *sumX,
+                 double *denoX, int *nb_nona_col, int *n_bad);
+/* bed_col_counts_cpp / bed_row_counts_cpp: src/bed-fun.cpp:51-69, :72-98.  out is 4 x nc (4 x nr) */
+int bsg_col_counts(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, int *out);
+int bsg_row_counts(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, int *out);
+/* snp_colstats: src/colstats.cpp:8-35 (FBM.code256 handles; NA handling as the reference: none) */
+int bsg_snp_colstats(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, double *sumX,
+                     double *denoX);
+
+/* ---- dense decode ------------------------------------------------------------------------------ */
+/* read_bed: src/bed-mat-acc.cpp:8-26 (NA -> na_val; R passes NA_INTEGER) */
+int bsg_read_bed(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, int na_val,
+                 int *out);
+/* read_bed_scaled: src/bed-mat-acc.cpp:30-49 */
+int bsg_read_bed_scaled(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc,
+                        const double *center, const double *scale, double *out);
+
+/* ---- windowed correlations ---------------------------------------------------------------------- */
+/* corMat: src/corr.cpp:11-97,102-126.  CSC pieces: p[nc+1], *i (0-based rows, ascending, diagonal
+ * last), *x; the caller releases *i and *x with bsg_free.  thr has nr entries, pos has nc. */
+int bsg_cor(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, double size,
+            const double *thr, const double *pos, int fill_diag, int64_t *p, int **i, double **x);
+/* ld_scores: src/ld-scores.cpp:11-78,83-105 */
+int bsg_ld_scores(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, double size,
+                  const double *pos, double *out);
+void bsg_free(void *ptr);
+
+/* ---- Gram product --------------------------------------------------------------------------------- */
+/* bed_tcrossprodSelf's block loop collapsed into one call: R/bed-tcrossprodSelf.R:38-49 +
+ * src/bed-mat-acc.cpp:30-49.  K is nr x nr; center/scale are the per-column scaling (length nc). */
+int bsg_tcrossprod(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc,
+                   const double *center, const double *scale, double *K);
+
+/* ---- truncated SVD ----------------------------------------------------------------------------------- */
+/* bed_randomSVD: R/autoSVD.R:205-219 -> bigstatsr::big_randomSVD -> RSpectra::svds.  The Lanczos
+ * iteration runs on the device over the two products above.  center/scale NULL = bed_scaleBinom
+ * (R/binom-scaling.R:133-142) computed on the device and returned in center_out/scale_out.
+ * d[k], u[nr x k], v[nc x k] column-major. */
+int bsg_randomsvd(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc,
+                  const double *center, const double *scale, int k, double tol, int maxit, double *d,
+                  double *u, double *v, double *center_out, double *scale_out, int *niter, int *nops);
+
+/* ---- instrumentation --------------------------------------------------------------------------------- */
+/* kernels launched by this library since load (the bench's gpu_launches claim) */
+int64_t bsg_launch_count(void);
+/* CUDA-event timing of the matvecs' dominant kernel (k_pmv), recorded on the launching stream:
+ * enable with bsg_set_kernel_timing(1); after a stream synchronise bsg_last_kernel_ms() is the device
+ * time of the last launch. */
+int bsg_set_kernel_timing(int on);
+double bsg_last_kernel_ms(void);
+/* number of k_pmv launches timed since bsg_set_kernel_timing(1) (at most the last 128) and their summed
+ * device time in ms; call after synchronising */
+int bsg_kernel_time_stats(int *count, double *total_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSGPU_H */

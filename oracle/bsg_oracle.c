@@ -555,6 +555,36 @@ int orc_ld_scores(int kind, const uint8_t *mat, int n_tot, int m_tot, const doub
   return ORC_OK;
 }
 
+/* Synthetic .bed generator, the CPU twin of the device generator
+ * (bigsnpr_b200/csrc/bsg_core.cu: k_synth): per-SNP maf ~ U(0.02, 0.5), g ~ Binomial(2, maf), missing with
+ * probability na_rate; written in the .bed bit layout of src/write-plink.cpp:29-47 (pads = 00). */
+static inline uint64_t orc_mix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+void orc_synth_packed(int n, int m, uint64_t seed, double na_rate, long long col_offset, uint8_t *out) {
+  static const uint8_t bedcode[4] = {3, 2, 0, 1}; /* genotype 0,1,2,NA -> .bed code 11,10,00,01 */
+  size_t n_byte = ((size_t)n + 3) / 4;
+  uint32_t na_thr = (uint32_t)(na_rate * 65536.0);
+#pragma omp parallel for schedule(static)
+  for (int j = 0; j < m; j++) {
+    uint64_t kj = orc_mix64(seed ^ orc_mix64((uint64_t)(col_offset + j)));
+    double maf = 0.02 + 0.48 * ((double)(kj >> 11) * (1.0 / 9007199254740992.0));
+    uint32_t thr = (uint32_t)(maf * 16777216.0);
+    uint8_t *col = out + (size_t)j * n_byte;
+    memset(col, 0, n_byte);
+    for (int i = 0; i < n; i++) {
+      uint64_t hs = orc_mix64(kj + (uint64_t)i * 0xD1342543DE82EF95ull);
+      uint32_t g = ((uint32_t)(hs & 0xFFFFFFu) < thr) + ((uint32_t)((hs >> 24) & 0xFFFFFFu) < thr);
+      if ((uint32_t)((hs >> 48) & 0xFFFFu) < na_thr) g = 3;
+      col[i >> 2] |= (uint8_t)(bedcode[g] << (2 * (i & 3)));
+    }
+  }
+}
+
 int orc_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -483,6 +483,17 @@ def bed_randomSVD(obj, fun_scaling=bed_scaleBinom, ind_row=None, ind_col=None, k
     return {"d": d[:k], "u": u[:, :k], "v": vt[:k].T, "center": ms["center"], "scale": ms["scale"]}
 
 
+def synth_bed(n, m, seed=20250924, na_rate=0.0, col_offset=0) -> "OracleBed":
+    """CPU twin of the device synthetic generator (same counter-based RNG), as an OracleBed."""
+    nb = (n + 3) // 4
+    out = np.zeros(nb * m, dtype=np.uint8)
+    f = lib().orc_synth_packed
+    f.restype = None
+    f.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_double, C.c_longlong, C.POINTER(C.c_uint8)]
+    f(int(n), int(m), int(seed), float(na_rate), int(col_offset), _p(out, C.c_uint8))
+    return OracleBed.from_packed(out, n, m)
+
+
 def decode_dense(obj) -> np.ndarray:
     """Vectorised NumPy twin of the accessor: full (n, m) uint8 matrix with NA = 3."""
     code = getCode().astype(np.uint8)  # (4, 256)

@@ -1,0 +1,94 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads, and exports every symbol that
+include/bsgpu.h declares; the host mirror validates arguments like the reference's R wrappers.
+No compute call is made here (no GPU in this container)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    from bigsnpr_b200 import build
+
+    return build.build()
+
+
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "bsgpu.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(bsg_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_symbols_exported(built):
+    import ctypes
+
+    L = ctypes.CDLL(built)
+    syms = _declared_symbols()
+    assert len(syms) >= 35
+    missing = [s for s in syms if not hasattr(L, s)]
+    assert not missing, missing
+
+
+def test_python_binding_covers_header(built):
+    from bigsnpr_b200 import _lib
+
+    assert set(_declared_symbols()) == set(_lib.SIGNATURES)
+    _lib.lib()  # loads and types every symbol
+
+
+def test_sass_is_blackwell_native(built):
+    """The matvec kernel must be IMMA (integer tensor pipe) + UBLKCP (bulk async copy) code for sm_100a."""
+    import subprocess
+
+    out = subprocess.run(["cuobjdump", "-sass", built], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    assert "IMMA.16832.U8.S8" in out
+    assert "UBLKCP" in out
+
+
+def test_no_gpu_fails_loudly(built):
+    """Without a CUDA device every compute entry point must fail (no CPU fallback)."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    from bigsnpr_b200 import Bed, BsgError
+
+    with pytest.raises(BsgError, match="no CPU fallback|CUDA"):
+        Bed(os.path.join(ROOT, "tests", "golden", "example.bed"))
+
+
+def test_product_does_not_import_oracle():
+    """The product package must never reach into oracle/ (parity claims depend on it)."""
+    pk = os.path.join(ROOT, "bigsnpr_b200")
+    for dp, _, fns in os.walk(pk):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, fn)).read()
+                assert "oracle" not in src.replace("test oracle", ""), fn
+
+
+def test_host_argument_checks_mirror_reference(built):
+    """R-side checks that run before any .Call (R/bed-mult-vec.R:65-72, R/utils-assert.R:14-17)."""
+    from bigsnpr_b200 import api
+
+    with pytest.raises(TypeError, match="is not of class 'bed' or 'bed_light'"):
+        api.bed_prodVec(np.zeros(3), np.zeros(3))
+    thr = api.cor_thresholds(10, alpha=1.0)
+    assert np.isnan(thr[:2]).all() and np.all(thr[2:] == 0)
+    r = np.sqrt(0.2)  # tests/testthat/test-2-corr.R:16-19
+    t = r * np.sqrt((517 - 2) / (1 - r * r))
+    assert abs(t / np.sqrt(517 - 2 + t * t) - r) < 1e-15
+
+
+def test_synth_reference_shapes():
+    from tests.synth_ref import synth_matrix
+
+    g = synth_matrix(50, 20, seed=7, na_rate=0.1)
+    assert g.shape == (50, 20) and set(np.unique(g)) <= {0, 1, 2, 3} and (g == 3).any()
+    g2 = synth_matrix(50, 10, seed=7, na_rate=0.1, col_offset=10)
+    assert np.array_equal(g[:, 10:], g2)
