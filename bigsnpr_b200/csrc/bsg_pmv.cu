@@ -20,9 +20,13 @@
 //         R = sum code*y, N = sum [NA]*y, Y = sum y.
 //   * integer partial sums make the result independent of the work split and of the GPU count.
 //
-// Data movement: each CTA streams 256 lines x 128 B per stage with cp.async.bulk (UBLKCP) into a
-// 4-stage shared-memory ring (mbarrier full/empty), one producer warp, 8 consumer warps that read
-// their fragments with conflict-free LDS.128 (line pitch 144 B) straight into IMMA operands.
+// Data movement (measured on B200, tools/ubench.cu): cp.async.bulk costs ~55 cycles per copy whatever
+// its size, so 128-byte per-line copies cap at 0.7 TB/s; IMMA.16832 sustains one per 2.4 cycles per SM.
+// Hence: the packed genotypes never touch shared memory -- each consumer lane streams its own fragment
+// bytes with ld.global.nc.L1::no_allocate.v4 (every warp-level load covers 8 lines x 64 contiguous
+// bytes = full sectors) through a 4-slot register ring (3 half-stages in flight per warp); only the
+// 4 KB digit block of each 512-code chunk goes through a shared-memory ring, filled by one bulk copy
+// per stage from a producer warp (mbarrier full/empty).
 #include <algorithm>
 #include <math.h>
 #include <string.h>
@@ -35,12 +39,10 @@ namespace pmv {
 constexpr int CW = 8;                 // consumer warps
 constexpr int GROUP = 256;            // lines per work item (32 per consumer warp)
 constexpr int SEG = 128;              // bytes per line per stage = 512 codes
-constexpr int PITCH = 144;            // smem line pitch: odd multiple of 16 B -> conflict-free LDS.128
 constexpr int CODES = 512;            // codes per line per stage
 constexpr int DIG = 4096;             // digit bytes per stage per plane (512 codes x 8 slices)
-constexpr int STAGES = 4;
-constexpr int GENO_BYTES = GROUP * PITCH;            // 36864
-constexpr int STAGE_BYTES = GENO_BYTES + 2 * DIG;    // 45056
+constexpr int STAGES = 6;
+constexpr int STAGE_BYTES = 2 * DIG;  // raw-plane digits + NA-plane digits
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 128;
 constexpr int THREADS = (CW + 1) * 32;
 constexpr int MAX_CHUNKS_PER_ITEM = 512;  // 262144 codes: |acc16| <= 262144*48*128 < 2^31
@@ -101,12 +103,34 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   return v;
 }
 
-// One 16-line sub-tile x one stage.  wA / wB: the 8 packed words (128 codes) of lines g and g+8 owned
-// by this lane; b[w][c]: digits of slice g for the 4 codes 4r+c (r = byte) of word w.
-template <bool NA>
-__device__ __forceinline__ void tile_stage(const uint32_t (&wA)[8], const uint32_t (&wB)[8], const uint4 (&b1)[8],
-                                           const uint4 (&b2)[8], int (&acc1)[4], int (&acc16)[4], int (&accn1)[4],
-                                           int (&accn16)[4]) {
+__device__ __forceinline__ uint4 ldg_stream(const uint8_t *p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+
+// Fragment bytes of one lane for one 16-line sub-tile and one 128-byte chunk: lines g (a*) and g+8 (b*),
+// bytes [16q, 16q+16) (lo) and [64+16q, 64+16q+16) (hi) of the chunk.
+struct Slot {
+  uint4 alo, ahi, blo, bhi;
+};
+
+__device__ __forceinline__ void slot_load(Slot &s, const uint8_t *pa, const uint8_t *pb, int64_t off) {
+  s.alo = ldg_stream(pa + off);
+  s.ahi = ldg_stream(pa + off + 64);
+  s.blo = ldg_stream(pb + off);
+  s.bhi = ldg_stream(pb + off + 64);
+}
+
+// One 16-line sub-tile x one chunk.  Word w of the lane (w < 4: lo bytes, w >= 4: hi bytes) holds 16
+// codes; b[w] = digits of slice g for those 16 codes, register c <-> codes 4r+c (r = byte of the register).
+template <int MODE>
+__device__ __forceinline__ void tile_stage(const Slot &sl, const uint4 (&b1)[8], uint32_t dig2_addr, int (&acc1)[4],
+                                           int (&acc16)[4], int (&accn1)[4], int (&accn16)[4]) {
+  const uint32_t wA[8] = {sl.alo.x, sl.alo.y, sl.alo.z, sl.alo.w, sl.ahi.x, sl.ahi.y, sl.ahi.z, sl.ahi.w};
+  const uint32_t wB[8] = {sl.blo.x, sl.blo.y, sl.blo.z, sl.blo.w, sl.bhi.x, sl.bhi.y, sl.bhi.z, sl.bhi.w};
 #pragma unroll
   for (int w = 0; w < 8; w++) {
     const uint32_t a = wA[w], bq = wB[w];
@@ -114,15 +138,18 @@ __device__ __forceinline__ void tile_stage(const uint32_t (&wA)[8], const uint32
     // codes 4r (x1) and 4r+1 (x1) | codes 4r+2 (x16) and 4r+3 (x16)
     mma_u8s8(acc1, a & 0x03030303u, bq & 0x03030303u, at & 0x03030303u, bt & 0x03030303u, b1[w].x, b1[w].y);
     mma_u8s8(acc16, a & 0x30303030u, bq & 0x30303030u, at & 0x30303030u, bt & 0x30303030u, b1[w].z, b1[w].w);
-    if (NA) {
+    if (MODE != 0) {
+      uint4 d = b1[w];
+      if (MODE == 2) d = lds128(dig2_addr + w * 512);
       const uint32_t an = a & (a >> 1), bn = bq & (bq >> 1);      // bit 2p set iff code p == 3
       const uint32_t ant = at & (at >> 1), bnt = bt & (bt >> 1);
-      mma_u8s8(accn1, an & 0x01010101u, bn & 0x01010101u, ant & 0x01010101u, bnt & 0x01010101u, b2[w].x, b2[w].y);
-      mma_u8s8(accn16, an & 0x10101010u, bn & 0x10101010u, ant & 0x10101010u, bnt & 0x10101010u, b2[w].z, b2[w].w);
+      mma_u8s8(accn1, an & 0x01010101u, bn & 0x01010101u, ant & 0x01010101u, bnt & 0x01010101u, d.x, d.y);
+      mma_u8s8(accn16, an & 0x10101010u, bn & 0x10101010u, ant & 0x10101010u, bnt & 0x10101010u, d.z, d.w);
     }
   }
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(THREADS, 1) k_pmv(const Args a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -140,53 +167,53 @@ __global__ void __launch_bounds__(THREADS, 1) k_pmv(const Args a) {
 
   const int ngroups = a.nlines_pad / GROUP;
   const int nitems = ngroups * a.ksplit;
-  const bool two_dig = a.use_na && a.dig2 != nullptr;
-  const uint32_t stage_tx = GROUP * SEG + DIG + (two_dig ? DIG : 0);
+  constexpr bool two_dig = MODE == 2;
+  const uint32_t stage_tx = DIG + (two_dig ? DIG : 0);
 
   int stage = 0;
   uint32_t phase = 0;
 
   if (warp == CW) {
-    // ===================== producer warp: bulk copies global -> shared =====================
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-      const int group = item / a.ksplit, ks = item - group * a.ksplit;
-      const int c0 = ks * a.chunks_per_split;
-      const int c1 = min(a.nchunks, c0 + a.chunks_per_split);
-      const uint8_t *src[8];
-#pragma unroll
-      for (int t = 0; t < 8; t++) {
-        int l = group * GROUP + lane * 8 + t;
-        l = min(l, a.nlines - 1);
-        const int phys = a.lines ? a.lines[l] : l;
-        src[t] = a.P + (int64_t)phys * a.stride;
-      }
-      for (int c = c0; c < c1; c++) {
-        const uint32_t full = bar_base + 8 * stage, empty = bar_base + 8 * (STAGES + stage);
-        mbar_wait(empty, phase ^ 1);
-        if (lane == 0) mbar_expect_tx(full, stage_tx);
-        __syncwarp();
-        const uint32_t dst = smem_base + stage * STAGE_BYTES;
-#pragma unroll
-        for (int t = 0; t < 8; t++)
-          bulk_g2s(dst + (lane * 8 + t) * PITCH, src[t] + (int64_t)c * SEG, SEG, full);
-        if (lane == 0) bulk_g2s(dst + GENO_BYTES, a.dig1 + (int64_t)c * DIG, DIG, full);
-        if (lane == 1 && two_dig) bulk_g2s(dst + GENO_BYTES + DIG, a.dig2 + (int64_t)c * DIG, DIG, full);
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
+    // ============ producer warp: one bulk copy of the digit block(s) per chunk ============
+    if (lane == 0) {
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int group = item / a.ksplit, ks = item - group * a.ksplit;
+        const int c0 = ks * a.chunks_per_split;
+        const int c1 = min(a.nchunks, c0 + a.chunks_per_split);
+        for (int c = c0; c < c1; c++) {
+          const uint32_t full = bar_base + 8 * stage, empty = bar_base + 8 * (STAGES + stage);
+          mbar_wait(empty, phase ^ 1);
+          mbar_expect_tx(full, stage_tx);
+          const uint32_t dst = smem_base + stage * STAGE_BYTES;
+          bulk_g2s(dst, a.dig1 + (int64_t)c * DIG, DIG, full);
+          if (two_dig) bulk_g2s(dst + DIG, a.dig2 + (int64_t)c * DIG, DIG, full);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     }
   } else {
-    // ===================== consumer warps: LDS.128 -> IMMA ================================
+    // ============ consumer warps: LDG.128 register ring -> IMMA ===========================
     const int g = lane >> 2, q = lane & 3;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
       const int group = item / a.ksplit, ks = item - group * a.ksplit;
       const int c0 = ks * a.chunks_per_split;
       const int c1 = min(a.nchunks, c0 + a.chunks_per_split);
+      // line pointers of this lane: sub-tile u, lines g and g+8, pre-offset by the lane's 16 q bytes
+      const uint8_t *pA[2], *pB[2];
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        int la = min(group * GROUP + warp * 32 + u * 16 + g, a.nlines - 1);
+        int lb = min(group * GROUP + warp * 32 + u * 16 + g + 8, a.nlines - 1);
+        const int pa = a.lines ? a.lines[la] : la, pb = a.lines ? a.lines[lb] : lb;
+        pA[u] = a.P + (int64_t)pa * a.stride + 16 * q;
+        pB[u] = a.P + (int64_t)pb * a.stride + 16 * q;
+      }
       // does any of this warp's 32 lines hold a missing value?  (warp-uniform)
       bool tile_na = false;
-      if (a.use_na) {
+      if (MODE != 0) {
         if (a.na_flags) {
           int l = min(group * GROUP + warp * 32 + lane, a.nlines - 1);
           const int phys = a.lines ? a.lines[l] : l;
@@ -201,40 +228,48 @@ __global__ void __launch_bounds__(THREADS, 1) k_pmv(const Args a) {
 #pragma unroll
         for (int k = 0; k < 4; k++) acc1[u][k] = acc16[u][k] = accn1[u][k] = accn16[u][k] = 0;
 
-      for (int c = c0; c < c1; c++) {
-        const uint32_t full = bar_base + 8 * stage, empty = bar_base + 8 * (STAGES + stage);
-        mbar_wait(full, phase);
-        const uint32_t sbase = smem_base + stage * STAGE_BYTES;
-        const uint32_t dbase = sbase + GENO_BYTES + (g * 4 + q) * 16;
-        uint4 b1[8], b2[8];
+      // register ring: slots 0/1 = even chunk (sub-tiles 0/1), slots 2/3 = odd chunk
+      Slot s0, s1, s2, s3;
+      s0 = s1 = s2 = s3 = Slot{make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+      if (c0 < c1) {
+        slot_load(s0, pA[0], pB[0], (int64_t)c0 * SEG);
+        slot_load(s1, pA[1], pB[1], (int64_t)c0 * SEG);
+      }
+      if (c0 + 1 < c1) {
+        slot_load(s2, pA[0], pB[0], (int64_t)(c0 + 1) * SEG);
+        slot_load(s3, pA[1], pB[1], (int64_t)(c0 + 1) * SEG);
+      }
+
+      for (int c = c0; c < c1; c += 2) {
 #pragma unroll
-        for (int w = 0; w < 8; w++) b1[w] = lds128(dbase + w * 512);
-        if (tile_na) {
-          if (two_dig) {
+        for (int par = 0; par < 2; par++) {
+          if (par == 1 && c + 1 >= c1) break;
+          const uint32_t full = bar_base + 8 * stage, empty = bar_base + 8 * (STAGES + stage);
+          mbar_wait(full, phase);
+          const uint32_t dbase = smem_base + stage * STAGE_BYTES + (g * 4 + q) * 16;
+          uint4 b1[8];
 #pragma unroll
-            for (int w = 0; w < 8; w++) b2[w] = lds128(dbase + DIG + w * 512);
-          } else {
-#pragma unroll
-            for (int w = 0; w < 8; w++) b2[w] = b1[w];
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-          const uint32_t la = sbase + (warp * 32 + u * 16 + g) * PITCH + q * 32;
-          const uint32_t lb = la + 8 * PITCH;
-          uint4 x0 = lds128(la), x1 = lds128(la + 16), y0 = lds128(lb), y1 = lds128(lb + 16);
-          const uint32_t wA[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-          const uint32_t wB[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
-          if (tile_na)
-            tile_stage<true>(wA, wB, b1, b2, acc1[u], acc16[u], accn1[u], accn16[u]);
+          for (int w = 0; w < 8; w++) b1[w] = lds128(dbase + w * 512);
+          const int64_t next = (int64_t)(c + par + 2) * SEG;
+          const bool more = (c + par + 2) < c1;
+          Slot &t0 = par ? s2 : s0;
+          Slot &t1 = par ? s3 : s1;
+          if (MODE != 0 && tile_na)
+            tile_stage<MODE>(t0, b1, dbase + DIG, acc1[0], acc16[0], accn1[0], accn16[0]);
           else
-            tile_stage<false>(wA, wB, b1, b1, acc1[u], acc16[u], accn1[u], accn16[u]);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty);
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
+            tile_stage<0>(t0, b1, 0, acc1[0], acc16[0], accn1[0], accn16[0]);
+          if (more) slot_load(t0, pA[0], pB[0], next);
+          if (MODE != 0 && tile_na)
+            tile_stage<MODE>(t1, b1, dbase + DIG, acc1[1], acc16[1], accn1[1], accn16[1]);
+          else
+            tile_stage<0>(t1, b1, 0, acc1[1], acc16[1], accn1[1], accn16[1]);
+          if (more) slot_load(t1, pA[1], pB[1], next);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(empty);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
       // ---- item epilogue: exact recombination of the x1 / x16 accumulators, 16 B stores ----
@@ -250,7 +285,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_pmv(const Args a) {
           vn.x = (long long)accn1[u][2 * hrow] + (long long)(accn16[u][2 * hrow] >> 4);
           vn.y = (long long)accn1[u][2 * hrow + 1] + (long long)(accn16[u][2 * hrow + 1] >> 4);
           *reinterpret_cast<longlong2 *>(dst) = v;
-          *reinterpret_cast<longlong2 *>(dst + 8) = vn;
+          if (MODE != 0) *reinterpret_cast<longlong2 *>(dst + 8) = vn;
         }
       }
     }
@@ -353,8 +388,9 @@ __global__ void k_quantise(int mode, const double *__restrict__ x, const double 
   }
 }
 
-// digits: one thread per 16-byte unit (chunk, w, s, q) -> 16 int8 digits of slice s for the codes
-// t = 128 q + 16 w + 4 r + c of the chunk, stored at byte c*4 + r  (see tile_stage).
+// digits: one thread per 16-byte unit (chunk, w, s, q) -> 16 int8 digits of slice s for the 16 codes of
+// word w of lane q (bytes 16q + 4w of the chunk for w < 4, bytes 64 + 16q + 4(w-4) for w >= 4), i.e. codes
+// t = (w < 4 ? 64 q + 16 w : 256 + 64 q + 16 (w - 4)) + 4 r + c, stored at byte c*4 + r  (see tile_stage).
 __global__ void k_digits(const long long *__restrict__ Q, int len, int nchunks, uint8_t *__restrict__ dig) {
   int64_t total = (int64_t)nchunks * 256;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -365,7 +401,7 @@ __global__ void k_digits(const long long *__restrict__ Q, int len, int nchunks, 
     for (int c = 0; c < 4; c++) {
 #pragma unroll
       for (int r = 0; r < 4; r++) {
-        int64_t k = (int64_t)chunk * CODES + 128 * q + 16 * w + 4 * r + c;
+        int64_t k = (int64_t)chunk * CODES + (w < 4 ? 64 * q + 16 * w : 256 + 64 * q + 16 * (w - 4)) + 4 * r + c;
         long long v = k < len ? Q[k] : 0;
         // signed base-256 digit s: peel s digits
         int d = 0;
@@ -428,13 +464,19 @@ __global__ void k_sum_cz(const double *__restrict__ x, const double *__restrict_
   }
 }
 
-__device__ __forceinline__ double combine8(const long long *__restrict__ part, int64_t line, int plane, int ksplit,
+// sum over the k-splits and the 8 digit slices of (raw-plane * c0 + NA-plane * c1), exact in integers per
+// slice, then one top-down fp64 sum of the 8 scaled slice totals.
+__device__ __forceinline__ double combine8(const long long *__restrict__ part, int64_t line, int c0, int c1, int ksplit,
                                            int64_t nlines_pad, int e) {
   double acc = 0;
 #pragma unroll
   for (int s = 7; s >= 0; s--) {
     long long v = 0;
-    for (int ks = 0; ks < ksplit; ks++) v += part[((int64_t)ks * nlines_pad + line) * 16 + plane * 8 + s];
+    for (int ks = 0; ks < ksplit; ks++) {
+      const long long *p = part + ((int64_t)ks * nlines_pad + line) * 16;
+      if (c0) v += c0 * p[s];
+      if (c1) v += c1 * p[8 + s];
+    }
     acc += scalbn((double)v, 8 * s - e);
   }
   return acc;
@@ -451,9 +493,8 @@ __global__ void k_finish_cprod(const long long *__restrict__ part, int ksplit, i
     return;
   }
   const int e = sc->e[0];
-  double R = combine8(part, j, 0, ksplit, nlines_pad, e);
-  double N = use_na ? combine8(part, j, 1, ksplit, nlines_pad, e) : 0.0;
-  double G = R - 3.0 * N;
+  double G = combine8(part, j, 1, use_na ? -3 : 0, ksplit, nlines_pad, e);  // R - 3N, exact
+  double N = use_na ? combine8(part, j, 0, 1, ksplit, nlines_pad, e) : 0.0;
   if (center) {
     out[j] = (G - center[j] * (sc->Y - N)) / scale[j];
   } else {
@@ -471,13 +512,12 @@ __global__ void k_finish_prod(const long long *__restrict__ part, int ksplit, in
     full[l] = nan("");
     return;
   }
-  double R = combine8(part, l, 0, ksplit, nlines_pad, sc->e[0]);
   if (has_scaling) {
-    double Nw = use_na ? combine8(part, l, 1, ksplit, nlines_pad, sc->e[1]) : 0.0;
+    double R = combine8(part, l, 1, 0, ksplit, nlines_pad, sc->e[0]);
+    double Nw = use_na ? combine8(part, l, 0, 1, ksplit, nlines_pad, sc->e[1]) : 0.0;
     full[l] = (R + Nw) - sc->C;
   } else {
-    double N = use_na ? combine8(part, l, 1, ksplit, nlines_pad, sc->e[0]) : 0.0;
-    full[l] = R - 3.0 * N;
+    full[l] = combine8(part, l, 1, use_na ? -3 : 0, ksplit, nlines_pad, sc->e[0]);  // R - 3N, exact
   }
 }
 
@@ -533,13 +573,15 @@ static int run_pmv(bsg_view *v, const uint8_t *P, int64_t stride, int L, const i
   a.use_na = use_na;
   BSG_TRY(v->s_part.ensure((size_t)a.ksplit * a.nlines_pad * 16 * sizeof(long long)));
   a.part = v->s_part.as<long long>();
-  BSG_CUDA(cudaFuncSetAttribute(k_pmv, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  const int mode = !use_na ? 0 : (dig2 ? 2 : 1);
+  auto kern = mode == 0 ? k_pmv<0> : (mode == 1 ? k_pmv<1> : k_pmv<2>);
+  BSG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   int nsm = 148;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, v->h->device);
   int nitems = ngroups * a.ksplit;
   int grid = std::min(nitems, nsm);
   if (g_timing) cudaEventRecord(g_ev0[g_ev_n % EV_POOL], s);
-  k_pmv<<<grid, THREADS, SMEM_BYTES, s>>>(a);
+  kern<<<grid, THREADS, SMEM_BYTES, s>>>(a);
   if (g_timing) {
     cudaEventRecord(g_ev1[g_ev_n % EV_POOL], s);
     g_ev_n++;

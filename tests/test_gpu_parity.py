@@ -39,9 +39,9 @@ def gbed_na(B):
 def _close(got, want, scale=None, tol=1e-11):
     got, want = np.asarray(got), np.asarray(want)
     s = np.max(np.abs(want)) if scale is None else scale
-    s = max(s, 1e-300)
+    s = np.maximum(np.asarray(s, dtype=float), 1e-300)
     assert got.shape == want.shape
-    err = np.max(np.abs(got - want)) / s if got.size else 0.0
+    err = float(np.max(np.abs(got - want) / s)) if got.size else 0.0
     assert err < tol, err
 
 
@@ -126,8 +126,8 @@ def test_prodvec_equality_with_dense(B, gbed_na, oracle, obed_na, rng):
         ic = rng.choice(M, m, replace=False) + 1
         y_col, y_row = rng.normal(size=m), rng.normal(size=n)
         X = oracle.read_bed_scaled(obed_na, ir, ic, np.zeros(m), np.ones(m))
-        _close(B.bed_prodVec(gbed_na, y_col, ir, ic), X @ y_col, scale=np.abs(X) @ np.abs(y_col) + 1e-300)
-        _close(B.bed_cprodVec(gbed_na, y_row, ir, ic), X.T @ y_row, scale=np.abs(X.T) @ np.abs(y_row) + 1e-300)
+        _close(B.bed_prodVec(gbed_na, y_col, ir, ic), X @ y_col, scale=np.abs(X) @ np.abs(y_col) + 1e-9)
+        _close(B.bed_cprodVec(gbed_na, y_row, ir, ic), X.T @ y_row, scale=np.abs(X.T) @ np.abs(y_row) + 1e-9)
         c, s = rng.normal(size=m), rng.uniform(size=m)
         _close(B.bed_prodVec(gbed_na, y_col, ir, ic, c, s), oracle.bed_prodVec(obed_na, y_col, ir, ic, c, s),
                scale=np.max(np.abs(y_col / s)) * m * 3)

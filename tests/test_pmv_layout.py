@@ -23,7 +23,8 @@ def digits_of(Q):
 
 
 def make_digit_chunk(Qchunk):
-    """k_digits: unit (w, s, q) at ((w*8+s)*4+q)*16, byte c*4+r <-> code t = 128q + 16w + 4r + c."""
+    """k_digits: unit (w, s, q) at ((w*8+s)*4+q)*16, byte c*4+r <-> code
+    t = (64q + 16w if w < 4 else 256 + 64q + 16(w-4)) + 4r + c  (word w of lane q, see k_pmv slot_load)."""
     buf = np.zeros(DIG, dtype=np.int8)
     D = np.array([digits_of(q) for q in Qchunk], dtype=np.int64)  # (512, 8)
     for w in range(8):
@@ -32,7 +33,7 @@ def make_digit_chunk(Qchunk):
                 base = ((w * 8 + s) * 4 + q) * 16
                 for c in range(4):
                     for r in range(4):
-                        buf[base + c * 4 + r] = D[128 * q + 16 * w + 4 * r + c, s]
+                        buf[base + c * 4 + r] = D[(64 * q + 16 * w if w < 4 else 256 + 64 * q + 16 * (w - 4)) + 4 * r + c, s]
     return buf
 
 
@@ -72,8 +73,9 @@ def run_subtile(lines_words, dig_chunks, with_na):
             bA = np.zeros((32, 2), dtype=np.uint32); bB = np.zeros((32, 2), dtype=np.uint32)
             for lane in range(32):
                 g, q = lane >> 2, lane & 3
-                # lane owns bytes [32q, 32q+32) of the 128-byte chunk = words 8q..8q+7
-                a = int(lines_words[g][c][8 * q + w]); b = int(lines_words[g + 8][c][8 * q + w])
+                # lane owns bytes [16q, 16q+16) (words 4q..4q+3) and [64+16q, 64+16q+16) (words 16+4q..) of the chunk
+                wi = 4 * q + w if w < 4 else 16 + 4 * q + (w - 4)
+                a = int(lines_words[g][c][wi]); b = int(lines_words[g + 8][c][wi])
                 at, bt = a >> 2, b >> 2
                 a1[lane] = [a & 0x03030303, b & 0x03030303, at & 0x03030303, bt & 0x03030303]
                 a16[lane] = [a & 0x30303030, b & 0x30303030, at & 0x30303030, bt & 0x30303030]
