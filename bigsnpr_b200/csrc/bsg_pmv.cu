@@ -29,6 +29,8 @@
 // per stage from a producer warp (mbarrier full/empty).
 #include <algorithm>
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "bsg_internal.cuh"
@@ -36,15 +38,14 @@
 namespace bsg {
 namespace pmv {
 
-constexpr int CW = 8;                 // consumer warps
-constexpr int GROUP = 256;            // lines per work item (32 per consumer warp)
 constexpr int SEG = 128;              // bytes per line per stage = 512 codes
 constexpr int CODES = 512;            // codes per line per stage
 constexpr int DIG = 4096;             // digit bytes per stage per plane (512 codes x 8 slices)
 constexpr int STAGES = 6;
 constexpr int STAGE_BYTES = 2 * DIG;  // raw-plane digits + NA-plane digits
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 128;
-constexpr int THREADS = (CW + 1) * 32;
+// Variants <CW consumer warps, R chunks of register ring per warp>; lines per work item = 32 * CW.
+// Register file: (CW + 1) warps share 4 SMSPs of 16 K registers -> cap 255 regs for 8 warps, 168 for 9..12.
 constexpr int MAX_CHUNKS_PER_ITEM = 512;  // 262144 codes: |acc16| <= 262144*48*128 < 2^31
 
 struct Args {
@@ -52,7 +53,7 @@ struct Args {
   int64_t stride;
   const int *lines;      // physical line per logical line (null = identity)
   int nlines;
-  int nlines_pad;        // multiple of GROUP
+  int nlines_pad;        // multiple of the group size (32 * consumer warps)
   int nchunks;           // 128-byte chunks per line
   int chunks_per_split;
   int ksplit;
@@ -124,33 +125,44 @@ __device__ __forceinline__ void slot_load(Slot &s, const uint8_t *pa, const uint
   s.bhi = ldg_stream(pb + off + 64);
 }
 
-// One 16-line sub-tile x one chunk.  Word w of the lane (w < 4: lo bytes, w >= 4: hi bytes) holds 16
-// codes; b[w] = digits of slice g for those 16 codes, register c <-> codes 4r+c (r = byte of the register).
+// One chunk of the warp's 32 lines (two 16-line sub-tiles t0 / t1).  Word w of the lane (w < 4: lo bytes,
+// w >= 4: hi bytes) holds 16 codes of each of its 4 lines; d = digits of slice g for those 16 codes (one
+// LDS.128 per word, shared by both sub-tiles), register c <-> codes 4r+c (r = byte of the register).
+// The four MMAs of a word go to four different accumulators: independent chains for the tensor pipe.
 template <int MODE>
-__device__ __forceinline__ void tile_stage(const Slot &sl, const uint4 (&b1)[8], uint32_t dig2_addr, int (&acc1)[4],
-                                           int (&acc16)[4], int (&accn1)[4], int (&accn16)[4]) {
-  const uint32_t wA[8] = {sl.alo.x, sl.alo.y, sl.alo.z, sl.alo.w, sl.ahi.x, sl.ahi.y, sl.ahi.z, sl.ahi.w};
-  const uint32_t wB[8] = {sl.blo.x, sl.blo.y, sl.blo.z, sl.blo.w, sl.bhi.x, sl.bhi.y, sl.bhi.z, sl.bhi.w};
+__device__ __forceinline__ void chunk_mma(const Slot &t0, const Slot &t1, uint32_t dig_addr, int (&acc1)[2][4],
+                                          int (&acc16)[2][4], int (&accn1)[2][4], int (&accn16)[2][4]) {
+  const uint32_t wA0[8] = {t0.alo.x, t0.alo.y, t0.alo.z, t0.alo.w, t0.ahi.x, t0.ahi.y, t0.ahi.z, t0.ahi.w};
+  const uint32_t wB0[8] = {t0.blo.x, t0.blo.y, t0.blo.z, t0.blo.w, t0.bhi.x, t0.bhi.y, t0.bhi.z, t0.bhi.w};
+  const uint32_t wA1[8] = {t1.alo.x, t1.alo.y, t1.alo.z, t1.alo.w, t1.ahi.x, t1.ahi.y, t1.ahi.z, t1.ahi.w};
+  const uint32_t wB1[8] = {t1.blo.x, t1.blo.y, t1.blo.z, t1.blo.w, t1.bhi.x, t1.bhi.y, t1.bhi.z, t1.bhi.w};
 #pragma unroll
   for (int w = 0; w < 8; w++) {
-    const uint32_t a = wA[w], bq = wB[w];
-    const uint32_t at = a >> 2, bt = bq >> 2;
+    const uint4 d = lds128(dig_addr + w * 512);
+    const uint32_t a0 = wA0[w], b0 = wB0[w], a1 = wA1[w], b1 = wB1[w];
+    const uint32_t a0t = a0 >> 2, b0t = b0 >> 2, a1t = a1 >> 2, b1t = b1 >> 2;
     // codes 4r (x1) and 4r+1 (x1) | codes 4r+2 (x16) and 4r+3 (x16)
-    mma_u8s8(acc1, a & 0x03030303u, bq & 0x03030303u, at & 0x03030303u, bt & 0x03030303u, b1[w].x, b1[w].y);
-    mma_u8s8(acc16, a & 0x30303030u, bq & 0x30303030u, at & 0x30303030u, bt & 0x30303030u, b1[w].z, b1[w].w);
+    mma_u8s8(acc1[0], a0 & 0x03030303u, b0 & 0x03030303u, a0t & 0x03030303u, b0t & 0x03030303u, d.x, d.y);
+    mma_u8s8(acc1[1], a1 & 0x03030303u, b1 & 0x03030303u, a1t & 0x03030303u, b1t & 0x03030303u, d.x, d.y);
+    mma_u8s8(acc16[0], a0 & 0x30303030u, b0 & 0x30303030u, a0t & 0x30303030u, b0t & 0x30303030u, d.z, d.w);
+    mma_u8s8(acc16[1], a1 & 0x30303030u, b1 & 0x30303030u, a1t & 0x30303030u, b1t & 0x30303030u, d.z, d.w);
     if (MODE != 0) {
-      uint4 d = b1[w];
-      if (MODE == 2) d = lds128(dig2_addr + w * 512);
-      const uint32_t an = a & (a >> 1), bn = bq & (bq >> 1);      // bit 2p set iff code p == 3
-      const uint32_t ant = at & (at >> 1), bnt = bt & (bt >> 1);
-      mma_u8s8(accn1, an & 0x01010101u, bn & 0x01010101u, ant & 0x01010101u, bnt & 0x01010101u, d.x, d.y);
-      mma_u8s8(accn16, an & 0x10101010u, bn & 0x10101010u, ant & 0x10101010u, bnt & 0x10101010u, d.z, d.w);
+      uint4 dn = d;
+      if (MODE == 2) dn = lds128(dig_addr + DIG + w * 512);
+      // bit 2p of x & (x >> 1) is set iff code p == 3
+      const uint32_t a0n = a0 & (a0 >> 1), b0n = b0 & (b0 >> 1), a0nt = a0t & (a0t >> 1), b0nt = b0t & (b0t >> 1);
+      const uint32_t a1n = a1 & (a1 >> 1), b1n = b1 & (b1 >> 1), a1nt = a1t & (a1t >> 1), b1nt = b1t & (b1t >> 1);
+      mma_u8s8(accn1[0], a0n & 0x01010101u, b0n & 0x01010101u, a0nt & 0x01010101u, b0nt & 0x01010101u, dn.x, dn.y);
+      mma_u8s8(accn1[1], a1n & 0x01010101u, b1n & 0x01010101u, a1nt & 0x01010101u, b1nt & 0x01010101u, dn.x, dn.y);
+      mma_u8s8(accn16[0], a0n & 0x10101010u, b0n & 0x10101010u, a0nt & 0x10101010u, b0nt & 0x10101010u, dn.z, dn.w);
+      mma_u8s8(accn16[1], a1n & 0x10101010u, b1n & 0x10101010u, a1nt & 0x10101010u, b1nt & 0x10101010u, dn.z, dn.w);
     }
   }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(THREADS, 1) k_pmv(const Args a) {
+template <int MODE, int CW, int R>
+__global__ void __launch_bounds__((CW + 1) * 32, 1) k_pmv(const Args a) {
+  constexpr int GROUP = CW * 32;
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = smem_u32(smem);
@@ -228,42 +240,36 @@ __global__ void __launch_bounds__(THREADS, 1) k_pmv(const Args a) {
 #pragma unroll
         for (int k = 0; k < 4; k++) acc1[u][k] = acc16[u][k] = accn1[u][k] = accn16[u][k] = 0;
 
-      // register ring: slots 0/1 = even chunk (sub-tiles 0/1), slots 2/3 = odd chunk
-      Slot s0, s1, s2, s3;
-      s0 = s1 = s2 = s3 = Slot{make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-      if (c0 < c1) {
-        slot_load(s0, pA[0], pB[0], (int64_t)c0 * SEG);
-        slot_load(s1, pA[1], pB[1], (int64_t)c0 * SEG);
-      }
-      if (c0 + 1 < c1) {
-        slot_load(s2, pA[0], pB[0], (int64_t)(c0 + 1) * SEG);
-        slot_load(s3, pA[1], pB[1], (int64_t)(c0 + 1) * SEG);
+      // register ring: ring[k][u] = fragment bytes of chunk (c0 + j*R + k), sub-tile u; R chunks resident,
+      // each slot is refilled for chunk + R right after its MMAs are issued (2R - 1 slots in flight)
+      Slot ring[R][2];
+#pragma unroll
+      for (int k = 0; k < R; k++) {
+        ring[k][0] = ring[k][1] =
+            Slot{make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+        if (c0 + k < c1) {
+          slot_load(ring[k][0], pA[0], pB[0], (int64_t)(c0 + k) * SEG);
+          slot_load(ring[k][1], pA[1], pB[1], (int64_t)(c0 + k) * SEG);
+        }
       }
 
-      for (int c = c0; c < c1; c += 2) {
+      for (int c = c0; c < c1; c += R) {
 #pragma unroll
-        for (int par = 0; par < 2; par++) {
-          if (par == 1 && c + 1 >= c1) break;
+        for (int par = 0; par < R; par++) {
+          if (par > 0 && c + par >= c1) break;
           const uint32_t full = bar_base + 8 * stage, empty = bar_base + 8 * (STAGES + stage);
           mbar_wait(full, phase);
           const uint32_t dbase = smem_base + stage * STAGE_BYTES + (g * 4 + q) * 16;
-          uint4 b1[8];
-#pragma unroll
-          for (int w = 0; w < 8; w++) b1[w] = lds128(dbase + w * 512);
-          const int64_t next = (int64_t)(c + par + 2) * SEG;
-          const bool more = (c + par + 2) < c1;
-          Slot &t0 = par ? s2 : s0;
-          Slot &t1 = par ? s3 : s1;
+          const int64_t next = (int64_t)(c + par + R) * SEG;
+          const bool more = (c + par + R) < c1;
           if (MODE != 0 && tile_na)
-            tile_stage<MODE>(t0, b1, dbase + DIG, acc1[0], acc16[0], accn1[0], accn16[0]);
+            chunk_mma<MODE>(ring[par][0], ring[par][1], dbase, acc1, acc16, accn1, accn16);
           else
-            tile_stage<0>(t0, b1, 0, acc1[0], acc16[0], accn1[0], accn16[0]);
-          if (more) slot_load(t0, pA[0], pB[0], next);
-          if (MODE != 0 && tile_na)
-            tile_stage<MODE>(t1, b1, dbase + DIG, acc1[1], acc16[1], accn1[1], accn16[1]);
-          else
-            tile_stage<0>(t1, b1, 0, acc1[1], acc16[1], accn1[1], accn16[1]);
-          if (more) slot_load(t1, pA[1], pB[1], next);
+            chunk_mma<0>(ring[par][0], ring[par][1], dbase, acc1, acc16, accn1, accn16);
+          if (more) {
+            slot_load(ring[par][0], pA[0], pB[0], next);
+            slot_load(ring[par][1], pA[1], pB[1], next);
+          }
           __syncwarp();
           if (lane == 0) mbar_arrive(empty);
           if (++stage == STAGES) {
@@ -300,8 +306,9 @@ struct Scal {          // device-resident scalars of one call
   int nonfinite;
   int e[2];            // Q = rint(v * 2^e)
   double Y;            // sum of the (scattered) vector, for Xt.y
-  double C;            // sum_k c_k z_k, for X.y
+  double C;            // (unused, kept for layout)
   long long sum_hi, sum_lo;
+  double cpart[128];   // per-block partials of sum_k c_k z_k (X.y), added in index order by the finish kernel
 };
 
 // mode 0: v0 = x                      (Xt.y, identity scaling handled in finish)
@@ -416,11 +423,11 @@ __global__ void k_digits(const long long *__restrict__ Q, int len, int nchunks, 
   }
 }
 
-// exact integer sum of Q (split in 32-bit halves), then Y = sum * 2^-e     (single block)
+// exact integer sum of Q (split in 32-bit halves, integer atomics: order independent); Y is formed from
+// (sum_hi, sum_lo) in the finish kernel.
 __global__ void k_sum_q(const long long *__restrict__ Q, int len, Scal *sc) {
-  __shared__ long long sh[64], sl[64];
   long long hi = 0, lo = 0;
-  for (int k = threadIdx.x; k < len; k += blockDim.x) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < len; k += gridDim.x * blockDim.x) {
     long long v = Q[k];
     hi += v >> 32;
     lo += (long long)(unsigned int)(v & 0xFFFFFFFFll);
@@ -431,28 +438,20 @@ __global__ void k_sum_q(const long long *__restrict__ Q, int len, Scal *sc) {
     lo += __shfl_xor_sync(0xffffffffu, lo, o);
   }
   if ((threadIdx.x & 31) == 0) {
-    sh[threadIdx.x >> 5] = hi;
-    sl[threadIdx.x >> 5] = lo;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    long long H = 0, L = 0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); w++) {
-      H += sh[w];
-      L += sl[w];
-    }
-    sc->sum_hi = H;
-    sc->sum_lo = L;
-    sc->Y = scalbn((double)H, 32 - sc->e[0]) + scalbn((double)L, -sc->e[0]);
+    atomicAdd(reinterpret_cast<unsigned long long *>(&sc->sum_hi), (unsigned long long)hi);
+    atomicAdd(reinterpret_cast<unsigned long long *>(&sc->sum_lo), (unsigned long long)lo);
   }
 }
 
-// C = sum_k c_k * (x_k / s_k), fixed-shape tree (single block) -> deterministic
+// C = sum_k c_k * (x_k / s_k): per-block partial sums with a fixed-shape tree, written to cpart[block];
+// the finish kernel adds the SUMCZ_BLOCKS partials in index order -> deterministic.
+constexpr int SUMCZ_BLOCKS = 128;
 __global__ void k_sum_cz(const double *__restrict__ x, const double *__restrict__ center,
-                         const double *__restrict__ scale, int len, Scal *sc) {
+                         const double *__restrict__ scale, int len, double *__restrict__ cpart) {
   __shared__ double sh[32];
   double acc = 0;
-  for (int k = threadIdx.x; k < len; k += blockDim.x) acc += center[k] * (x[k] / scale[k]);
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < len; k += gridDim.x * blockDim.x)
+    acc += center[k] * (x[k] / scale[k]);
 #pragma unroll
   for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
@@ -460,7 +459,7 @@ __global__ void k_sum_cz(const double *__restrict__ x, const double *__restrict_
   if (threadIdx.x == 0) {
     double t = 0;
     for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += sh[w];
-    sc->C = t;
+    cpart[blockIdx.x] = t;
   }
 }
 
@@ -496,7 +495,8 @@ __global__ void k_finish_cprod(const long long *__restrict__ part, int ksplit, i
   double G = combine8(part, j, 1, use_na ? -3 : 0, ksplit, nlines_pad, e);  // R - 3N, exact
   double N = use_na ? combine8(part, j, 0, 1, ksplit, nlines_pad, e) : 0.0;
   if (center) {
-    out[j] = (G - center[j] * (sc->Y - N)) / scale[j];
+    const double Y = scalbn((double)sc->sum_hi, 32 - e) + scalbn((double)sc->sum_lo, -e);
+    out[j] = (G - center[j] * (Y - N)) / scale[j];
   } else {
     out[j] = G;
   }
@@ -513,9 +513,11 @@ __global__ void k_finish_prod(const long long *__restrict__ part, int ksplit, in
     return;
   }
   if (has_scaling) {
+    double C = 0;
+    for (int b = 0; b < SUMCZ_BLOCKS; b++) C += sc->cpart[b];
     double R = combine8(part, l, 1, 0, ksplit, nlines_pad, sc->e[0]);
     double Nw = use_na ? combine8(part, l, 0, 1, ksplit, nlines_pad, sc->e[1]) : 0.0;
-    full[l] = (R + Nw) - sc->C;
+    full[l] = (R + Nw) - C;
   } else {
     full[l] = combine8(part, l, 1, use_na ? -3 : 0, ksplit, nlines_pad, sc->e[0]);  // R - 3N, exact
   }
@@ -550,6 +552,21 @@ static int hb_bits(int maxmult) {
 static int run_pmv(bsg_view *v, const uint8_t *P, int64_t stride, int L, const int *lines, int nlines,
                    const uint8_t *dig1, const uint8_t *dig2, const uint8_t *na_flags, int use_na, Args *out_args,
                    cudaStream_t s) {
+  // variant: BSG_PMV_VARIANT = "<consumer warps>x<ring chunks>" (tuning knob; default chosen from measurements)
+  static int var_cw = 0, var_r = 0;
+  if (!var_cw) {
+    var_cw = 11;
+    var_r = 2;
+    const char *ev = getenv("BSG_PMV_VARIANT");
+    int cw = 0, r = 0;
+    if (ev && sscanf(ev, "%dx%d", &cw, &r) == 2) {
+      if ((cw == 11 && (r == 2 || r == 3)) || (cw == 15 && (r == 2 || r == 3)) || (cw == 7 && r == 4)) {
+        var_cw = cw;
+        var_r = r;
+      }
+    }
+  }
+  const int GROUP = var_cw * 32;
   Args a;
   a.P = P;
   a.stride = stride;
@@ -574,14 +591,24 @@ static int run_pmv(bsg_view *v, const uint8_t *P, int64_t stride, int L, const i
   BSG_TRY(v->s_part.ensure((size_t)a.ksplit * a.nlines_pad * 16 * sizeof(long long)));
   a.part = v->s_part.as<long long>();
   const int mode = !use_na ? 0 : (dig2 ? 2 : 1);
-  auto kern = mode == 0 ? k_pmv<0> : (mode == 1 ? k_pmv<1> : k_pmv<2>);
+  void (*kern)(const Args) = nullptr;
+#define PMV_PICK(CWv, Rv)                                                                       \
+  if (var_cw == CWv && var_r == Rv)                                                             \
+    kern = mode == 0 ? k_pmv<0, CWv, Rv> : (mode == 1 ? k_pmv<1, CWv, Rv> : k_pmv<2, CWv, Rv>);
+  PMV_PICK(11, 2)
+  PMV_PICK(11, 3)
+  PMV_PICK(15, 2)
+  PMV_PICK(15, 3)
+  PMV_PICK(7, 4)
+#undef PMV_PICK
+  if (!kern) return fail(BSG_ERR_ARG, "unknown k_pmv variant");
   BSG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   int nsm = 148;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, v->h->device);
   int nitems = ngroups * a.ksplit;
   int grid = std::min(nitems, nsm);
   if (g_timing) cudaEventRecord(g_ev0[g_ev_n % EV_POOL], s);
-  kern<<<grid, THREADS, SMEM_BYTES, s>>>(a);
+  kern<<<grid, (var_cw + 1) * 32, SMEM_BYTES, s>>>(a);
   if (g_timing) {
     cudaEventRecord(g_ev1[g_ev_n % EV_POOL], s);
     g_ev_n++;
@@ -729,7 +756,7 @@ int bsg_view_cprodvec_dev(bsg_view *v, const double *x_dev, double *out_dev, voi
   if (!v->row_identity) BSG_CUDA(cudaMemsetAsync(Q, 0, (size_t)n * sizeof(long long), s));
   k_quantise<<<launch_cap(v->nr, 256, 592), 256, 0, s>>>(0, x_dev, nullptr, nullptr, v->nr, v->d_row, sc, Q, nullptr);
   k_digits<<<launch_cap((int64_t)nchunks * 256, 256, 1184), 256, 0, s>>>(Q, n, nchunks, v->s_dig1.as<uint8_t>());
-  k_sum_q<<<1, 1024, 0, s>>>(Q, n, sc);
+  k_sum_q<<<launch_cap(n, 256, 296), 256, 0, s>>>(Q, n, sc);
   count_launch(6);
   Args a;
   BSG_TRY(run_pmv(v, h->A, h->strideA, n, v->d_col, v->nc, v->s_dig1.as<uint8_t>(), nullptr, h->naA, h->has_na, &a, s));
@@ -775,7 +802,7 @@ int bsg_view_prodvec_dev(bsg_view *v, const double *x_dev, double *out_dev, void
   k_quantise<<<launch_cap(v->nc, 256, 592), 256, 0, s>>>(mode, x_dev, v->d_center, v->d_scale, v->nc, v->d_col, sc, Q0, Q1);
   k_digits<<<launch_cap((int64_t)nchunks * 256, 256, 1184), 256, 0, s>>>(Q0, m, nchunks, v->s_dig1.as<uint8_t>());
   if (Q1) k_digits<<<launch_cap((int64_t)nchunks * 256, 256, 1184), 256, 0, s>>>(Q1, m, nchunks, v->s_dig2.as<uint8_t>());
-  if (v->has_scaling) k_sum_cz<<<1, 1024, 0, s>>>(x_dev, v->d_center, v->d_scale, v->nc, sc);
+  if (v->has_scaling) k_sum_cz<<<SUMCZ_BLOCKS, 256, 0, s>>>(x_dev, v->d_center, v->d_scale, v->nc, sc->cpart);
   count_launch(5 + (Q1 ? 1 : 0) + (v->has_scaling ? 1 : 0));
   Args a;
   const int nlines = v->row_identity ? h->n : v->nru;
