@@ -129,16 +129,21 @@ __device__ __forceinline__ void slot_load(Slot &s, const uint8_t *pa, const uint
 // w >= 4: hi bytes) holds 16 codes of each of its 4 lines; d = digits of slice g for those 16 codes (one
 // LDS.128 per word, shared by both sub-tiles), register c <-> codes 4r+c (r = byte of the register).
 // The four MMAs of a word go to four different accumulators: independent chains for the tensor pipe.
-template <int MODE>
+template <int MODE, bool PRE>
 __device__ __forceinline__ void chunk_mma(const Slot &t0, const Slot &t1, uint32_t dig_addr, int (&acc1)[2][4],
                                           int (&acc16)[2][4], int (&accn1)[2][4], int (&accn16)[2][4]) {
   const uint32_t wA0[8] = {t0.alo.x, t0.alo.y, t0.alo.z, t0.alo.w, t0.ahi.x, t0.ahi.y, t0.ahi.z, t0.ahi.w};
   const uint32_t wB0[8] = {t0.blo.x, t0.blo.y, t0.blo.z, t0.blo.w, t0.bhi.x, t0.bhi.y, t0.bhi.z, t0.bhi.w};
   const uint32_t wA1[8] = {t1.alo.x, t1.alo.y, t1.alo.z, t1.alo.w, t1.ahi.x, t1.ahi.y, t1.ahi.z, t1.ahi.w};
   const uint32_t wB1[8] = {t1.blo.x, t1.blo.y, t1.blo.z, t1.blo.w, t1.bhi.x, t1.bhi.y, t1.bhi.z, t1.bhi.w};
+  uint4 dpre[8];
+  if (PRE) {
+#pragma unroll
+    for (int w = 0; w < 8; w++) dpre[w] = lds128(dig_addr + w * 512);
+  }
 #pragma unroll
   for (int w = 0; w < 8; w++) {
-    const uint4 d = lds128(dig_addr + w * 512);
+    const uint4 d = PRE ? dpre[w] : lds128(dig_addr + w * 512);
     const uint32_t a0 = wA0[w], b0 = wB0[w], a1 = wA1[w], b1 = wB1[w];
     const uint32_t a0t = a0 >> 2, b0t = b0 >> 2, a1t = a1 >> 2, b1t = b1 >> 2;
     // codes 4r (x1) and 4r+1 (x1) | codes 4r+2 (x16) and 4r+3 (x16)
@@ -160,7 +165,33 @@ __device__ __forceinline__ void chunk_mma(const Slot &t0, const Slot &t1, uint32
   }
 }
 
-template <int MODE, int CW, int R>
+// One 16-line sub-tile x one chunk with digits already in registers (STRUCT 0: sub-tiles in sequence,
+// the slot is refilled as soon as its own MMAs are issued).
+template <int MODE>
+__device__ __forceinline__ void tile_mma(const Slot &sl, const uint4 (&b1)[8], uint32_t dig2_addr, int (&acc1)[4],
+                                         int (&acc16)[4], int (&accn1)[4], int (&accn16)[4]) {
+  const uint32_t wA[8] = {sl.alo.x, sl.alo.y, sl.alo.z, sl.alo.w, sl.ahi.x, sl.ahi.y, sl.ahi.z, sl.ahi.w};
+  const uint32_t wB[8] = {sl.blo.x, sl.blo.y, sl.blo.z, sl.blo.w, sl.bhi.x, sl.bhi.y, sl.bhi.z, sl.bhi.w};
+#pragma unroll
+  for (int w = 0; w < 8; w++) {
+    const uint32_t a = wA[w], bq = wB[w];
+    const uint32_t at = a >> 2, bt = bq >> 2;
+    mma_u8s8(acc1, a & 0x03030303u, bq & 0x03030303u, at & 0x03030303u, bt & 0x03030303u, b1[w].x, b1[w].y);
+    mma_u8s8(acc16, a & 0x30303030u, bq & 0x30303030u, at & 0x30303030u, bt & 0x30303030u, b1[w].z, b1[w].w);
+    if (MODE != 0) {
+      uint4 d = b1[w];
+      if (MODE == 2) d = lds128(dig2_addr + w * 512);
+      const uint32_t an = a & (a >> 1), bn = bq & (bq >> 1);
+      const uint32_t ant = at & (at >> 1), bnt = bt & (bt >> 1);
+      mma_u8s8(accn1, an & 0x01010101u, bn & 0x01010101u, ant & 0x01010101u, bnt & 0x01010101u, d.x, d.y);
+      mma_u8s8(accn16, an & 0x10101010u, bn & 0x10101010u, ant & 0x10101010u, bnt & 0x10101010u, d.z, d.w);
+    }
+  }
+}
+
+// STRUCT 0: digits preloaded, sub-tiles in sequence, early refill.  1: digits just in time, both sub-tiles
+// interleaved per word (4 independent MMA chains).  2: digits preloaded, interleaved.
+template <int MODE, int CW, int R, int STRUCT>
 __global__ void __launch_bounds__((CW + 1) * 32, 1) k_pmv(const Args a) {
   constexpr int GROUP = CW * 32;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -262,13 +293,27 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_pmv(const Args a) {
           const uint32_t dbase = smem_base + stage * STAGE_BYTES + (g * 4 + q) * 16;
           const int64_t next = (int64_t)(c + par + R) * SEG;
           const bool more = (c + par + R) < c1;
-          if (MODE != 0 && tile_na)
-            chunk_mma<MODE>(ring[par][0], ring[par][1], dbase, acc1, acc16, accn1, accn16);
-          else
-            chunk_mma<0>(ring[par][0], ring[par][1], dbase, acc1, acc16, accn1, accn16);
-          if (more) {
-            slot_load(ring[par][0], pA[0], pB[0], next);
-            slot_load(ring[par][1], pA[1], pB[1], next);
+          if (STRUCT == 0) {
+            uint4 b1[8];
+#pragma unroll
+            for (int w = 0; w < 8; w++) b1[w] = lds128(dbase + w * 512);
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+              if (MODE != 0 && tile_na)
+                tile_mma<MODE>(ring[par][u], b1, dbase + DIG, acc1[u], acc16[u], accn1[u], accn16[u]);
+              else
+                tile_mma<0>(ring[par][u], b1, 0, acc1[u], acc16[u], accn1[u], accn16[u]);
+              if (more) slot_load(ring[par][u], pA[u], pB[u], next);
+            }
+          } else {
+            if (MODE != 0 && tile_na)
+              chunk_mma<MODE, STRUCT == 2>(ring[par][0], ring[par][1], dbase, acc1, acc16, accn1, accn16);
+            else
+              chunk_mma<0, STRUCT == 2>(ring[par][0], ring[par][1], dbase, acc1, acc16, accn1, accn16);
+            if (more) {
+              slot_load(ring[par][0], pA[0], pB[0], next);
+              slot_load(ring[par][1], pA[1], pB[1], next);
+            }
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(empty);
@@ -553,16 +598,18 @@ static int run_pmv(bsg_view *v, const uint8_t *P, int64_t stride, int L, const i
                    const uint8_t *dig1, const uint8_t *dig2, const uint8_t *na_flags, int use_na, Args *out_args,
                    cudaStream_t s) {
   // variant: BSG_PMV_VARIANT = "<consumer warps>x<ring chunks>" (tuning knob; default chosen from measurements)
-  static int var_cw = 0, var_r = 0;
+  static int var_cw = 0, var_r = 0, var_s = 0;
   if (!var_cw) {
-    var_cw = 11;
-    var_r = 2;
+    var_cw = 11;  // measured on B200 (profiles/r01_pmv_variants.md): 11x3s1 1.066 ms, 11x2s0 1.075, 15x2s1 1.078
+    var_r = 3;
+    var_s = 1;
     const char *ev = getenv("BSG_PMV_VARIANT");
-    int cw = 0, r = 0;
-    if (ev && sscanf(ev, "%dx%d", &cw, &r) == 2) {
-      if ((cw == 11 && (r == 2 || r == 3)) || (cw == 15 && (r == 2 || r == 3)) || (cw == 7 && r == 4)) {
+    int cw = 0, r = 0, st = 0;
+    if (ev && sscanf(ev, "%dx%ds%d", &cw, &r, &st) >= 2) {
+      if ((cw == 11 || cw == 15) && (r == 2 || r == 3) && st >= 0 && st <= 2) {
         var_cw = cw;
         var_r = r;
+        var_s = st;
       }
     }
   }
@@ -592,14 +639,15 @@ static int run_pmv(bsg_view *v, const uint8_t *P, int64_t stride, int L, const i
   a.part = v->s_part.as<long long>();
   const int mode = !use_na ? 0 : (dig2 ? 2 : 1);
   void (*kern)(const Args) = nullptr;
-#define PMV_PICK(CWv, Rv)                                                                       \
-  if (var_cw == CWv && var_r == Rv)                                                             \
-    kern = mode == 0 ? k_pmv<0, CWv, Rv> : (mode == 1 ? k_pmv<1, CWv, Rv> : k_pmv<2, CWv, Rv>);
-  PMV_PICK(11, 2)
-  PMV_PICK(11, 3)
-  PMV_PICK(15, 2)
-  PMV_PICK(15, 3)
-  PMV_PICK(7, 4)
+#define PMV_PICK(CWv, Rv, Sv)                                                                   \
+  if (var_cw == CWv && var_r == Rv && var_s == Sv)                                              \
+    kern = mode == 0 ? k_pmv<0, CWv, Rv, Sv> : (mode == 1 ? k_pmv<1, CWv, Rv, Sv> : k_pmv<2, CWv, Rv, Sv>);
+  PMV_PICK(11, 2, 0)
+  PMV_PICK(11, 2, 1)
+  PMV_PICK(11, 2, 2)
+  PMV_PICK(11, 3, 0)
+  PMV_PICK(11, 3, 1)
+  PMV_PICK(15, 2, 1)
 #undef PMV_PICK
   if (!kern) return fail(BSG_ERR_ARG, "unknown k_pmv variant");
   BSG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -671,6 +719,13 @@ int bsg_view_create(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, 
   v->row_identity = is_identity(ind_row, nr, h->n);
   v->col_identity = is_identity(ind_col, nc, h->m);
   v->has_scaling = center != nullptr;
+  if (center) {
+    // center = 0, scale = 1 (the reference's defaults, R/bed-mult-vec.R:23-24): identity scaling, which takes
+    // the path whose missing-value correction cancels exactly in integers
+    bool ident = true;
+    for (int j = 0; j < nc && ident; j++) ident = center[j] == 0.0 && scale[j] == 1.0;
+    if (ident) v->has_scaling = 0;
+  }
   cudaStream_t s = h->stream;
   int rc = BSG_OK;
   std::vector<int> zr, zc, uniq, gat;
@@ -866,7 +921,9 @@ static int cached_view(bsg_bed *h, const int *ind_row, int nr, const int *ind_co
   if (!ind_col) nc = h->m;
   if (nr < 0 || nc < 0) return fail(BSG_ERR_ARG, "negative length");
   if ((center == nullptr) != (scale == nullptr)) return fail(BSG_ERR_ARG, "center and scale must be given together");
-  bool hit = h->cv != nullptr && h->cv->nr == nr && h->cv->nc == nc && (h->cv->has_scaling != 0) == (center != nullptr);
+  // the cached view must have device copies of center / scale to refresh (identity scaling keeps none)
+  bool hit = h->cv != nullptr && h->cv->nr == nr && h->cv->nc == nc && (h->cv->d_center != nullptr) == (center != nullptr) &&
+             (center == nullptr || h->cv->has_scaling != 0);
   if (hit) {
     hit = (ind_row == nullptr) == h->cv_row.empty() || (ind_row && (int)h->cv_row.size() == nr);
     if (hit && ind_row) hit = (int)h->cv_row.size() == nr && memcmp(h->cv_row.data(), ind_row, (size_t)nr * sizeof(int)) == 0;

@@ -142,6 +142,18 @@ int bsg_randomsvd(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, in
                   const double *center, const double *scale, int k, double tol, int maxit, double *d,
                   double *u, double *v, double *center_out, double *scale_out, int *niter, int *nops);
 
+/* Same iteration for a matrix whose SNP columns are sharded over several handles (one per GPU / rank):
+ * every rank calls it with its own shard and the same (ind_row, k, tol).  z_dev is a device buffer of nr
+ * doubles owned by the caller; after each local A (A^T x) the library synchronises its stream and calls
+ * reduce_cb(ctx), which must sum z_dev over the ranks (NCCL all-reduce) and return when the sum is visible
+ * to the device.  ncol_total = number of columns of the whole matrix.  u is replicated, v is this rank's
+ * rows. */
+typedef void (*bsg_reduce_cb)(void *ctx);
+int bsg_randomsvd_ex(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc,
+                     const double *center, const double *scale, int k, double tol, int maxit, double *d,
+                     double *u, double *v, double *center_out, double *scale_out, int *niter, int *nops,
+                     double *z_dev, bsg_reduce_cb reduce_cb, void *ctx, int ncol_total);
+
 /* ---- instrumentation --------------------------------------------------------------------------------- */
 /* kernels launched by this library since load (the bench's gpu_launches claim) */
 int64_t bsg_launch_count(void);

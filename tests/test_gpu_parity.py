@@ -126,8 +126,9 @@ def test_prodvec_equality_with_dense(B, gbed_na, oracle, obed_na, rng):
         ic = rng.choice(M, m, replace=False) + 1
         y_col, y_row = rng.normal(size=m), rng.normal(size=n)
         X = oracle.read_bed_scaled(obed_na, ir, ic, np.zeros(m), np.ones(m))
-        _close(B.bed_prodVec(gbed_na, y_col, ir, ic), X @ y_col, scale=np.abs(X) @ np.abs(y_col) + 1e-9)
-        _close(B.bed_cprodVec(gbed_na, y_row, ir, ic), X.T @ y_row, scale=np.abs(X.T) @ np.abs(y_row) + 1e-9)
+        sa, sb = np.abs(X) @ np.abs(y_col), np.abs(X.T) @ np.abs(y_row)
+        _close(B.bed_prodVec(gbed_na, y_col, ir, ic), X @ y_col, scale=sa + 1e-6 * sa.max() + 1e-300)
+        _close(B.bed_cprodVec(gbed_na, y_row, ir, ic), X.T @ y_row, scale=sb + 1e-6 * sb.max() + 1e-300)
         c, s = rng.normal(size=m), rng.uniform(size=m)
         _close(B.bed_prodVec(gbed_na, y_col, ir, ic, c, s), oracle.bed_prodVec(obed_na, y_col, ir, ic, c, s),
                scale=np.max(np.abs(y_col / s)) * m * 3)
@@ -296,3 +297,29 @@ def test_full_size_properties(B):
     assert abs(lhs - rhs) <= 1e-10 * (np.linalg.norm(y) * np.linalg.norm(Ax))
     x2 = rng.normal(size=m)
     _close(v.prodvec(x + 2 * x2), Ax + 2 * v.prodvec(x2), tol=1e-11, scale=np.max(np.abs(Ax)) * 10)
+
+
+def test_randomsvd_and_grm(B, gbed, gbed_na, oracle, obed, obed_na):
+    # tests/testthat/test-2-bed-clumping-SVD.R:41-57,72-79: singular values vs the dense decomposition and vs
+    # sqrt(eigen(K)); north_star tolerance 1e-6 relative (the reference's own test: 1.5e-8)
+    for g, o, ic in ((gbed_na, obed_na, np.arange(1, 501, 2)), (gbed, obed, np.arange(1, 4543, 3))):
+        ic = ic.astype(np.int32)
+        svd = B.bed_randomSVD(g, ind_col=ic, k=10)
+        want = oracle.bed_randomSVD(o, ind_col=ic, k=10)
+        np.testing.assert_allclose(svd["d"], want["d"], rtol=1e-7)
+        assert np.array_equal(svd["center"], want["center"]) and np.array_equal(svd["scale"], want["scale"])
+        cu = np.abs(np.sum(svd["u"] * want["u"], axis=0))
+        cv = np.abs(np.sum(svd["v"] * want["v"], axis=0))
+        assert cu.min() > 1 - 1e-6 and cv.min() > 1 - 1e-6
+        np.testing.assert_allclose(np.linalg.norm(svd["u"], axis=0), 1.0, rtol=1e-10)
+        K, c, s = B.bed_tcrossprodSelf(g, ind_col=ic)
+        Ko, co, so = oracle.bed_tcrossprodSelf(o, ind_col=ic, block_size=200)
+        np.testing.assert_allclose(K, Ko, rtol=1e-11, atol=1e-9)
+        assert np.array_equal(c, co) and np.array_equal(s, so)
+        ev = np.linalg.eigvalsh(K)[::-1][:10]
+        np.testing.assert_allclose(np.sqrt(ev), svd["d"], rtol=1e-7)
+    if not gbed.has_na:  # colMeans(u) == 0 without missing values (:52)
+        svd = B.bed_randomSVD(gbed, k=5)
+        assert np.max(np.abs(svd["u"].mean(0))) < 1e-10
+    with pytest.raises(ValueError, match="can't be `NULL`"):
+        B.bed_randomSVD(gbed, ind_row=None)
