@@ -349,7 +349,8 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_pmv(const Args a) {
 struct Scal {          // device-resident scalars of one call
   double maxabs[2];    // [0] raw-plane vector, [1] NA-plane vector
   int nonfinite;
-  int e[2];            // Q = rint(v * 2^e)
+  int e[2];            // Q = rint(v * 2^e); written by the scatter path, derived from maxabs on the direct path
+  int hb;              // headroom bits (log2 of the largest index multiplicity)
   double Y;            // sum of the (scattered) vector, for Xt.y
   double C;            // (unused, kept for layout)
   long long sum_hi, sum_lo;
@@ -468,6 +469,121 @@ __global__ void k_digits(const long long *__restrict__ Q, int len, int nchunks, 
   }
 }
 
+// e = 60 - exponent(maxabs) - headroom_bits  ->  |sum of <= 2^hb quantised values| < 2^60
+__device__ __forceinline__ int pick_e(double m, int hb) {
+  int ex = 0;
+  if (m > 0 && isfinite(m)) {
+    frexp(m, &ex);
+    return 60 - ex - hb;
+  }
+  return 0;
+}
+
+// Fused preparation, direct (identity index) path -- pass 1: max |v0|, max |v1|, finiteness and, for X.y with
+// scaling, the per-block partials of C = sum_k c_k z_k.  Fixed grid of SUMCZ_BLOCKS blocks.
+constexpr int SUMCZ_BLOCKS = 128;
+__global__ void k_prep1(int mode, const double *__restrict__ x, const double *__restrict__ center,
+                        const double *__restrict__ scale, int len, int hb, Scal *sc) {
+  __shared__ double sh[32];
+  double m0 = 0, m1 = 0, cz = 0;
+  int bad = 0;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < len; k += gridDim.x * blockDim.x) {
+    double v0, v1;
+    make_vals(mode, x, center, scale, k, v0, v1);
+    if (!isfinite(v0) || !isfinite(v1)) bad = 1;
+    m0 = fmax(m0, fabs(v0));
+    m1 = fmax(m1, fabs(v1));
+    if (mode == 1) cz += center[k] * v0;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    m0 = fmax(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+    m1 = fmax(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+    bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    cz += __shfl_xor_sync(0xffffffffu, cz, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(reinterpret_cast<unsigned long long *>(&sc->maxabs[0]), (unsigned long long)__double_as_longlong(m0));
+    atomicMax(reinterpret_cast<unsigned long long *>(&sc->maxabs[1]), (unsigned long long)__double_as_longlong(m1));
+    if (bad) atomicOr(&sc->nonfinite, 1);
+    sh[threadIdx.x >> 5] = cz;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += sh[w];
+    sc->cpart[blockIdx.x] = t;
+    if (blockIdx.x == 0) sc->hb = hb;
+  }
+}
+
+// pass 2: quantise and lay out the digits straight from the input vector (no Q array).  One thread per
+// 16-byte unit (chunk, w, s, q) as in k_digits; with two planes the thread writes both units.  want_sum: the
+// slice-0 threads also accumulate the exact integer sum of Q (Xt.y needs Y = sum y).
+__global__ void k_prep2(int mode, const double *__restrict__ x, const double *__restrict__ center,
+                        const double *__restrict__ scale, int len, int nchunks, Scal *sc, uint8_t *__restrict__ dig1,
+                        uint8_t *__restrict__ dig2, int want_sum) {
+  const int e0 = pick_e(sc->maxabs[0], sc->hb), e1 = pick_e(sc->maxabs[1], sc->hb);
+  const bool bad = sc->nonfinite != 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    sc->e[0] = e0;
+    sc->e[1] = e1;
+  }
+  long long hi = 0, lo = 0;
+  int64_t total = (int64_t)nchunks * 256;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    int chunk = (int)(t >> 8), unit = (int)(t & 255);
+    int q = unit & 3, s = (unit >> 2) & 7, w = unit >> 5;
+    uint32_t o1[4] = {0, 0, 0, 0}, o2[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        int64_t k = (int64_t)chunk * CODES + (w < 4 ? 64 * q + 16 * w : 256 + 64 * q + 16 * (w - 4)) + 4 * r + c;
+        long long qa = 0, qb = 0;
+        if (k < len && !bad) {
+          double v0, v1;
+          make_vals(mode, x, center, scale, (int)k, v0, v1);
+          qa = __double2ll_rn(scalbn(v0, e0));
+          if (dig2) qb = __double2ll_rn(scalbn(v1, e1));
+        }
+        if (want_sum && s == 0) {
+          hi += qa >> 32;
+          lo += (long long)(unsigned int)(qa & 0xFFFFFFFFll);
+        }
+        int d = 0;
+        long long v = qa;
+        for (int i = 0; i <= s; i++) {
+          d = (int)(signed char)(v & 0xFF);
+          v = (v - d) >> 8;
+        }
+        o1[c] |= (uint32_t)(d & 0xFF) << (8 * r);
+        if (dig2) {
+          v = qb;
+          for (int i = 0; i <= s; i++) {
+            d = (int)(signed char)(v & 0xFF);
+            v = (v - d) >> 8;
+          }
+          o2[c] |= (uint32_t)(d & 0xFF) << (8 * r);
+        }
+      }
+    }
+    reinterpret_cast<uint4 *>(dig1)[t] = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+    if (dig2) reinterpret_cast<uint4 *>(dig2)[t] = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+  }
+  if (want_sum) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      hi += __shfl_xor_sync(0xffffffffu, hi, o);
+      lo += __shfl_xor_sync(0xffffffffu, lo, o);
+    }
+    if ((threadIdx.x & 31) == 0 && (hi | lo)) {
+      atomicAdd(reinterpret_cast<unsigned long long *>(&sc->sum_hi), (unsigned long long)hi);
+      atomicAdd(reinterpret_cast<unsigned long long *>(&sc->sum_lo), (unsigned long long)lo);
+    }
+  }
+}
+
 // exact integer sum of Q (split in 32-bit halves, integer atomics: order independent); Y is formed from
 // (sum_hi, sum_lo) in the finish kernel.
 __global__ void k_sum_q(const long long *__restrict__ Q, int len, Scal *sc) {
@@ -490,7 +606,6 @@ __global__ void k_sum_q(const long long *__restrict__ Q, int len, Scal *sc) {
 
 // C = sum_k c_k * (x_k / s_k): per-block partial sums with a fixed-shape tree, written to cpart[block];
 // the finish kernel adds the SUMCZ_BLOCKS partials in index order -> deterministic.
-constexpr int SUMCZ_BLOCKS = 128;
 __global__ void k_sum_cz(const double *__restrict__ x, const double *__restrict__ center,
                          const double *__restrict__ scale, int len, double *__restrict__ cpart) {
   __shared__ double sh[32];
@@ -805,14 +920,24 @@ int bsg_view_cprodvec_dev(bsg_view *v, const double *x_dev, double *out_dev, voi
   BSG_TRY(v->s_q0.ensure((size_t)n * sizeof(long long)));
   BSG_TRY(v->s_dig1.ensure((size_t)nchunks * DIG));
   long long *Q = v->s_q0.as<long long>();
-  k_scal_reset<<<1, 1, 0, s>>>(sc);
-  k_maxabs<<<launch_cap(v->nr, 256, 592), 256, 0, s>>>(0, x_dev, nullptr, nullptr, v->nr, sc);
-  k_pick_exp<<<1, 1, 0, s>>>(sc, hb_bits(v->row_maxmult));
-  if (!v->row_identity) BSG_CUDA(cudaMemsetAsync(Q, 0, (size_t)n * sizeof(long long), s));
-  k_quantise<<<launch_cap(v->nr, 256, 592), 256, 0, s>>>(0, x_dev, nullptr, nullptr, v->nr, v->d_row, sc, Q, nullptr);
-  k_digits<<<launch_cap((int64_t)nchunks * 256, 256, 1184), 256, 0, s>>>(Q, n, nchunks, v->s_dig1.as<uint8_t>());
-  k_sum_q<<<launch_cap(n, 256, 296), 256, 0, s>>>(Q, n, sc);
-  count_launch(6);
+  const int hb = hb_bits(v->row_maxmult);
+  if (v->row_identity) {
+    // direct path: memset + 2 kernels
+    BSG_CUDA(cudaMemsetAsync(sc, 0, sizeof(Scal), s));
+    k_prep1<<<SUMCZ_BLOCKS, 256, 0, s>>>(0, x_dev, nullptr, nullptr, v->nr, hb, sc);
+    k_prep2<<<launch_cap((int64_t)nchunks * 256, 256, 1184), 256, 0, s>>>(0, x_dev, nullptr, nullptr, n, nchunks, sc,
+                                                                          v->s_dig1.as<uint8_t>(), nullptr, 1);
+    count_launch(2);
+  } else {
+    k_scal_reset<<<1, 1, 0, s>>>(sc);
+    k_maxabs<<<launch_cap(v->nr, 256, 592), 256, 0, s>>>(0, x_dev, nullptr, nullptr, v->nr, sc);
+    k_pick_exp<<<1, 1, 0, s>>>(sc, hb);
+    BSG_CUDA(cudaMemsetAsync(Q, 0, (size_t)n * sizeof(long long), s));
+    k_quantise<<<launch_cap(v->nr, 256, 592), 256, 0, s>>>(0, x_dev, nullptr, nullptr, v->nr, v->d_row, sc, Q, nullptr);
+    k_digits<<<launch_cap((int64_t)nchunks * 256, 256, 1184), 256, 0, s>>>(Q, n, nchunks, v->s_dig1.as<uint8_t>());
+    k_sum_q<<<launch_cap(n, 256, 296), 256, 0, s>>>(Q, n, sc);
+    count_launch(6);
+  }
   Args a;
   BSG_TRY(run_pmv(v, h->A, h->strideA, n, v->d_col, v->nc, v->s_dig1.as<uint8_t>(), nullptr, h->naA, h->has_na, &a, s));
   k_finish_cprod<<<(v->nc + 255) / 256, 256, 0, s>>>(a.part, a.ksplit, a.nlines_pad, v->nc, sc, v->d_center, v->d_scale,
@@ -847,18 +972,26 @@ int bsg_view_prodvec_dev(bsg_view *v, const double *x_dev, double *out_dev, void
   }
   long long *Q0 = v->s_q0.as<long long>();
   long long *Q1 = two ? v->s_q1.as<long long>() : nullptr;
-  k_scal_reset<<<1, 1, 0, s>>>(sc);
-  k_maxabs<<<launch_cap(v->nc, 256, 592), 256, 0, s>>>(mode, x_dev, v->d_center, v->d_scale, v->nc, sc);
-  k_pick_exp<<<1, 1, 0, s>>>(sc, hb_bits(v->col_maxmult));
-  if (!v->col_identity) {
+  const int hb = hb_bits(v->col_maxmult);
+  if (v->col_identity) {
+    BSG_CUDA(cudaMemsetAsync(sc, 0, sizeof(Scal), s));
+    k_prep1<<<SUMCZ_BLOCKS, 256, 0, s>>>(mode, x_dev, v->d_center, v->d_scale, v->nc, hb, sc);
+    k_prep2<<<launch_cap((int64_t)nchunks * 256, 256, 1184), 256, 0, s>>>(
+        mode, x_dev, v->d_center, v->d_scale, m, nchunks, sc, v->s_dig1.as<uint8_t>(),
+        two ? v->s_dig2.as<uint8_t>() : nullptr, 0);
+    count_launch(2);
+  } else {
+    k_scal_reset<<<1, 1, 0, s>>>(sc);
+    k_maxabs<<<launch_cap(v->nc, 256, 592), 256, 0, s>>>(mode, x_dev, v->d_center, v->d_scale, v->nc, sc);
+    k_pick_exp<<<1, 1, 0, s>>>(sc, hb);
     BSG_CUDA(cudaMemsetAsync(Q0, 0, (size_t)m * sizeof(long long), s));
     if (Q1) BSG_CUDA(cudaMemsetAsync(Q1, 0, (size_t)m * sizeof(long long), s));
+    k_quantise<<<launch_cap(v->nc, 256, 592), 256, 0, s>>>(mode, x_dev, v->d_center, v->d_scale, v->nc, v->d_col, sc, Q0, Q1);
+    k_digits<<<launch_cap((int64_t)nchunks * 256, 256, 1184), 256, 0, s>>>(Q0, m, nchunks, v->s_dig1.as<uint8_t>());
+    if (Q1) k_digits<<<launch_cap((int64_t)nchunks * 256, 256, 1184), 256, 0, s>>>(Q1, m, nchunks, v->s_dig2.as<uint8_t>());
+    if (v->has_scaling) k_sum_cz<<<SUMCZ_BLOCKS, 256, 0, s>>>(x_dev, v->d_center, v->d_scale, v->nc, sc->cpart);
+    count_launch(5 + (Q1 ? 1 : 0) + (v->has_scaling ? 1 : 0));
   }
-  k_quantise<<<launch_cap(v->nc, 256, 592), 256, 0, s>>>(mode, x_dev, v->d_center, v->d_scale, v->nc, v->d_col, sc, Q0, Q1);
-  k_digits<<<launch_cap((int64_t)nchunks * 256, 256, 1184), 256, 0, s>>>(Q0, m, nchunks, v->s_dig1.as<uint8_t>());
-  if (Q1) k_digits<<<launch_cap((int64_t)nchunks * 256, 256, 1184), 256, 0, s>>>(Q1, m, nchunks, v->s_dig2.as<uint8_t>());
-  if (v->has_scaling) k_sum_cz<<<SUMCZ_BLOCKS, 256, 0, s>>>(x_dev, v->d_center, v->d_scale, v->nc, sc->cpart);
-  count_launch(5 + (Q1 ? 1 : 0) + (v->has_scaling ? 1 : 0));
   Args a;
   const int nlines = v->row_identity ? h->n : v->nru;
   BSG_TRY(run_pmv(v, h->B, h->strideB, m, v->d_rows_unique, nlines, v->s_dig1.as<uint8_t>(),
