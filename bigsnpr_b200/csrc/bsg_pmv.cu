@@ -61,7 +61,7 @@ struct Args {
   const uint8_t *dig2;   // NA-plane digits (null = same as dig1)
   const uint8_t *na_flags;  // per physical line (null = assume missing values anywhere)
   int use_na;            // 0: matrix has no missing value, skip the NA plane
-  long long *part;       // [ksplit][nlines_pad][16]: 8 raw-plane slices, 8 NA-plane slices
+  long long *part;       // [nlines_pad][16] zeroed accumulators: 8 raw-plane slices, 8 NA-plane slices
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -329,14 +329,18 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_pmv(const Args a) {
 #pragma unroll
         for (int hrow = 0; hrow < 2; hrow++) {
           const int row = group * GROUP + warp * 32 + u * 16 + g + 8 * hrow;
-          long long *dst = a.part + ((int64_t)ks * a.nlines_pad + row) * 16 + 2 * q;
-          longlong2 v, vn;
-          v.x = (long long)acc1[u][2 * hrow] + (long long)(acc16[u][2 * hrow] >> 4);
-          v.y = (long long)acc1[u][2 * hrow + 1] + (long long)(acc16[u][2 * hrow + 1] >> 4);
-          vn.x = (long long)accn1[u][2 * hrow] + (long long)(accn16[u][2 * hrow] >> 4);
-          vn.y = (long long)accn1[u][2 * hrow + 1] + (long long)(accn16[u][2 * hrow + 1] >> 4);
-          *reinterpret_cast<longlong2 *>(dst) = v;
-          if (MODE != 0) *reinterpret_cast<longlong2 *>(dst + 8) = vn;
+          // integer adds commute: the k-splits of a line accumulate in any order to the same exact sum
+          unsigned long long *dst = reinterpret_cast<unsigned long long *>(a.part) + (int64_t)row * 16 + 2 * q;
+          long long vx = (long long)acc1[u][2 * hrow] + (long long)(acc16[u][2 * hrow] >> 4);
+          long long vy = (long long)acc1[u][2 * hrow + 1] + (long long)(acc16[u][2 * hrow + 1] >> 4);
+          atomicAdd(dst, (unsigned long long)vx);
+          atomicAdd(dst + 1, (unsigned long long)vy);
+          if (MODE != 0) {
+            long long nx = (long long)accn1[u][2 * hrow] + (long long)(accn16[u][2 * hrow] >> 4);
+            long long ny = (long long)accn1[u][2 * hrow + 1] + (long long)(accn16[u][2 * hrow + 1] >> 4);
+            atomicAdd(dst + 8, (unsigned long long)nx);
+            atomicAdd(dst + 9, (unsigned long long)ny);
+          }
         }
       }
     }
@@ -530,11 +534,18 @@ __global__ void k_prep2(int mode, const double *__restrict__ x, const double *__
     sc->e[1] = e1;
   }
   long long hi = 0, lo = 0;
-  int64_t total = (int64_t)nchunks * 256;
+  // 2^e as a double when it is a normal number (always, unless the vector is denormal-small or huge)
+  const bool fast0 = e0 > -1000 && e0 < 1000, fast1 = e1 > -1000 && e1 < 1000;
+  const double f0 = fast0 ? scalbn(1.0, e0) : 0.0, f1 = fast1 ? scalbn(1.0, e1) : 0.0;
+  int64_t total = (int64_t)nchunks * 32;  // (chunk, w, q)
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    int chunk = (int)(t >> 8), unit = (int)(t & 255);
-    int q = unit & 3, s = (unit >> 2) & 7, w = unit >> 5;
-    uint32_t o1[4] = {0, 0, 0, 0}, o2[4] = {0, 0, 0, 0};
+    const int chunk = (int)(t >> 5), wq = (int)(t & 31);
+    const int q = wq & 3, w = wq >> 2;
+    uint32_t o1[8][4], o2[8][4];
+#pragma unroll
+    for (int sl = 0; sl < 8; sl++)
+#pragma unroll
+      for (int c = 0; c < 4; c++) o1[sl][c] = o2[sl][c] = 0;
 #pragma unroll
     for (int c = 0; c < 4; c++) {
 #pragma unroll
@@ -544,32 +555,32 @@ __global__ void k_prep2(int mode, const double *__restrict__ x, const double *__
         if (k < len && !bad) {
           double v0, v1;
           make_vals(mode, x, center, scale, (int)k, v0, v1);
-          qa = __double2ll_rn(scalbn(v0, e0));
-          if (dig2) qb = __double2ll_rn(scalbn(v1, e1));
+          qa = __double2ll_rn(fast0 ? v0 * f0 : scalbn(v0, e0));
+          if (dig2) qb = __double2ll_rn(fast1 ? v1 * f1 : scalbn(v1, e1));
         }
-        if (want_sum && s == 0) {
+        if (want_sum) {
           hi += qa >> 32;
           lo += (long long)(unsigned int)(qa & 0xFFFFFFFFll);
         }
-        int d = 0;
-        long long v = qa;
-        for (int i = 0; i <= s; i++) {
-          d = (int)(signed char)(v & 0xFF);
-          v = (v - d) >> 8;
-        }
-        o1[c] |= (uint32_t)(d & 0xFF) << (8 * r);
-        if (dig2) {
-          v = qb;
-          for (int i = 0; i <= s; i++) {
-            d = (int)(signed char)(v & 0xFF);
-            v = (v - d) >> 8;
+#pragma unroll
+        for (int sl = 0; sl < 8; sl++) {
+          int d = (int)(signed char)(qa & 0xFF);
+          qa = (qa - d) >> 8;
+          o1[sl][c] |= (uint32_t)(d & 0xFF) << (8 * r);
+          if (dig2) {
+            int d2 = (int)(signed char)(qb & 0xFF);
+            qb = (qb - d2) >> 8;
+            o2[sl][c] |= (uint32_t)(d2 & 0xFF) << (8 * r);
           }
-          o2[c] |= (uint32_t)(d & 0xFF) << (8 * r);
         }
       }
     }
-    reinterpret_cast<uint4 *>(dig1)[t] = make_uint4(o1[0], o1[1], o1[2], o1[3]);
-    if (dig2) reinterpret_cast<uint4 *>(dig2)[t] = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+#pragma unroll
+    for (int sl = 0; sl < 8; sl++) {
+      const int64_t unit = (int64_t)chunk * 256 + (w * 8 + sl) * 4 + q;
+      reinterpret_cast<uint4 *>(dig1)[unit] = make_uint4(o1[sl][0], o1[sl][1], o1[sl][2], o1[sl][3]);
+      if (dig2) reinterpret_cast<uint4 *>(dig2)[unit] = make_uint4(o2[sl][0], o2[sl][1], o2[sl][2], o2[sl][3]);
+    }
   }
   if (want_sum) {
 #pragma unroll
@@ -623,19 +634,16 @@ __global__ void k_sum_cz(const double *__restrict__ x, const double *__restrict_
   }
 }
 
-// sum over the k-splits and the 8 digit slices of (raw-plane * c0 + NA-plane * c1), exact in integers per
-// slice, then one top-down fp64 sum of the 8 scaled slice totals.
-__device__ __forceinline__ double combine8(const long long *__restrict__ part, int64_t line, int c0, int c1, int ksplit,
-                                           int64_t nlines_pad, int e) {
+// (raw-plane * c0 + NA-plane * c1) per digit slice, exact in integers, then one top-down fp64 sum of the 8
+// scaled slice totals.
+__device__ __forceinline__ double combine8(const long long *__restrict__ part, int64_t line, int c0, int c1, int e) {
+  const long long *p = part + line * 16;
   double acc = 0;
 #pragma unroll
   for (int s = 7; s >= 0; s--) {
     long long v = 0;
-    for (int ks = 0; ks < ksplit; ks++) {
-      const long long *p = part + ((int64_t)ks * nlines_pad + line) * 16;
-      if (c0) v += c0 * p[s];
-      if (c1) v += c1 * p[8 + s];
-    }
+    if (c0) v += c0 * p[s];
+    if (c1) v += c1 * p[8 + s];
     acc += scalbn((double)v, 8 * s - e);
   }
   return acc;
@@ -652,8 +660,8 @@ __global__ void k_finish_cprod(const long long *__restrict__ part, int ksplit, i
     return;
   }
   const int e = sc->e[0];
-  double G = combine8(part, j, 1, use_na ? -3 : 0, ksplit, nlines_pad, e);  // R - 3N, exact
-  double N = use_na ? combine8(part, j, 0, 1, ksplit, nlines_pad, e) : 0.0;
+  double G = combine8(part, j, 1, use_na ? -3 : 0, e);  // R - 3N, exact
+  double N = use_na ? combine8(part, j, 0, 1, e) : 0.0;
   if (center) {
     const double Y = scalbn((double)sc->sum_hi, 32 - e) + scalbn((double)sc->sum_lo, -e);
     out[j] = (G - center[j] * (Y - N)) / scale[j];
@@ -675,11 +683,11 @@ __global__ void k_finish_prod(const long long *__restrict__ part, int ksplit, in
   if (has_scaling) {
     double C = 0;
     for (int b = 0; b < SUMCZ_BLOCKS; b++) C += sc->cpart[b];
-    double R = combine8(part, l, 1, 0, ksplit, nlines_pad, sc->e[0]);
-    double Nw = use_na ? combine8(part, l, 0, 1, ksplit, nlines_pad, sc->e[1]) : 0.0;
+    double R = combine8(part, l, 1, 0, sc->e[0]);
+    double Nw = use_na ? combine8(part, l, 0, 1, sc->e[1]) : 0.0;
     full[l] = (R + Nw) - C;
   } else {
-    full[l] = combine8(part, l, 1, use_na ? -3 : 0, ksplit, nlines_pad, sc->e[0]);  // R - 3N, exact
+    full[l] = combine8(part, l, 1, use_na ? -3 : 0, sc->e[0]);  // R - 3N, exact
   }
 }
 
@@ -750,8 +758,9 @@ static int run_pmv(bsg_view *v, const uint8_t *P, int64_t stride, int L, const i
   a.dig2 = dig2;
   a.na_flags = na_flags;
   a.use_na = use_na;
-  BSG_TRY(v->s_part.ensure((size_t)a.ksplit * a.nlines_pad * 16 * sizeof(long long)));
+  BSG_TRY(v->s_part.ensure((size_t)a.nlines_pad * 16 * sizeof(long long)));
   a.part = v->s_part.as<long long>();
+  BSG_CUDA(cudaMemsetAsync(a.part, 0, (size_t)a.nlines_pad * 16 * sizeof(long long), s));
   const int mode = !use_na ? 0 : (dig2 ? 2 : 1);
   void (*kern)(const Args) = nullptr;
 #define PMV_PICK(CWv, Rv, Sv)                                                                   \
@@ -925,7 +934,7 @@ int bsg_view_cprodvec_dev(bsg_view *v, const double *x_dev, double *out_dev, voi
     // direct path: memset + 2 kernels
     BSG_CUDA(cudaMemsetAsync(sc, 0, sizeof(Scal), s));
     k_prep1<<<SUMCZ_BLOCKS, 256, 0, s>>>(0, x_dev, nullptr, nullptr, v->nr, hb, sc);
-    k_prep2<<<launch_cap((int64_t)nchunks * 256, 256, 1184), 256, 0, s>>>(0, x_dev, nullptr, nullptr, n, nchunks, sc,
+    k_prep2<<<launch_cap((int64_t)nchunks * 32, 128, 1184), 128, 0, s>>>(0, x_dev, nullptr, nullptr, n, nchunks, sc,
                                                                           v->s_dig1.as<uint8_t>(), nullptr, 1);
     count_launch(2);
   } else {
@@ -976,7 +985,7 @@ int bsg_view_prodvec_dev(bsg_view *v, const double *x_dev, double *out_dev, void
   if (v->col_identity) {
     BSG_CUDA(cudaMemsetAsync(sc, 0, sizeof(Scal), s));
     k_prep1<<<SUMCZ_BLOCKS, 256, 0, s>>>(mode, x_dev, v->d_center, v->d_scale, v->nc, hb, sc);
-    k_prep2<<<launch_cap((int64_t)nchunks * 256, 256, 1184), 256, 0, s>>>(
+    k_prep2<<<launch_cap((int64_t)nchunks * 32, 128, 1184), 128, 0, s>>>(
         mode, x_dev, v->d_center, v->d_scale, m, nchunks, sc, v->s_dig1.as<uint8_t>(),
         two ? v->s_dig2.as<uint8_t>() : nullptr, 0);
     count_launch(2);
