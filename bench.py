@@ -161,6 +161,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--na-rate", type=float, default=0.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-svd", action="store_true", help="skip the bed_randomSVD wall-time leg")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -303,6 +304,29 @@ def main():
     # agreement of the two paths (device-resident vs host call) on this rank's data
     chk = float((out.cpu() - outh).abs().max().item()) if world == 1 else None
 
+    # ---------------- second headline metric: bed_randomSVD wall time (not part of `value`) ----------------
+    svd_info = None
+    if not args.no_svd:
+        k = 10 if args.workload == "cfg2" else 20
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        if world > 1:
+            from bigsnpr_b200.dist import randomsvd_sharded
+
+            sv = randomsvd_sharded(g, int(tg.item() / n), k=k)
+        else:
+            sv = B.bed_randomSVD(g, k=k)
+        tsvd = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tsvd, op=dist.ReduceOp.MAX)
+        svd_info = {"k": k, "tol": 1e-4, "wall_s": float(tsvd.item()), "nops": sv["nops"], "niter": sv["niter"],
+                    "d_top3": [float(v) for v in sv["d"][:3]],
+                    "packed_bytes_read": float(alg_bytes) * (2 * sv["nops"] + k + 1),
+                    "note": "bed_randomSVD(fun.scaling = bed_scaleBinom), Lanczos on the device; wall time includes "
+                            "the scaling pass, the iteration and the k products for v"}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
@@ -333,7 +357,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_val, "unit": "genotypes/s", "h2d_bytes_per_step": 3 * 8 * m_loc,
                     "d2h_bytes_per_step": 8 * n, "steps": e2e_steps, "max_abs_diff_vs_resident": chk},
-            "clocks": clocks, "gpu_launches": launches,
+            "clocks": clocks, "gpu_launches": launches, "svd": svd_info,
         }
         print(json.dumps(line), flush=True)
     view.close()

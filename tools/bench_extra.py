@@ -1,0 +1,59 @@
+#!/usr/bin/env python
+"""Timings of the other hot-path rows on shapes scaled from BASELINE.json configs[2] (snp_cor) and configs[3]
+(bed_tcrossprodSelf), plus colstats/counts.  Prints one JSON line per op.  Not the driver's bench."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bigsnpr_b200 as B  # noqa: E402
+
+
+def timeit(f, reps=1):
+    import torch
+
+    f()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        r = f()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / reps, r
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cor-n", type=int, default=100000)
+    ap.add_argument("--cor-m", type=int, default=20000)
+    ap.add_argument("--size", type=int, default=500)
+    ap.add_argument("--grm-n", type=int, default=10000)
+    ap.add_argument("--grm-m", type=int, default=50000)
+    a = ap.parse_args()
+    # --- snp_cor / ld_scores (configs[2] is 100,000 x 200,000, size 500: 9.99e7 pairs)
+    g = B.Bed.synthetic(a.cor_n, a.cor_m, seed=20250927, layouts=B.LAYOUT_SNP_MAJOR)
+    t, (p, i, x) = timeit(lambda: B.bed_cor(g, size=a.size))
+    pairs = int(p[-1]) - a.cor_m
+    print(json.dumps({"op": "bed_cor", "n": a.cor_n, "m": a.cor_m, "size": a.size, "pairs": pairs, "seconds": t,
+                      "pairs_per_s": pairs / t, "useful_flops": 2.0 * a.cor_n * pairs,
+                      "cfg3_extrapolated_s": t * 99874750 / max(pairs, 1)}), flush=True)
+    t, ld = timeit(lambda: B.bed_ld_scores(g, size=a.size))
+    print(json.dumps({"op": "bed_ld_scores", "n": a.cor_n, "m": a.cor_m, "size": a.size, "seconds": t}), flush=True)
+    t, _ = timeit(lambda: B.bed_counts(g))
+    print(json.dumps({"op": "bed_counts(all)", "seconds": t}), flush=True)
+    g.close()
+    # --- bed_tcrossprodSelf (configs[3] is 10,000 x 1,000,000)
+    g = B.Bed.synthetic(a.grm_n, a.grm_m, seed=20250928, layouts=B.LAYOUT_SNP_MAJOR)
+    t, (K, c, s) = timeit(lambda: B.bed_tcrossprodSelf(g))
+    print(json.dumps({"op": "bed_tcrossprodSelf", "n": a.grm_n, "m": a.grm_m, "seconds": t,
+                      "useful_flops": float(a.grm_n) * (a.grm_n + 1) * a.grm_m,
+                      "tflops": float(a.grm_n) * (a.grm_n + 1) * a.grm_m / t / 1e12,
+                      "cfg4_extrapolated_s": t * 1_000_000 / a.grm_m}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
