@@ -12,8 +12,11 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include <vector>
 
+#include "bsg_gram.cuh"
 #include "bsg_internal.cuh"
 
 namespace bsg {
@@ -36,6 +39,42 @@ __global__ void k_compact(const uint8_t *__restrict__ A, int64_t strideA, const 
       }
     }
     reinterpret_cast<uint32_t *>(out + j * stride_out)[wq] = v;
+  }
+}
+
+// per-line counts of codes {0,1,2,3} over the first L codes (pads are code 0), one warp per line
+__global__ void k_line_counts_ext(const uint8_t *__restrict__ P, int64_t stride, int nlines, int L,
+                                  int32_t *__restrict__ cnt, uint8_t *__restrict__ na) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  int nw = (gridDim.x * blockDim.x) >> 5;
+  int64_t nvec = ((int64_t)(L + 3) / 4 + 15) / 16;
+  for (int l = warp; l < nlines; l += nw) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(P + (int64_t)l * stride);
+    int c1 = 0, c2 = 0, c3 = 0;
+    for (int64_t v = lane; v < nvec; v += 32) {
+      uint4 q = __ldg(src + v);
+      uint32_t ws[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        uint32_t lo = ws[k] & 0x55555555u, hi = (ws[k] >> 1) & 0x55555555u;
+        c3 += __popc(lo & hi);
+        c1 += __popc(lo & ~hi);
+        c2 += __popc(hi & ~lo);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+      c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+      c3 += __shfl_xor_sync(0xffffffffu, c3, o);
+    }
+    if (lane == 0) {
+      cnt[4 * (int64_t)l + 0] = L - c1 - c2 - c3;
+      cnt[4 * (int64_t)l + 1] = c1;
+      cnt[4 * (int64_t)l + 2] = c2;
+      cnt[4 * (int64_t)l + 3] = c3;
+      na[l] = c3 > 0;
+    }
   }
 }
 
@@ -142,6 +181,180 @@ __global__ void k_ld_reduce(const double *__restrict__ band, const long long *__
   res[j] = acc;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Tensor-pipe path: integer Gram tiles (bsg_gram.cuh) + per-pair fp64 epilogue.
+// ---------------------------------------------------------------------------------------------------
+namespace gram {
+
+struct Frag {
+  uint4 a[4];  // A lines: (mt 0: g, g+8), (mt 1: g, g+8)
+  uint4 b[4];  // B lines: nt 0..3, line g
+};
+
+__device__ __forceinline__ void frag_load(Frag &f, const uint8_t *const (&pa)[4], const uint8_t *const (&pb)[4], int64_t off) {
+#pragma unroll
+  for (int l = 0; l < 4; l++) f.a[l] = ldg128(pa[l] + off);
+#pragma unroll
+  for (int l = 0; l < 4; l++) f.b[l] = ldg128(pb[l] + off);
+}
+
+template <int PA, int PB, bool RAW>
+__device__ __forceinline__ void frag_mma(const Frag &f, int (&acc)[2][4][4]) {
+  const uint32_t *aw[4] = {&f.a[0].x, &f.a[1].x, &f.a[2].x, &f.a[3].x};
+  const uint32_t *bw[4] = {&f.b[0].x, &f.b[1].x, &f.b[2].x, &f.b[3].x};
+#pragma unroll
+  for (int w = 0; w < 4; w++) {
+    uint32_t wa[4], wb[4];
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+      wa[l] = RAW ? aw[l][w] : plane_word<PA>(aw[l][w]);
+      wb[l] = RAW ? bw[l][w] : plane_word<PB>(bw[l][w]);
+    }
+#pragma unroll
+    for (int cp = 0; cp < 2; cp++) {
+      const int s0 = 4 * cp, s1 = 4 * cp + 2;
+      uint32_t b0[4], b1[4];
+#pragma unroll
+      for (int nt = 0; nt < 4; nt++) {
+        b0[nt] = (wb[nt] >> s0) & 0x03030303u;
+        b1[nt] = (wb[nt] >> s1) & 0x03030303u;
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++) {
+        const uint32_t a0 = (wa[2 * mt] >> s0) & 0x03030303u, a1 = (wa[2 * mt + 1] >> s0) & 0x03030303u;
+        const uint32_t a2 = (wa[2 * mt] >> s1) & 0x03030303u, a3 = (wa[2 * mt + 1] >> s1) & 0x03030303u;
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) mma_u8u8(acc[mt][nt], a0, a1, a2, a3, b0[nt], b1[nt]);
+      }
+    }
+  }
+}
+
+// one product over the whole contraction range, double-buffered fragments
+template <int PA, int PB, bool RAW>
+__device__ __forceinline__ void gram_product(const uint8_t *const (&pa)[4], const uint8_t *const (&pb)[4], int nchunks,
+                                             int *__restrict__ out, int row0, int col0, int g, int q) {
+  int acc[2][4][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+      for (int k = 0; k < 4; k++) acc[mt][nt][k] = 0;
+  Frag f0, f1;
+  frag_load(f0, pa, pb, 0);
+  for (int c = 0; c < nchunks; c += 2) {
+    if (c + 1 < nchunks) frag_load(f1, pa, pb, (int64_t)(c + 1) * CHUNK);
+    frag_mma<PA, PB, RAW>(f0, acc);
+    if (c + 2 < nchunks) frag_load(f0, pa, pb, (int64_t)(c + 2) * CHUNK);
+    if (c + 1 < nchunks) frag_mma<PA, PB, RAW>(f1, acc);
+  }
+#pragma unroll
+  for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++) {
+      const int r = row0 + mt * 16 + g, cc = col0 + nt * 8 + 2 * q;
+      *reinterpret_cast<int2 *>(out + (int64_t)r * TN + cc) = make_int2(acc[mt][nt][0], acc[mt][nt][1]);
+      *reinterpret_cast<int2 *>(out + (int64_t)(r + 8) * TN + cc) = make_int2(acc[mt][nt][2], acc[mt][nt][3]);
+    }
+}
+
+// grid = tiles; block = 8 warps (4 x 2), each warp a 32 x 32 block of line pairs over the whole k range
+__global__ void __launch_bounds__(THREADS, 1) k_gram(const uint8_t *__restrict__ P, int64_t stride, int nlines,
+                                                     int nchunks, const Tile *__restrict__ tiles, int *__restrict__ sums) {
+  const Tile t = tiles[blockIdx.x];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+  const int wm = warp >> 1, wn = warp & 1;
+  const uint8_t *pa[4], *pb[4];
+#pragma unroll
+  for (int l = 0; l < 4; l++) {
+    int la = t.i0 + wm * 32 + (l >> 1) * 16 + g + 8 * (l & 1);
+    int lb = t.j0 + wn * 32 + l * 8 + g;
+    la = min(max(la, 0), nlines - 1);
+    lb = min(max(lb, 0), nlines - 1);
+    pa[l] = P + (int64_t)la * stride + 16 * q;
+    pb[l] = P + (int64_t)lb * stride + 16 * q;
+  }
+  int *out = sums + t.out;
+  const int row0 = wm * 32, col0 = wn * 32;
+  if (t.mode == 0) {
+    gram_product<PL_A, PL_A, true>(pa, pb, nchunks, out, row0, col0, g, q);
+  } else {
+    // products of the pairwise-complete statistics: aa (xySum), bb (nona), ab (xSum over valid y), ba, hb, bh
+    gram_product<PL_A, PL_A, false>(pa, pb, nchunks, out + 0 * TM * TN, row0, col0, g, q);
+    gram_product<PL_B, PL_B, false>(pa, pb, nchunks, out + 1 * TM * TN, row0, col0, g, q);
+    gram_product<PL_A, PL_B, false>(pa, pb, nchunks, out + 2 * TM * TN, row0, col0, g, q);
+    gram_product<PL_B, PL_A, false>(pa, pb, nchunks, out + 3 * TM * TN, row0, col0, g, q);
+    gram_product<PL_H, PL_B, false>(pa, pb, nchunks, out + 4 * TM * TN, row0, col0, g, q);
+    gram_product<PL_B, PL_H, false>(pa, pb, nchunks, out + 5 * TM * TN, row0, col0, g, q);
+  }
+}
+
+struct RowBlock {
+  int first_tile;  // index of the tile holding column block jb0 (relative to the batch)
+  int jb0;         // first column block
+};
+
+// fp64 epilogue per pair (j0, j0-1-k), same operation order as src/corr.cpp:77-80 / src/ld-scores.cpp:63-66
+template <bool LD>
+__global__ void k_cor_from_sums(const int *__restrict__ sums, const Tile *__restrict__ tiles,
+                                const RowBlock *__restrict__ rbs, int ib0, int j0_begin, int j0_end,
+                                const int *__restrict__ wlen, const long long *__restrict__ boff,
+                                const int32_t *__restrict__ cnt, int nrow, int npad, const double *__restrict__ thr,
+                                double *__restrict__ band, uint8_t *__restrict__ keep) {
+  const long long first = boff[j0_begin], total = boff[j0_end] - first;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    // locate j0 by binary search on boff
+    int lo = j0_begin, hi = j0_end - 1;
+    const long long o = first + t;
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (boff[mid] <= o) lo = mid; else hi = mid - 1;
+    }
+    const int j0 = lo, k = (int)(o - boff[j0]), j = j0 - 1 - k;
+    const int ib = j0 / TM - ib0;
+    const RowBlock rb = rbs[ib];
+    const Tile tl = tiles[rb.first_tile + (j / TN - rb.jb0)];
+    const int *sp = sums + tl.out + (int64_t)(j0 - tl.i0) * TN + (j - tl.j0);
+    double nona_d, xSum, xxSum, ySum, yySum, xySum;
+    int nona;
+    if (tl.mode == 0) {
+      nona = nrow;
+      const int32_t *cx = cnt + 4 * (int64_t)j0, *cy = cnt + 4 * (int64_t)j;
+      xSum = (double)cx[1] + 2.0 * (double)cx[2];
+      xxSum = (double)cx[1] + 4.0 * (double)cx[2];
+      ySum = (double)cy[1] + 2.0 * (double)cy[2];
+      yySum = (double)cy[1] + 4.0 * (double)cy[2];
+      xySum = (double)sp[0];
+    } else {
+      const int S = TM * TN;
+      const int aa = sp[0], bb = sp[S], ab = sp[2 * S], ba = sp[3 * S], hb = sp[4 * S], bh = sp[5 * S];
+      nona = bb - npad;  // pads are valid zeros on both sides
+      xSum = (double)ab;
+      xxSum = (double)ab + 2.0 * (double)hb;
+      ySum = (double)ba;
+      yySum = (double)ba + 2.0 * (double)bh;
+      xySum = (double)aa;
+    }
+    (void)nona_d;
+    const double num = xySum - xSum * ySum / nona;
+    const double deno_x = xxSum - xSum * xSum / nona;
+    const double deno_y = yySum - ySum * ySum / nona;
+    if (LD) {
+      band[o] = num * num / (deno_x * deno_y);
+    } else {
+      double r = num / sqrt(deno_x * deno_y);
+      bool kp = isnan(r) || fabs(r) > thr[nona > 0 ? nona - 1 : 0];
+      if (r > 1) r = 1; else if (r < -1) r = -1;
+      band[o] = r;
+      keep[o] = kp;
+    }
+  }
+}
+
+}  // namespace gram
+
 struct Window {
   std::vector<int> wlen, reach;
   std::vector<long long> boff;
@@ -203,8 +416,8 @@ static int cor_common(bsg_bed *h, const int *ind_row, int nr, const int *ind_col
   BSG_TRY(upload_index(h, ind_row, nr, h->n, h->w_idx_row, &d_row));
   BSG_TRY(upload_index(h, ind_col, nc, h->m, h->w_idx_col, &d_col));
   build_window(pos, nc, size, w);
-  int64_t stride = round_up(((int64_t)nr + 3) / 4, 16);
-  if (stride < 16) stride = 16;
+  int64_t stride = round_up(((int64_t)nr + 3) / 4, 64);
+  if (stride < 64) stride = 64;
   BSG_CUDA(cudaMalloc((void **)&sc.M, (size_t)stride * (nc > 0 ? nc : 1)));
   if (nc > 0) {
     int64_t work = (int64_t)nc * (stride / 4);
@@ -221,12 +434,111 @@ static int cor_common(bsg_bed *h, const int *ind_row, int nr, const int *ind_col
     BSG_TRY(to_dev(&sc.thr, t, s));
     BSG_CUDA(cudaMalloc((void **)&sc.keep, (size_t)(w.total ? w.total : 1)));
   }
-  if (nc > 0) {
+  static int use_popc = -1;
+  if (use_popc < 0) {
+    const char *ev = getenv("BSG_COR_POPC");
+    use_popc = (ev && ev[0] == '1') ? 1 : 0;
+  }
+  if (nc > 0 && use_popc) {
     if (ld)
       k_cor_pairs<true><<<nc, 256, 0, s>>>(sc.M, stride, nr, nc, sc.wlen, sc.boff, nullptr, sc.band, nullptr);
     else
       k_cor_pairs<false><<<nc, 256, 0, s>>>(sc.M, stride, nr, nc, sc.wlen, sc.boff, sc.thr, sc.band, sc.keep);
     count_launch();
+  } else if (nc > 0 && w.total > 0) {
+    using namespace gram;
+    // per-line counts over the selected rows (exact) and missing-value flags
+    int32_t *d_cnt = nullptr;
+    uint8_t *d_na = nullptr;
+    BSG_CUDA(cudaMalloc((void **)&d_cnt, (size_t)nc * 4 * sizeof(int32_t)));
+    BSG_CUDA(cudaMalloc((void **)&d_na, (size_t)nc));
+    struct Guard {
+      void *a, *b, *c, *d, *e;
+      ~Guard() {
+        void *p[] = {a, b, c, d, e};
+        for (void *q : p)
+          if (q) cudaFree(q);
+      }
+    } gd{d_cnt, d_na, nullptr, nullptr, nullptr};
+    {
+      int grid = (int)std::min<int64_t>(((int64_t)nc * 32 + 255) / 256, 148 * 32);
+      k_line_counts_ext<<<grid, 256, 0, s>>>(sc.M, stride, nc, nr, d_cnt, d_na);
+      count_launch();
+    }
+    std::vector<uint8_t> na(nc);
+    BSG_CUDA(cudaMemcpyAsync(na.data(), d_na, (size_t)nc, cudaMemcpyDeviceToHost, s));
+    BSG_CUDA(cudaStreamSynchronize(s));
+    const int nchunks = (int)(stride / CHUNK);
+    const int npad = nchunks * 256 - nr;  // code-0 slots beyond the last row count as valid on both sides
+    const int nib = (nc + TM - 1) / TM;
+    // any-missing flag per 64-line block
+    const int njb = (nc + TN - 1) / TN;
+    std::vector<uint8_t> na_jb(njb, 0);
+    for (int j = 0; j < nc; j++) na_jb[j / TN] |= na[j];
+    // tiles, in batches of row blocks bounded by the size of the sums buffer
+    const size_t max_sum_ints = (size_t)768 << 20;  // 3 GB of int32
+    int ib = 0;
+    while (ib < nib) {
+      std::vector<Tile> tiles;
+      std::vector<RowBlock> rbs;
+      size_t used = 0;
+      const int ib_start = ib;
+      for (; ib < nib; ib++) {
+        const int r0 = ib * TM, r1 = std::min(nc, r0 + TM);
+        int jmin = r1, jmax = -1;
+        for (int j0 = r0; j0 < r1; j0++)
+          if (w.wlen[j0] > 0) {
+            jmin = std::min(jmin, j0 - w.wlen[j0]);
+            jmax = std::max(jmax, j0 - 1);
+          }
+        RowBlock rb{(int)tiles.size(), 0};
+        if (jmax >= jmin) {
+          const int jb0 = jmin / TN, jb1 = jmax / TN;
+          bool na_i = false;
+          for (int b = r0 / TN; b <= (r1 - 1) / TN; b++) na_i |= na_jb[b] != 0;
+          size_t need = 0;
+          for (int jb = jb0; jb <= jb1; jb++) need += (size_t)((na_i || na_jb[jb]) ? 6 : 1) * TM * TN;
+          if (used + need > max_sum_ints && ib > ib_start) break;
+          rb.jb0 = jb0;
+          for (int jb = jb0; jb <= jb1; jb++) {
+            const int mode = (na_i || na_jb[jb]) ? 1 : 0;
+            tiles.push_back(Tile{r0, jb * TN, mode, (long long)used});
+            used += (size_t)(mode ? 6 : 1) * TM * TN;
+          }
+        }
+        rbs.push_back(rb);
+      }
+      const int j0_begin = ib_start * TM, j0_end = std::min(nc, ib * TM);
+      if (tiles.empty() || w.boff[j0_end] == w.boff[j0_begin]) continue;
+      Tile *d_tiles = nullptr;
+      RowBlock *d_rbs = nullptr;
+      int *d_sums = nullptr;
+      BSG_CUDA(cudaMalloc((void **)&d_tiles, tiles.size() * sizeof(Tile)));
+      BSG_CUDA(cudaMalloc((void **)&d_rbs, rbs.size() * sizeof(RowBlock)));
+      cudaError_t e = cudaMalloc((void **)&d_sums, used * sizeof(int));
+      if (e != cudaSuccess) {
+        cudaFree(d_tiles);
+        cudaFree(d_rbs);
+        return cuda_fail(e, "correlation tile sums");
+      }
+      cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice, s);
+      cudaMemcpyAsync(d_rbs, rbs.data(), rbs.size() * sizeof(RowBlock), cudaMemcpyHostToDevice, s);
+      k_gram<<<(unsigned)tiles.size(), THREADS, 0, s>>>(sc.M, stride, nc, nchunks, d_tiles, d_sums);
+      const long long npairs = w.boff[j0_end] - w.boff[j0_begin];
+      const int eg = (int)std::min<long long>((npairs + 255) / 256, 148 * 16);
+      if (ld)
+        k_cor_from_sums<true><<<eg, 256, 0, s>>>(d_sums, d_tiles, d_rbs, ib_start, j0_begin, j0_end, sc.wlen, sc.boff, d_cnt,
+                                                 nr, npad, nullptr, sc.band, nullptr);
+      else
+        k_cor_from_sums<false><<<eg, 256, 0, s>>>(d_sums, d_tiles, d_rbs, ib_start, j0_begin, j0_end, sc.wlen, sc.boff, d_cnt,
+                                                  nr, npad, sc.thr, sc.band, sc.keep);
+      count_launch(2);
+      cudaError_t e2 = cudaStreamSynchronize(s);
+      cudaFree(d_tiles);
+      cudaFree(d_rbs);
+      cudaFree(d_sums);
+      if (e2 != cudaSuccess) return cuda_fail(e2, "correlation tiles");
+    }
   }
   BSG_CUDA(cudaGetLastError());
   return BSG_OK;
