@@ -78,6 +78,28 @@ __global__ void k_line_counts_ext(const uint8_t *__restrict__ P, int64_t stride,
   }
 }
 
+// host wrappers (used by the Gram product in bsg_la.cu): out line l = codes (code_idx[k]) of source line
+// line_idx[l], packed 16 per word
+int compact_lines(const uint8_t *src, int64_t src_stride, const int *code_idx, int ncodes, const int *line_idx,
+                  int nlines, uint8_t *out, int64_t out_stride, cudaStream_t s) {
+  if (nlines == 0) return BSG_OK;
+  int64_t work = (int64_t)nlines * (out_stride / 4);
+  k_compact<<<(int)std::min<int64_t>((work + 255) / 256, 148 * 32), 256, 0, s>>>(src, src_stride, code_idx, ncodes, line_idx,
+                                                                               nlines, out, out_stride);
+  count_launch();
+  BSG_CUDA(cudaGetLastError());
+  return BSG_OK;
+}
+
+int line_counts(const uint8_t *P, int64_t stride, int nlines, int L, int32_t *cnt, uint8_t *na, cudaStream_t s) {
+  if (nlines == 0) return BSG_OK;
+  k_line_counts_ext<<<(int)std::min<int64_t>(((int64_t)nlines * 32 + 255) / 256, 148 * 32), 256, 0, s>>>(P, stride, nlines, L,
+                                                                                                       cnt, na);
+  count_launch();
+  BSG_CUDA(cudaGetLastError());
+  return BSG_OK;
+}
+
 struct PairSums {
   int nona, x1v, x2v, y1v, y2v, c11, c12, c21, c22;
 };
@@ -355,6 +377,49 @@ __global__ void k_cor_from_sums(const int *__restrict__ sums, const Tile *__rest
 
 }  // namespace gram
 
+
+// CSC assembly on the device: kept entries per column, then an order-preserving fill (ascending row index,
+// diagonal last -- rev() of src/corr.cpp:90-92).
+__global__ void k_count_keep(const uint8_t *__restrict__ keep, const long long *__restrict__ boff,
+                             const int *__restrict__ wlen, int ncol, int fill_diag, int *__restrict__ cnt) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  int nw = (gridDim.x * blockDim.x) >> 5;
+  for (int j0 = warp; j0 < ncol; j0 += nw) {
+    int c = 0;
+    for (int k = lane; k < wlen[j0]; k += 32) c += keep[boff[j0] + k];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) cnt[j0] = c + (fill_diag ? 1 : 0);
+  }
+}
+
+__global__ void k_fill_csc(const double *__restrict__ band, const uint8_t *__restrict__ keep,
+                           const long long *__restrict__ boff, const int *__restrict__ wlen,
+                           const long long *__restrict__ p, int ncol, int fill_diag, int *__restrict__ oi,
+                           double *__restrict__ ox) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  int nw = (gridDim.x * blockDim.x) >> 5;
+  for (int j0 = warp; j0 < ncol; j0 += nw) {
+    const int wl = wlen[j0];
+    long long o = p[j0];
+    for (int base = 0; base < wl; base += 32) {
+      const int k = wl - 1 - (base + lane);  // descending k = ascending row index j0-1-k
+      const bool kp = (k >= 0) && keep[boff[j0] + k];
+      const unsigned m = __ballot_sync(0xffffffffu, kp);
+      if (kp) {
+        const long long pos = o + __popc(m & ((1u << lane) - 1u));
+        oi[pos] = j0 - 1 - k;
+        ox[pos] = band[boff[j0] + k];
+      }
+      o += __popc(m);
+    }
+    if (fill_diag && lane == 0) {
+      oi[o] = j0;
+      ox[o] = 1.0;
+    }
+  }
+}
+
 struct Window {
   std::vector<int> wlen, reach;
   std::vector<long long> boff;
@@ -561,20 +626,35 @@ int bsg_cor(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, 
   Window w;
   CorScratch sc;
   BSG_TRY(cor_common(h, ind_row, nr, ind_col, nc, size, pos, thr, false, w, sc));
-  std::vector<double> band((size_t)w.total);
-  std::vector<uint8_t> keep((size_t)w.total);
-  if (w.total) {
-    BSG_CUDA(cudaMemcpyAsync(band.data(), sc.band, (size_t)w.total * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    BSG_CUDA(cudaMemcpyAsync(keep.data(), sc.keep, (size_t)w.total, cudaMemcpyDeviceToHost, h->stream));
+  cudaStream_t s = h->stream;
+  std::vector<int> cnt((size_t)std::max(nc, 1));
+  int *d_cnt = nullptr;
+  long long *d_p = nullptr;
+  BSG_CUDA(cudaMalloc((void **)&d_cnt, (size_t)std::max(nc, 1) * sizeof(int)));
+  BSG_CUDA(cudaMalloc((void **)&d_p, (size_t)(nc + 1) * sizeof(long long)));
+  struct G2 {
+    void *a, *b, *c, *d;
+    ~G2() {
+      void *q[] = {a, b, c, d};
+      for (void *x : q)
+        if (x) cudaFree(x);
+    }
+  } g2{d_cnt, d_p, nullptr, nullptr};
+  if (nc > 0) {
+    k_count_keep<<<(int)std::min<int64_t>(((int64_t)nc * 32 + 255) / 256, 148 * 16), 256, 0, s>>>(sc.keep, sc.boff, sc.wlen, nc,
+                                                                                               fill_diag, d_cnt);
+    count_launch();
   }
-  BSG_CUDA(cudaStreamSynchronize(h->stream));
-  // CSC assembly: ascending row index, diagonal last (rev() of src/corr.cpp:90-92)
+  BSG_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)nc * sizeof(int), cudaMemcpyDeviceToHost, s));
+  BSG_CUDA(cudaStreamSynchronize(s));
   long long nnz = 0;
+  std::vector<long long> hp((size_t)nc + 1);
   for (int j0 = 0; j0 < nc; j0++) {
+    hp[j0] = nnz;
     p[j0] = nnz;
-    for (int k = 0; k < w.wlen[j0]; k++) nnz += keep[(size_t)(w.boff[j0] + k)];
-    nnz += fill_diag ? 1 : 0;
+    nnz += cnt[j0];
   }
+  hp[nc] = nnz;
   p[nc] = nnz;
   int *oi = (int *)malloc((size_t)(nnz ? nnz : 1) * sizeof(int));
   double *ox = (double *)malloc((size_t)(nnz ? nnz : 1) * sizeof(double));
@@ -583,19 +663,26 @@ int bsg_cor(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, 
     free(ox);
     return fail(BSG_ERR_ALLOC, "cannot allocate the correlation triplets");
   }
-  for (int j0 = 0; j0 < nc; j0++) {
-    long long o = p[j0];
-    for (int k = w.wlen[j0] - 1; k >= 0; k--) {
-      size_t b = (size_t)(w.boff[j0] + k);
-      if (keep[b]) {
-        oi[o] = j0 - 1 - k;
-        ox[o] = band[b];
-        o++;
-      }
+  if (nnz > 0) {
+    int *d_oi = nullptr;
+    double *d_ox = nullptr;
+    cudaError_t e = cudaMalloc((void **)&d_oi, (size_t)nnz * sizeof(int));
+    g2.c = d_oi;
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_ox, (size_t)nnz * sizeof(double));
+    g2.d = d_ox;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_p, hp.data(), (size_t)(nc + 1) * sizeof(long long), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) {
+      k_fill_csc<<<(int)std::min<int64_t>(((int64_t)nc * 32 + 255) / 256, 148 * 16), 256, 0, s>>>(
+          sc.band, sc.keep, sc.boff, sc.wlen, d_p, nc, fill_diag, d_oi, d_ox);
+      count_launch();
+      e = cudaMemcpyAsync(oi, d_oi, (size_t)nnz * sizeof(int), cudaMemcpyDeviceToHost, s);
     }
-    if (fill_diag) {
-      oi[o] = j0;
-      ox[o] = 1.0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ox, d_ox, (size_t)nnz * sizeof(double), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+      free(oi);
+      free(ox);
+      return cuda_fail(e, "correlation CSC assembly");
     }
   }
   *pi = oi;

@@ -100,6 +100,11 @@ int read_dense(bsg_bed *h, const int *d_row, int nr, const int *d_col, int nc, i
 int read_dense_scaled(bsg_bed *h, const int *d_row, int nr, const int *d_col, int nc, const double *d_center,
                       const double *d_scale, double *d_out, cudaStream_t s);
 
+// ---- bsg_cor.cu: dense sub-matrix of a packed matrix, per-line code counts ------------------------
+int compact_lines(const uint8_t *src, int64_t src_stride, const int *code_idx, int ncodes, const int *line_idx,
+                  int nlines, uint8_t *out, int64_t out_stride, cudaStream_t s);
+int line_counts(const uint8_t *P, int64_t stride, int nlines, int L, int32_t *cnt, uint8_t *na, cudaStream_t s);
+
 // ---- bsg_pmv.cu: packed matrix x vector on the integer tensor pipe ----------------------------
 struct PmvPlan;  // opaque, owned by a view
 }  // namespace bsg

@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <vector>
 
+#include "bsg_gram.cuh"
 #include "bsg_internal.cuh"
 
 namespace bsg {
@@ -125,6 +126,221 @@ static void jacobi_eigh(std::vector<double> A, int n, std::vector<double> &w, st
   }
   Z.swap(Z2);
 }
+
+
+// ---------------------------------------------------------------------------------------------------
+// Weighted integer Gram on the tensor pipe:  K += scale * sum_k fA(code(i,k)) * fB(code(j,k)) * d_k
+// with d_k one base-64 digit (0..63) of a non-negative per-k weight.  The digit is folded into the B bytes
+// ((x & 1) ? d : 0) | ((x & 2) ? 2d : 0), so the products stay exact in int32; slices are combined in fp64.
+// ---------------------------------------------------------------------------------------------------
+namespace wgram {
+using namespace gram;
+
+enum { WP_AA = 0, WP_AN = 1, WP_NA = 2, WP_NN = 3 };
+
+struct WTile {
+  int i0, j0;   // first A line (TM block), first B line (TN block)
+  int mode;     // 0: lines without missing values -> product aa only; 1: aa, an, na, nn
+};
+
+struct WArgs {
+  const uint8_t *P;
+  int64_t stride;
+  int nlines, nchunks, nslices;
+  const uint8_t *dig[3];   // weight digits of W1, W2' = -W2, W3: [nslices][nchunks * 256] in fragment order
+  double scale[3][10];     // 64^t * 2^-e per weight and slice
+  const WTile *tiles;
+  double *K;               // n x n column-major, pre-zeroed; tile (i0, j0) writes K[i, j] for i >= j only
+  int64_t ldk;
+};
+
+struct WFrag {
+  uint4 a[4], b[4];
+};
+
+// NA-indicator plane: bit 2p set iff code p is missing
+__device__ __forceinline__ uint32_t plane_n(uint32_t w) { return w & (w >> 1) & 0x55555555u; }
+
+template <int PROD, bool RAW>
+__device__ __forceinline__ void wfrag_mma(const WFrag &f, const uint8_t *dp, int (&acc)[2][4][4]) {
+  const uint32_t *aw[4] = {&f.a[0].x, &f.a[1].x, &f.a[2].x, &f.a[3].x};
+  const uint32_t *bw[4] = {&f.b[0].x, &f.b[1].x, &f.b[2].x, &f.b[3].x};
+  constexpr bool A_IS_N = (PROD == WP_NA || PROD == WP_NN), B_IS_N = (PROD == WP_AN || PROD == WP_NN);
+#pragma unroll
+  for (int w = 0; w < 4; w++) {
+    const uint4 dq = ldg128(dp + w * 16);  // digits of this word (L1-resident, shared by the 8 lanes of equal q)
+    const uint32_t dcls[4] = {dq.x, dq.y, dq.z, dq.w};  // digits of class c: byte r <-> code 4r + c
+    uint32_t wa[4], wb[4];
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+      wa[l] = A_IS_N ? plane_n(aw[l][w]) : (RAW ? aw[l][w] : plane_word<PL_A>(aw[l][w]));
+      wb[l] = B_IS_N ? plane_n(bw[l][w]) : (RAW ? bw[l][w] : plane_word<PL_A>(bw[l][w]));
+    }
+#pragma unroll
+    for (int cp = 0; cp < 2; cp++) {
+      const int s0 = 4 * cp, s1 = 4 * cp + 2;
+      const uint32_t d0 = dcls[2 * cp], d1 = dcls[2 * cp + 1];
+      uint32_t b0[4], b1[4];
+#pragma unroll
+      for (int nt = 0; nt < 4; nt++) {
+        const uint32_t x0 = wb[nt] >> s0, x1 = wb[nt] >> s1;
+        const uint32_t m0 = (x0 & 0x01010101u) * 0xFFu, m1 = (x1 & 0x01010101u) * 0xFFu;
+        if (B_IS_N) {
+          b0[nt] = m0 & d0;
+          b1[nt] = m1 & d1;
+        } else {
+          const uint32_t h0 = ((x0 >> 1) & 0x01010101u) * 0xFFu, h1 = ((x1 >> 1) & 0x01010101u) * 0xFFu;
+          b0[nt] = (m0 & d0) | (h0 & (d0 << 1));
+          b1[nt] = (m1 & d1) | (h1 & (d1 << 1));
+        }
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++) {
+        const uint32_t a0 = (wa[2 * mt] >> s0) & 0x03030303u, a1 = (wa[2 * mt + 1] >> s0) & 0x03030303u;
+        const uint32_t a2 = (wa[2 * mt] >> s1) & 0x03030303u, a3 = (wa[2 * mt + 1] >> s1) & 0x03030303u;
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) mma_u8u8(acc[mt][nt], a0, a1, a2, a3, b0[nt], b1[nt]);
+      }
+    }
+  }
+}
+
+template <int PROD, bool RAW>
+__device__ __forceinline__ void wgram_product(const uint8_t *const (&pa)[4], const uint8_t *const (&pb)[4],
+                                              const uint8_t *dig, int nchunks, int q, int (&acc)[2][4][4]) {
+#pragma unroll
+  for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+      for (int k = 0; k < 4; k++) acc[mt][nt][k] = 0;
+  WFrag f0, f1;
+  auto load = [&](WFrag &f, int c) {
+    const int64_t off = (int64_t)c * CHUNK;
+#pragma unroll
+    for (int l = 0; l < 4; l++) f.a[l] = ldg128(pa[l] + off);
+#pragma unroll
+    for (int l = 0; l < 4; l++) f.b[l] = ldg128(pb[l] + off);
+  };
+  const uint8_t *dq = dig + (int64_t)q * 64;  // [chunk][q][w][16]
+  load(f0, 0);
+  for (int c = 0; c < nchunks; c += 2) {
+    if (c + 1 < nchunks) load(f1, c + 1);
+    wfrag_mma<PROD, RAW>(f0, dq + (int64_t)c * 256, acc);
+    if (c + 2 < nchunks) load(f0, c + 2);
+    if (c + 1 < nchunks) wfrag_mma<PROD, RAW>(f1, dq + (int64_t)(c + 1) * 256, acc);
+  }
+}
+
+__global__ void __launch_bounds__(THREADS, 1) k_wgram(const WArgs a) {
+  const WTile t = a.tiles[blockIdx.x];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+  const int wm = warp >> 1, wn = warp & 1;
+  // this warp's 32 x 32 block lies strictly above the diagonal -> nothing to do (K is filled for i >= j)
+  if (t.i0 + wm * 32 + 31 < t.j0 + wn * 32) return;
+  const uint8_t *pa[4], *pb[4];
+#pragma unroll
+  for (int l = 0; l < 4; l++) {
+    int la = t.i0 + wm * 32 + (l >> 1) * 16 + g + 8 * (l & 1);
+    int lb = t.j0 + wn * 32 + l * 8 + g;
+    la = min(la, a.nlines - 1);
+    lb = min(lb, a.nlines - 1);
+    pa[l] = a.P + (int64_t)la * a.stride + 16 * q;
+    pb[l] = a.P + (int64_t)lb * a.stride + 16 * q;
+  }
+  int acc[2][4][4];
+  const int64_t dstride = (int64_t)a.nchunks * 256;
+  // K is pre-zeroed and every (i, j) of the tile is owned by one thread: accumulate in place, slice by slice
+  auto fold = [&](double sc) {
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+      for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int i = t.i0 + wm * 32 + mt * 16 + g + 8 * (k >> 1);
+          const int j = t.j0 + wn * 32 + nt * 8 + 2 * q + (k & 1);
+          if (i < a.nlines && j < a.nlines && i >= j) a.K[(int64_t)j * a.ldk + i] += sc * (double)acc[mt][nt][k];
+        }
+  };
+  for (int sl = a.nslices - 1; sl >= 0; sl--) {
+    if (t.mode == 0) {
+      wgram_product<WP_AA, true>(pa, pb, a.dig[0] + sl * dstride, a.nchunks, q, acc);
+      fold(a.scale[0][sl]);
+    } else {
+      wgram_product<WP_AA, false>(pa, pb, a.dig[0] + sl * dstride, a.nchunks, q, acc);
+      fold(a.scale[0][sl]);
+      wgram_product<WP_AN, false>(pa, pb, a.dig[1] + sl * dstride, a.nchunks, q, acc);
+      fold(a.scale[1][sl]);
+      wgram_product<WP_NA, false>(pa, pb, a.dig[1] + sl * dstride, a.nchunks, q, acc);
+      fold(a.scale[1][sl]);
+      wgram_product<WP_NN, false>(pa, pb, a.dig[2] + sl * dstride, a.nchunks, q, acc);
+      fold(a.scale[2][sl]);
+    }
+  }
+}
+
+// weight digits in fragment order: byte ((chunk*4 + q)*4 + w)*16 + c*4 + r  <->  k = chunk*256 + (4q+w)*16 + 4r + c
+__global__ void k_weight_digits(const double *__restrict__ W, int len, int nchunks, int nslices, int e,
+                                uint8_t *__restrict__ dig) {
+  int64_t total = (int64_t)nchunks * 256;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int byte = (int)(t & 15), unit = (int)((t >> 4) & 15), chunk = (int)(t >> 8);
+    const int c = byte >> 2, r = byte & 3, w = unit & 3, q = unit >> 2;
+    const int64_t k = (int64_t)chunk * 256 + (4 * q + w) * 16 + 4 * r + c;
+    unsigned long long v = 0;
+    if (k < len) v = (unsigned long long)__double2ll_rn(scalbn(W[k], e));
+    for (int sl = 0; sl < nslices; sl++) {
+      dig[(int64_t)sl * total + t] = (uint8_t)(v & 63ull);
+      v >>= 6;
+    }
+  }
+}
+
+// lower triangle + vector terms -> full symmetric K:  K_ij += r_i + r_j + cst - q_i - q_j
+__global__ void k_grm_finish(double *__restrict__ K, int64_t ld, int n, const double *__restrict__ r,
+                             const double *__restrict__ qv, double cst) {
+  int64_t total = (int64_t)n * n;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(t / n), i = (int)(t - (int64_t)j * n);
+    if (i < j) continue;
+    double v = K[(int64_t)j * ld + i] + r[i] + r[j] + cst;
+    if (qv) v -= qv[i] + qv[j];
+    K[(int64_t)j * ld + i] = v;
+    K[(int64_t)i * ld + j] = v;
+  }
+}
+
+// u = 1/s, t = -c/s:  W1 = u^2, W2' = -u t = c/s^2 (>= 0 for c >= 0), W3 = t^2 ; w2 = u t (signed, for the vector term)
+__global__ void k_grm_weights(const double *__restrict__ center, const double *__restrict__ scale, int len,
+                              double *__restrict__ W1, double *__restrict__ W2p, double *__restrict__ W3,
+                              double *__restrict__ w2, double *__restrict__ stats /* max1,max2,max3,sumW3,bad */) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  double m1 = 0, m2 = 0, m3 = 0, s3 = 0;
+  int bad = 0;
+  if (k < len) {
+    const double u = 1.0 / scale[k], tt = -center[k] / scale[k];
+    const double a = u * u, b = -(u * tt), c = tt * tt;
+    W1[k] = a; W2p[k] = b; W3[k] = c; w2[k] = u * tt;
+    if (!isfinite(a) || !isfinite(b) || !isfinite(c) || b < 0) bad = 1;
+    m1 = a; m2 = b; m3 = c; s3 = c;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    m1 = fmax(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+    m2 = fmax(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+    m3 = fmax(m3, __shfl_xor_sync(0xffffffffu, m3, o));
+    bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(reinterpret_cast<unsigned long long *>(&stats[0]), (unsigned long long)__double_as_longlong(m1));
+    atomicMax(reinterpret_cast<unsigned long long *>(&stats[1]), (unsigned long long)__double_as_longlong(m2));
+    atomicMax(reinterpret_cast<unsigned long long *>(&stats[2]), (unsigned long long)__double_as_longlong(m3));
+    if (bad) atomicMax(reinterpret_cast<unsigned long long *>(&stats[4]), (unsigned long long)__double_as_longlong(1.0));
+  }
+}
+
+}  // namespace wgram
 
 struct SvdWork {
   double *V = nullptr, *w = nullptr, *tmp = nullptr, *h = nullptr, *S = nullptr, *Y = nullptr;
@@ -365,13 +581,10 @@ int bsg_randomsvd(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, in
 }
 
 // ---------------------------------------------------------------------------------------------------
-int bsg_tcrossprod(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, const double *center,
-                   const double *scale, double *K) {
-  if (!h || !K) return fail(BSG_ERR_ARG, "null argument");
-  if (!center || !scale) return fail(BSG_ERR_DIM, "Incompatibility between dimensions.");
-  BSG_TRY(bind_device(h));
-  if (!ind_row) nr = h->n;
-  if (!ind_col) nc = h->m;
+// fp64 path: device decode of column blocks + cuBLAS DSYRK.  Used when no sample-major copy is resident or the
+// scaling is degenerate (zero / negative scale, negative center, non-finite weights).
+static int tcrossprod_dsyrk(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, const double *center,
+                            const double *scale, double *K) {
   cudaStream_t s = h->stream;
   const int *d_row = nullptr, *d_col = nullptr;
   BSG_TRY(upload_index(h, ind_row, nr, h->n, h->w_idx_row, &d_row));
@@ -427,6 +640,182 @@ int bsg_tcrossprod(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, i
   for (int j = 0; j < nr; j++)
     for (int i = j + 1; i < nr; i++) K[(size_t)i * nr + j] = K[(size_t)j * nr + i];
   return BSG_OK;
+}
+
+
+}  // extern "C"
+
+struct DevPtrs {
+  std::vector<void *> p;
+  ~DevPtrs() {
+    for (void *q : p)
+      if (q) cudaFree(q);
+  }
+  template <class T>
+  int alloc(T **out, size_t count) {
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, (count ? count : 1) * sizeof(T));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(GRM)");
+    p.push_back(q);
+    *out = (T *)q;
+    return BSG_OK;
+  }
+};
+
+extern "C" {
+
+int bsg_tcrossprod(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, const double *center,
+                   const double *scale, double *K) {
+  if (!h || !K) return fail(BSG_ERR_ARG, "null argument");
+  if (!center || !scale) return fail(BSG_ERR_DIM, "Incompatibility between dimensions.");
+  BSG_TRY(bind_device(h));
+  if (!ind_row) nr = h->n;
+  if (!ind_col) nc = h->m;
+  static int force_dsyrk = -1, nslices = 8;
+  if (force_dsyrk < 0) {
+    const char *ev = getenv("BSG_GRM_DSYRK");
+    force_dsyrk = (ev && ev[0] == '1') ? 1 : 0;
+    const char *es = getenv("BSG_GRM_SLICES");
+    if (es) nslices = std::min(9, std::max(2, atoi(es)));
+  }
+  if (force_dsyrk || !h->B || nr == 0 || nc == 0) return tcrossprod_dsyrk(h, ind_row, nr, ind_col, nc, center, scale, K);
+  using namespace wgram;
+  cudaStream_t s = h->stream;
+  DevPtrs mem;
+  // ---- weights
+  double *d_c, *d_s, *W1, *W2p, *W3, *w2, *d_stats;
+  BSG_TRY(mem.alloc(&d_c, nc));
+  BSG_TRY(mem.alloc(&d_s, nc));
+  BSG_TRY(mem.alloc(&W1, nc));
+  BSG_TRY(mem.alloc(&W2p, nc));
+  BSG_TRY(mem.alloc(&W3, nc));
+  BSG_TRY(mem.alloc(&w2, nc));
+  BSG_TRY(mem.alloc(&d_stats, 8));
+  BSG_CUDA(cudaMemcpyAsync(d_c, center, (size_t)nc * sizeof(double), cudaMemcpyHostToDevice, s));
+  BSG_CUDA(cudaMemcpyAsync(d_s, scale, (size_t)nc * sizeof(double), cudaMemcpyHostToDevice, s));
+  BSG_CUDA(cudaMemsetAsync(d_stats, 0, 8 * sizeof(double), s));
+  k_grm_weights<<<(nc + 255) / 256, 256, 0, s>>>(d_c, d_s, nc, W1, W2p, W3, w2, d_stats);
+  count_launch();
+  double stats[8];
+  std::vector<double> hW3(nc);
+  BSG_CUDA(cudaMemcpyAsync(stats, d_stats, sizeof stats, cudaMemcpyDeviceToHost, s));
+  BSG_CUDA(cudaMemcpyAsync(hW3.data(), W3, (size_t)nc * sizeof(double), cudaMemcpyDeviceToHost, s));
+  BSG_CUDA(cudaStreamSynchronize(s));
+  if (stats[4] != 0.0) return tcrossprod_dsyrk(h, ind_row, nr, ind_col, nc, center, scale, K);
+  double sumW3 = 0;
+  for (int j = 0; j < nc; j++) sumW3 += hW3[j];
+
+  // ---- the sub-matrix X[ind_row, ind_col] as dense sample-major lines
+  const bool ident = (!ind_row || [&] { if (nr != h->n) return false; for (int i = 0; i < nr; i++) if (ind_row[i] != i + 1) return false; return true; }()) &&
+                     (!ind_col || [&] { if (nc != h->m) return false; for (int j = 0; j < nc; j++) if (ind_col[j] != j + 1) return false; return true; }());
+  const uint8_t *P = h->B;
+  int64_t stride = h->strideB;
+  uint8_t *d_na = nullptr;
+  BSG_TRY(mem.alloc(&d_na, nr));
+  if (!ident) {
+    const int *d_row = nullptr, *d_col = nullptr;
+    BSG_TRY(upload_index(h, ind_row, nr, h->n, h->w_idx_row, &d_row));
+    BSG_TRY(upload_index(h, ind_col, nc, h->m, h->w_idx_col, &d_col));
+    stride = round_up(((int64_t)nc + 3) / 4, CHUNK);
+    uint8_t *Pc = nullptr;
+    BSG_TRY(mem.alloc(&Pc, (size_t)stride * nr));
+    // sub-matrix of the sample-major copy: lines = selected samples, codes = selected SNPs
+    BSG_TRY(compact_lines(h->B, h->strideB, d_col, nc, d_row, nr, Pc, stride, s));
+    int32_t *d_cnt = nullptr;
+    BSG_TRY(mem.alloc(&d_cnt, (size_t)nr * 4));
+    BSG_TRY(line_counts(Pc, stride, nr, nc, d_cnt, d_na, s));
+    P = Pc;
+  } else {
+    BSG_CUDA(cudaMemcpyAsync(d_na, h->naB, (size_t)nr, cudaMemcpyDeviceToDevice, s));
+  }
+  std::vector<uint8_t> na(nr);
+  BSG_CUDA(cudaMemcpyAsync(na.data(), d_na, (size_t)nr, cudaMemcpyDeviceToHost, s));
+  BSG_CUDA(cudaStreamSynchronize(s));
+  const int nchunks = (int)(stride / CHUNK);
+
+  // ---- weight digits (base 64, nslices digits) in fragment order
+  WArgs a;
+  a.P = P;
+  a.stride = stride;
+  a.nlines = nr;
+  a.nchunks = nchunks;
+  a.nslices = nslices;
+  const double *Ws[3] = {W1, W2p, W3};
+  for (int wv = 0; wv < 3; wv++) {
+    uint8_t *dg = nullptr;
+    BSG_TRY(mem.alloc(&dg, (size_t)nslices * nchunks * 256));
+    int ex = 0;
+    if (stats[wv] > 0) frexp(stats[wv], &ex);
+    const int e = 6 * nslices - 1 - ex;
+    k_weight_digits<<<(int)std::min<int64_t>(((int64_t)nchunks * 256 + 255) / 256, 148 * 16), 256, 0, s>>>(Ws[wv], nc, nchunks,
+                                                                                                        nslices, e, dg);
+    count_launch();
+    a.dig[wv] = dg;
+    for (int sl = 0; sl < nslices; sl++) a.scale[wv][sl] = ldexp(1.0, 6 * sl - e);
+  }
+
+  // ---- tiles of the lower triangle
+  std::vector<WTile> tiles;
+  const int njb = (nr + TN - 1) / TN;
+  std::vector<uint8_t> na_jb(njb, 0);
+  for (int i = 0; i < nr; i++) na_jb[i / TN] |= na[i];
+  for (int i0 = 0; i0 < nr; i0 += TM) {
+    bool na_i = false;
+    for (int b = i0 / TN; b <= std::min(nr - 1, i0 + TM - 1) / TN; b++) na_i |= na_jb[b] != 0;
+    for (int j0 = 0; j0 <= std::min(nr - 1, i0 + TM - 1); j0 += TN) tiles.push_back(WTile{i0, j0, (na_i || na_jb[j0 / TN]) ? 1 : 0});
+  }
+  WTile *d_tiles = nullptr;
+  BSG_TRY(mem.alloc(&d_tiles, tiles.size()));
+  BSG_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(WTile), cudaMemcpyHostToDevice, s));
+  a.tiles = d_tiles;
+  double *dK = nullptr;
+  BSG_TRY(mem.alloc(&dK, (size_t)nr * nr));
+  BSG_CUDA(cudaMemsetAsync(dK, 0, (size_t)nr * nr * sizeof(double), s));
+  a.K = dK;
+  a.ldk = nr;
+  k_wgram<<<(unsigned)tiles.size(), THREADS, 0, s>>>(a);
+  count_launch();
+  BSG_CUDA(cudaGetLastError());
+
+  // ---- vector terms through the matvec engine:  r = A w2 ;  q = N w3 = (X~_{c=1,s=1} w3) - A w3 + sum(w3)
+  double *d_r = nullptr, *d_q = nullptr, *d_t1 = nullptr;
+  BSG_TRY(mem.alloc(&d_r, nr));
+  bsg_view *v0 = nullptr;
+  BSG_TRY(bsg_view_create(h, ind_row, nr, ind_col, nc, nullptr, nullptr, &v0));
+  int rc = bsg_view_prodvec_dev(v0, w2, d_r, s);
+  bool any_na = false;
+  for (int i = 0; i < nr && !any_na; i++) any_na = na[i] != 0;
+  if (!rc && any_na) {
+    rc = mem.alloc(&d_q, nr);
+    if (!rc) rc = mem.alloc(&d_t1, nr);
+    std::vector<double> ones(nc, 1.0);
+    bsg_view *v1 = nullptr;
+    if (!rc) rc = bsg_view_prodvec_dev(v0, W3, d_t1, s);  // A w3
+    if (!rc) rc = bsg_view_create(h, ind_row, nr, ind_col, nc, ones.data(), ones.data(), &v1);
+    if (!rc) rc = bsg_view_prodvec_dev(v1, W3, d_q, s);   // A w3 - sum_nonNA w3
+    if (!rc) {
+      cudaStreamSynchronize(s);
+      std::vector<double> hq(nr), ht(nr);
+      cudaMemcpy(hq.data(), d_q, (size_t)nr * sizeof(double), cudaMemcpyDeviceToHost);
+      cudaMemcpy(ht.data(), d_t1, (size_t)nr * sizeof(double), cudaMemcpyDeviceToHost);
+      for (int i = 0; i < nr; i++) hq[i] = hq[i] - ht[i] + sumW3;
+      cudaMemcpy(d_q, hq.data(), (size_t)nr * sizeof(double), cudaMemcpyHostToDevice);
+    }
+    if (v1) {
+      cudaStreamSynchronize(s);
+      bsg_view_destroy(v1);
+    }
+  }
+  if (!rc) {
+    k_grm_finish<<<(int)std::min<int64_t>(((int64_t)nr * nr + 255) / 256, 148 * 32), 256, 0, s>>>(dK, nr, nr, d_r, d_q, sumW3);
+    count_launch();
+    cudaError_t e2 = cudaMemcpyAsync(K, dK, (size_t)nr * nr * sizeof(double), cudaMemcpyDeviceToHost, s);
+    if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(s);
+    if (e2 != cudaSuccess) rc = cuda_fail(e2, "GRM download");
+  }
+  cudaStreamSynchronize(s);
+  bsg_view_destroy(v0);
+  return rc;
 }
 
 }  // extern "C"
