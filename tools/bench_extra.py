@@ -47,12 +47,17 @@ def main():
     print(json.dumps({"op": "bed_counts(all)", "seconds": t}), flush=True)
     g.close()
     # --- bed_tcrossprodSelf (configs[3] is 10,000 x 1,000,000)
-    g = B.Bed.synthetic(a.grm_n, a.grm_m, seed=20250928, layouts=B.LAYOUT_SNP_MAJOR)
-    t, (K, c, s) = timeit(lambda: B.bed_tcrossprodSelf(g))
-    print(json.dumps({"op": "bed_tcrossprodSelf", "n": a.grm_n, "m": a.grm_m, "seconds": t,
-                      "useful_flops": float(a.grm_n) * (a.grm_n + 1) * a.grm_m,
-                      "tflops": float(a.grm_n) * (a.grm_n + 1) * a.grm_m / t / 1e12,
-                      "cfg4_extrapolated_s": t * 1_000_000 / a.grm_m}), flush=True)
+    for na_rate in (0.0, 0.01):
+        g = B.Bed.synthetic(a.grm_n, a.grm_m, seed=20250928, na_rate=na_rate)
+        sc = B.bed_scaleBinom(g)
+        fun = lambda *aa, **kw: sc  # noqa: E731
+        t, (K, c, s) = timeit(lambda: B.bed_tcrossprodSelf(g, fun_scaling=fun))
+        print(json.dumps({"op": "bed_tcrossprodSelf", "n": a.grm_n, "m": a.grm_m, "na_rate": na_rate, "seconds": t,
+                          "useful_flops": float(a.grm_n) * (a.grm_n + 1) * a.grm_m,
+                          "useful_tflops": float(a.grm_n) * (a.grm_n + 1) * a.grm_m / t / 1e12,
+                          "cfg4_extrapolated_s": t * 1_000_000 / a.grm_m, "path": os.environ.get("BSG_GRM_DSYRK", "0"),
+                          "slices": os.environ.get("BSG_GRM_SLICES", "8")}), flush=True)
+        g.close()
 
 
 if __name__ == "__main__":
