@@ -324,7 +324,7 @@ __global__ void k_cor_from_sums(const int *__restrict__ sums, const Tile *__rest
                                 const RowBlock *__restrict__ rbs, int ib0, int j0_begin, int j0_end,
                                 const int *__restrict__ wlen, const long long *__restrict__ boff,
                                 const int32_t *__restrict__ cnt, int nrow, int npad, const double *__restrict__ thr,
-                                double *__restrict__ band, uint8_t *__restrict__ keep) {
+                                double *__restrict__ band, uint8_t *__restrict__ keep, int tn) {
   const long long first = boff[j0_begin], total = boff[j0_end] - first;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     // locate j0 by binary search on boff
@@ -337,8 +337,8 @@ __global__ void k_cor_from_sums(const int *__restrict__ sums, const Tile *__rest
     const int j0 = lo, k = (int)(o - boff[j0]), j = j0 - 1 - k;
     const int ib = j0 / TM - ib0;
     const RowBlock rb = rbs[ib];
-    const Tile tl = tiles[rb.first_tile + (j / TN - rb.jb0)];
-    const int *sp = sums + tl.out + (int64_t)(j0 - tl.i0) * TN + (j - tl.j0);
+    const Tile tl = tiles[rb.first_tile + (j / tn - rb.jb0)];
+    const int *sp = sums + tl.out + (int64_t)(j0 - tl.i0) * tn + (j - tl.j0);
     double nona_d, xSum, xxSum, ySum, yySum, xySum;
     int nona;
     if (tl.mode == 0) {
@@ -350,7 +350,7 @@ __global__ void k_cor_from_sums(const int *__restrict__ sums, const Tile *__rest
       yySum = (double)cy[1] + 4.0 * (double)cy[2];
       xySum = (double)sp[0];
     } else {
-      const int S = TM * TN;
+      const int S = TM * tn;
       const int aa = sp[0], bb = sp[S], ab = sp[2 * S], ba = sp[3 * S], hb = sp[4 * S], bh = sp[5 * S];
       nona = bb - npad;  // pads are valid zeros on both sides
       xSum = (double)ab;
@@ -536,10 +536,20 @@ static int cor_common(bsg_bed *h, const int *ind_row, int nr, const int *ind_col
     const int nchunks = (int)(stride / CHUNK);
     const int npad = nchunks * 256 - nr;  // code-0 slots beyond the last row count as valid on both sides
     const int nib = (nc + TM - 1) / TM;
-    // any-missing flag per 64-line block
-    const int njb = (nc + TN - 1) / TN;
+    // no missing value at all -> 128 x 128 tiles on tcgen05 (bsg_gram5.cu); else 128 x 64 six-plane IMMA tiles
+    bool clean = true;
+    for (int j = 0; j < nc && clean; j++) clean = na[j] == 0;
+    static int use_g5 = -1;
+    if (use_g5 < 0) {
+      const char *ev = getenv("BSG_GRAM5");
+      use_g5 = (ev && ev[0] == '0') ? 0 : 1;
+    }
+    const bool g5 = clean && use_g5;
+    const int TNv = g5 ? 128 : TN;
+    // any-missing flag per column block
+    const int njb = (nc + TNv - 1) / TNv;
     std::vector<uint8_t> na_jb(njb, 0);
-    for (int j = 0; j < nc; j++) na_jb[j / TN] |= na[j];
+    for (int j = 0; j < nc; j++) na_jb[j / TNv] |= na[j];
     // tiles, in batches of row blocks bounded by the size of the sums buffer
     const size_t max_sum_ints = (size_t)768 << 20;  // 3 GB of int32
     int ib = 0;
@@ -558,17 +568,17 @@ static int cor_common(bsg_bed *h, const int *ind_row, int nr, const int *ind_col
           }
         RowBlock rb{(int)tiles.size(), 0};
         if (jmax >= jmin) {
-          const int jb0 = jmin / TN, jb1 = jmax / TN;
+          const int jb0 = jmin / TNv, jb1 = jmax / TNv;
           bool na_i = false;
-          for (int b = r0 / TN; b <= (r1 - 1) / TN; b++) na_i |= na_jb[b] != 0;
+          for (int b = r0 / TNv; b <= (r1 - 1) / TNv; b++) na_i |= na_jb[b] != 0;
           size_t need = 0;
-          for (int jb = jb0; jb <= jb1; jb++) need += (size_t)((na_i || na_jb[jb]) ? 6 : 1) * TM * TN;
+          for (int jb = jb0; jb <= jb1; jb++) need += (size_t)((na_i || na_jb[jb]) ? 6 : 1) * TM * TNv;
           if (used + need > max_sum_ints && ib > ib_start) break;
           rb.jb0 = jb0;
           for (int jb = jb0; jb <= jb1; jb++) {
             const int mode = (na_i || na_jb[jb]) ? 1 : 0;
-            tiles.push_back(Tile{r0, jb * TN, mode, (long long)used});
-            used += (size_t)(mode ? 6 : 1) * TM * TN;
+            tiles.push_back(Tile{r0, jb * TNv, mode, (long long)used});
+            used += (size_t)(mode ? 6 : 1) * TM * TNv;
           }
         }
         rbs.push_back(rb);
@@ -588,15 +598,25 @@ static int cor_common(bsg_bed *h, const int *ind_row, int nr, const int *ind_col
       }
       cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice, s);
       cudaMemcpyAsync(d_rbs, rbs.data(), rbs.size() * sizeof(RowBlock), cudaMemcpyHostToDevice, s);
-      k_gram<<<(unsigned)tiles.size(), THREADS, 0, s>>>(sc.M, stride, nc, nchunks, d_tiles, d_sums);
+      if (g5) {
+        int rc5 = gram5_launch(sc.M, stride, nc, stride, d_tiles, (int)tiles.size(), d_sums, s);
+        if (rc5) {
+          cudaFree(d_tiles);
+          cudaFree(d_rbs);
+          cudaFree(d_sums);
+          return rc5;
+        }
+      } else {
+        k_gram<<<(unsigned)tiles.size(), THREADS, 0, s>>>(sc.M, stride, nc, nchunks, d_tiles, d_sums);
+      }
       const long long npairs = w.boff[j0_end] - w.boff[j0_begin];
       const int eg = (int)std::min<long long>((npairs + 255) / 256, 148 * 16);
       if (ld)
         k_cor_from_sums<true><<<eg, 256, 0, s>>>(d_sums, d_tiles, d_rbs, ib_start, j0_begin, j0_end, sc.wlen, sc.boff, d_cnt,
-                                                 nr, npad, nullptr, sc.band, nullptr);
+                                                 nr, npad, nullptr, sc.band, nullptr, TNv);
       else
         k_cor_from_sums<false><<<eg, 256, 0, s>>>(d_sums, d_tiles, d_rbs, ib_start, j0_begin, j0_end, sc.wlen, sc.boff, d_cnt,
-                                                  nr, npad, sc.thr, sc.band, sc.keep);
+                                                  nr, npad, sc.thr, sc.band, sc.keep, TNv);
       count_launch(2);
       cudaError_t e2 = cudaStreamSynchronize(s);
       cudaFree(d_tiles);

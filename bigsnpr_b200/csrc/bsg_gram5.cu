@@ -1,0 +1,214 @@
+// bsg_gram5.cu -- the integer Gram tile on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+//   S[i][j] = sum_k code(i, k) * code(j, k)      for a 128 x 128 tile of lines, exact int32
+//
+// Used for the windowed correlations when the tile holds no missing value (only xySum is pair specific then,
+// src/corr.cpp:58-75); tiles with missing values take the six-plane IMMA path of bsg_cor.cu.
+//
+// Pipeline per CTA (one 128 x 128 tile, whole contraction range):
+//   8 producer warps : stream the packed lines (2 x LDG.128 = 128 codes per line and stage, register prefetch),
+//                      expand 2-bit codes to bytes with the class masks (w >> 2c) & 0x03030303 -- any fixed
+//                      permutation of k inside a 16-byte row is fine for a Gram product because both operands
+//                      use the same one -- and STS.128 them into shared memory in the UMMA canonical K-major
+//                      no-swizzle layout: core matrix = 8 rows x 16 B, SBO = 128 B between 8-row groups,
+//                      LBO = 2048 B between core matrices along K; fence.proxy.async + mbarrier arrive.
+//   1 MMA thread     : waits for the stage, issues 4 x tcgen05.mma.cta_group::1.kind::i8 (M = 128, N = 128,
+//                      K = 32, u8 x u8 -> s32 accumulator in TMEM), tcgen05.commit -> frees the stage.
+//   4 epilogue warps : tcgen05.ld 32x32b.x32 of the 128 x 128 int32 accumulator, 16-byte stores of the tile sums.
+#include <stdint.h>
+
+#include "bsg_gram.cuh"
+#include "bsg_internal.cuh"
+
+namespace bsg {
+namespace gram5 {
+
+constexpr int T5M = 128, T5N = 128;      // tile of line pairs
+constexpr int KSTAGE = 128;              // codes per line per stage (32 packed bytes) = 4 MMAs of K = 32
+constexpr int STAGES = 3;
+constexpr int PROD_WARPS = 8;            // 256 producer threads: thread t expands line t (0..127 A, 128..255 B)
+constexpr int THREADS = (PROD_WARPS + 1) * 32;
+constexpr int OPER_BYTES = 128 * KSTAGE;  // 16 KB per operand and stage
+constexpr int STAGE_BYTES = 2 * OPER_BYTES;
+constexpr int LBO = 2048, SBO = 128;     // bytes: next core matrix along K / along M
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256;
+constexpr int TMEM_COLS = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// shared-memory matrix descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor): start >> 4 at [0,14),
+// LBO >> 4 at [16,30), SBO >> 4 at [32,46), version = 1 at [46,48), layout type 0 at [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(LBO >> 4) << 16) | ((uint64_t)(SBO >> 4) << 32) | (1ull << 46);
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format S32 = 2 at [4,6), a/b format U8 = 0, K-major both,
+// n_dim = N >> 3 at [17,23), m_dim = M >> 4 at [24,29)
+constexpr uint32_t IDESC = (2u << 4) | ((uint32_t)(T5N >> 3) << 17) | ((uint32_t)(T5M >> 4) << 24);
+
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(IDESC), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+using Tile5 = gram::Tile;  // {i0, j0, mode, out}: out = offset (int32) of the 128 x 128 sums of this tile
+
+__global__ void __launch_bounds__(THREADS, 1) k_gram5(const uint8_t *__restrict__ P, int64_t stride, int nlines,
+                                                     int nsteps, const Tile5 *__restrict__ tiles,
+                                                     int *__restrict__ sums) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint32_t tmem_base_sh;
+  const Tile5 t = tiles[blockIdx.x];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar = sbase + STAGES * STAGE_BYTES;  // full[s] +8s, empty[s] +8(STAGES+s), done +8(2*STAGES)
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(bar + 8 * s, PROD_WARPS * 32);
+      mbar_init(bar + 8 * (STAGES + s), 1);
+    }
+    mbar_init(bar + 8 * (2 * STAGES), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == PROD_WARPS) {  // the MMA warp owns the TMEM allocation
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_base_sh;
+
+  if (warp < PROD_WARPS) {
+    // ================= producers: packed line -> bytes in UMMA core-matrix layout =================
+    const int row = threadIdx.x & 127;         // row of the operand tile
+    const int oper = threadIdx.x >> 7;         // 0: A lines (i0 + row), 1: B lines (j0 + row)
+    int line = (oper ? t.j0 : t.i0) + row;
+    line = min(max(line, 0), nlines - 1);
+    const uint8_t *src = P + (int64_t)line * stride;
+    // byte offset of this row inside an operand stage: (row / 8) * SBO + (row % 8) * 16; core matrix k16 at + k16 * LBO
+    const uint32_t row_off = (uint32_t)oper * OPER_BYTES + (row >> 3) * SBO + (row & 7) * 16;
+    uint4 cur0 = *reinterpret_cast<const uint4 *>(src), cur1 = *reinterpret_cast<const uint4 *>(src + 16);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int st = 0; st < nsteps; st++) {
+      uint4 nx0 = cur0, nx1 = cur1;
+      if (st + 1 < nsteps) {
+        nx0 = *reinterpret_cast<const uint4 *>(src + (int64_t)(st + 1) * 32);
+        nx1 = *reinterpret_cast<const uint4 *>(src + (int64_t)(st + 1) * 32 + 16);
+      }
+      mbar_wait(bar + 8 * (STAGES + stage), phase ^ 1);
+      const uint32_t dst = sbase + stage * STAGE_BYTES + row_off;
+      const uint32_t w[8] = {cur0.x, cur0.y, cur0.z, cur0.w, cur1.x, cur1.y, cur1.z, cur1.w};
+#pragma unroll
+      for (int k16 = 0; k16 < 8; k16++) {
+        const uint32_t x = w[k16];
+        sts128(dst + k16 * LBO, x & 0x03030303u, (x >> 2) & 0x03030303u, (x >> 4) & 0x03030303u, (x >> 6) & 0x03030303u);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+      mbar_arrive(bar + 8 * stage);
+      cur0 = nx0;
+      cur1 = nx1;
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else if (lane == 0) {
+    // ================= MMA issuer =================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int st = 0; st < nsteps; st++) {
+      mbar_wait(bar + 8 * stage, phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a0 = sbase + stage * STAGE_BYTES, b0 = a0 + OPER_BYTES;
+#pragma unroll
+      for (int kk = 0; kk < KSTAGE / 32; kk++) {
+        umma_i8(tmem_d, make_desc(a0 + kk * 2 * LBO), make_desc(b0 + kk * 2 * LBO), (st | kk) ? 1u : 0u);
+      }
+      umma_commit(bar + 8 * (STAGES + stage));  // stage reusable once these MMAs have read it
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    umma_commit(bar + 8 * (2 * STAGES));  // accumulator complete
+  }
+
+  // ================= epilogue: TMEM -> registers -> global (warps 0..3 own TMEM lanes 32w..32w+31) =================
+  if (warp < 4) {
+    mbar_wait(bar + 8 * (2 * STAGES), 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int r = warp * 32 + lane;
+    int *out = sums + t.out + (int64_t)r * T5N;
+#pragma unroll
+    for (int c0 = 0; c0 < T5N; c0 += 32) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int q = 0; q < 8; q++)
+        *reinterpret_cast<uint4 *>(out + c0 + 4 * q) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == PROD_WARPS) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+}  // namespace gram5
+
+// host wrapper: sums[tile] = 128 x 128 int32 Gram of lines [i0, i0+128) x [j0, j0+128) of P
+int gram5_launch(const uint8_t *P, int64_t stride, int nlines, int64_t line_bytes, const void *d_tiles, int ntiles,
+                 int *d_sums, cudaStream_t s) {
+  using namespace gram5;
+  if (ntiles == 0) return BSG_OK;
+  BSG_CUDA(cudaFuncSetAttribute(k_gram5, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  const int nsteps = (int)((line_bytes + 31) / 32);
+  k_gram5<<<ntiles, THREADS, SMEM_BYTES, s>>>(P, stride, nlines, nsteps, reinterpret_cast<const Tile5 *>(d_tiles), d_sums);
+  count_launch();
+  BSG_CUDA(cudaGetLastError());
+  return BSG_OK;
+}
+
+}  // namespace bsg

@@ -105,6 +105,10 @@ int compact_lines(const uint8_t *src, int64_t src_stride, const int *code_idx, i
                   int nlines, uint8_t *out, int64_t out_stride, cudaStream_t s);
 int line_counts(const uint8_t *P, int64_t stride, int nlines, int L, int32_t *cnt, uint8_t *na, cudaStream_t s);
 
+// ---- bsg_gram5.cu: 128 x 128 integer Gram tiles on tcgen05 / TMEM (tiles = gram::Tile array on the device)
+int gram5_launch(const uint8_t *P, int64_t stride, int nlines, int64_t line_bytes, const void *d_tiles, int ntiles,
+                 int *d_sums, cudaStream_t s);
+
 // ---- bsg_pmv.cu: packed matrix x vector on the integer tensor pipe ----------------------------
 struct PmvPlan;  // opaque, owned by a view
 }  // namespace bsg
