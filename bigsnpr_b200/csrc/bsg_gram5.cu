@@ -211,4 +211,249 @@ int gram5_launch(const uint8_t *P, int64_t stride, int nlines, int64_t line_byte
   return BSG_OK;
 }
 
+
+// ===================================================================================================
+// Weighted Gram on tcgen05 for bed_tcrossprodSelf:  K[i][j] += scale * sum_k fA(code(i,k)) * fB(code(j,k)) * d_k
+// One CTA per 128 x 128 tile of the lower triangle; passes = weight slices x plane products, each pass a
+// full sweep over k with its own TMEM accumulator (two accumulators, ping-pong), so the epilogue of pass p
+// (TMEM -> registers -> K += scale * S) overlaps the MMAs of pass p + 1.
+//   warps 0..7  producers (as k_gram5; the B operand bytes are code * digit: ((x & 1) ? d : 0) | ((x & 2) ? 2d : 0))
+//   warp  8     MMA issuer + TMEM owner
+//   warps 9..12 epilogue (TMEM lane quarter = warp % 4)
+// ===================================================================================================
+namespace wg5 {
+using namespace gram5;
+
+constexpr int EPI_WARPS = 4;
+constexpr int W5_THREADS = (PROD_WARPS + 1 + EPI_WARPS) * 32;
+constexpr int W5_TMEM_COLS = 256;  // 2 accumulators of 128 columns
+constexpr int W5_SMEM_BYTES = STAGES * STAGE_BYTES + 256;
+
+struct W5Tile {
+  int i0, j0, mode;  // mode 0: product aa only; 1: aa, an, na, nn
+};
+
+struct W5Args {
+  const uint8_t *P;
+  int64_t stride;
+  int nlines, nsteps, nslices;
+  const uint8_t *dig[3];  // W1, W2', W3 digits: [nslices][nwords * 16], 16 bytes per packed word in class order [c][r]
+  int64_t dig_stride;     // bytes per slice
+  double scale[3][10];
+  const W5Tile *tiles;
+  double *K;
+  int64_t ldk;
+};
+
+// plane of the A / B operand per product: 0 = genotype (missing -> 0), 1 = missing indicator
+__device__ __forceinline__ void pass_info(int mode, int nslices, int pass, int &prod, int &slice, int &wsel) {
+  if (mode == 0) {
+    prod = 0;
+    slice = nslices - 1 - pass;
+  } else {
+    slice = nslices - 1 - pass / 4;
+    prod = pass & 3;
+  }
+  wsel = prod == 0 ? 0 : (prod == 3 ? 2 : 1);  // aa -> W1 ; an, na -> W2' ; nn -> W3
+}
+
+__global__ void __launch_bounds__(W5_THREADS, 1) k_wgram5(const W5Args a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint32_t tmem_base_sh;
+  const W5Tile t = a.tiles[blockIdx.x];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar = sbase + STAGES * STAGE_BYTES;
+  // full[s] +8s | empty[s] +8(STAGES+s) | acc_full[b] +8(2*STAGES+b) | acc_empty[b] +8(2*STAGES+2+b)
+  const uint32_t bar_accfull = bar + 8 * (2 * STAGES), bar_accempty = bar + 8 * (2 * STAGES + 2);
+  const int npass = t.mode == 0 ? a.nslices : 4 * a.nslices;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(bar + 8 * s, PROD_WARPS * 32);
+      mbar_init(bar + 8 * (STAGES + s), 1);
+    }
+    for (int b = 0; b < 2; b++) {
+      mbar_init(bar_accfull + 8 * b, 1);
+      mbar_init(bar_accempty + 8 * b, EPI_WARPS * 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == PROD_WARPS) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
+                 "n"(W5_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_base_sh;
+
+  if (warp < PROD_WARPS) {
+    // ================= producers =================
+    const int row = threadIdx.x & 127, oper = threadIdx.x >> 7;
+    int line = (oper ? t.j0 : t.i0) + row;
+    line = min(max(line, 0), a.nlines - 1);
+    const uint8_t *src = a.P + (int64_t)line * a.stride;
+    const uint32_t row_off = (uint32_t)oper * OPER_BYTES + (row >> 3) * SBO + (row & 7) * 16;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int pass = 0; pass < npass; pass++) {
+      int prod, slice, wsel;
+      pass_info(t.mode, a.nslices, pass, prod, slice, wsel);
+      // plane of this thread's operand: A uses the missing indicator for products na (2), nn (3); B for an (1), nn (3)
+      const bool nplane = oper == 0 ? (prod >= 2) : (prod == 1 || prod == 3);
+      const bool raw = t.mode == 0;  // no missing value in the tile: the packed word is the genotype plane
+      const uint8_t *dg = a.dig[wsel] + (int64_t)slice * a.dig_stride;
+      uint4 cur0 = *reinterpret_cast<const uint4 *>(src), cur1 = *reinterpret_cast<const uint4 *>(src + 16);
+      for (int st = 0; st < a.nsteps; st++) {
+        uint4 nx0 = cur0, nx1 = cur1;
+        if (st + 1 < a.nsteps) {
+          nx0 = *reinterpret_cast<const uint4 *>(src + (int64_t)(st + 1) * 32);
+          nx1 = *reinterpret_cast<const uint4 *>(src + (int64_t)(st + 1) * 32 + 16);
+        }
+        mbar_wait(bar + 8 * (STAGES + stage), phase ^ 1);
+        const uint32_t dst = sbase + stage * STAGE_BYTES + row_off;
+        const uint32_t w[8] = {cur0.x, cur0.y, cur0.z, cur0.w, cur1.x, cur1.y, cur1.z, cur1.w};
+#pragma unroll
+        for (int k16 = 0; k16 < 8; k16++) {
+          uint32_t x = w[k16];
+          const uint32_t nmask = x & (x >> 1) & 0x55555555u;
+          if (nplane) x = nmask;
+          else if (!raw) x &= ~(nmask | (nmask << 1));
+          uint32_t o[4];
+          if (oper == 0) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) o[c] = (x >> (2 * c)) & 0x03030303u;
+          } else {
+            const uint4 d4 = __ldg(reinterpret_cast<const uint4 *>(dg + ((int64_t)st * 8 + k16) * 16));
+            const uint32_t d[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+              const uint32_t xc = x >> (2 * c);
+              const uint32_t m = (xc & 0x01010101u) * 0xFFu, hsel = ((xc >> 1) & 0x01010101u) * 0xFFu;
+              o[c] = (m & d[c]) | (hsel & (d[c] << 1));
+            }
+          }
+          sts128(dst + k16 * LBO, o[0], o[1], o[2], o[3]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(bar + 8 * stage);
+        cur0 = nx0;
+        cur1 = nx1;
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == PROD_WARPS) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pass = 0; pass < npass; pass++) {
+        const int buf = pass & 1;
+        const uint32_t use = (uint32_t)(pass >> 1);           // n-th use of this accumulator
+        mbar_wait(bar_accempty + 8 * buf, (use & 1) ^ 1);     // epilogue of the previous use has drained it
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t acc = tmem_d + buf * 128;
+        for (int st = 0; st < a.nsteps; st++) {
+          mbar_wait(bar + 8 * stage, phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a0 = sbase + stage * STAGE_BYTES, b0 = a0 + OPER_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < KSTAGE / 32; kk++)
+            umma_i8(acc, make_desc(a0 + kk * 2 * LBO), make_desc(b0 + kk * 2 * LBO), (st | kk) ? 1u : 0u);
+          umma_commit(bar + 8 * (STAGES + stage));
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(bar_accfull + 8 * buf);
+      }
+    }
+  } else {
+    // ================= epilogue warps: K += scale * S =================
+    const int q4 = warp & 3;             // TMEM lane quarter of this warp
+    const int i = t.i0 + q4 * 32 + lane; // output row of this thread
+    for (int pass = 0; pass < npass; pass++) {
+      int prod, slice, wsel;
+      pass_info(t.mode, a.nslices, pass, prod, slice, wsel);
+      const double sc = a.scale[wsel][slice];
+      const int buf = pass & 1;
+      const uint32_t use = (uint32_t)(pass >> 1);
+      mbar_wait(bar_accfull + 8 * buf, use & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int c0 = 0; c0 < T5N; c0 += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_d + ((uint32_t)(q4 * 32) << 16) + buf * 128 + c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int e = 0; e < 32; e++) {
+          const int j = t.j0 + c0 + e;
+          if (i < a.nlines && j < a.nlines && i >= j) a.K[(int64_t)j * a.ldk + i] += sc * (double)(int)v[e];
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(bar_accempty + 8 * buf);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == PROD_WARPS) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(W5_TMEM_COLS) : "memory");
+  }
+}
+
+}  // namespace wg5
+
+int wgram5_launch(const uint8_t *P, int64_t stride, int nlines, int nslices, const uint8_t *const dig[3],
+                  int64_t dig_stride, const double (*scale)[10], const int *h_tiles /* i0, j0, mode triplets */,
+                  int ntiles, double *K, int64_t ldk, cudaStream_t s) {
+  using namespace wg5;
+  if (ntiles == 0) return BSG_OK;
+  W5Tile *d_tiles = nullptr;
+  BSG_CUDA(cudaMalloc((void **)&d_tiles, (size_t)ntiles * sizeof(W5Tile)));
+  cudaError_t e = cudaMemcpyAsync(d_tiles, h_tiles, (size_t)ntiles * sizeof(W5Tile), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_wgram5, cudaFuncAttributeMaxDynamicSharedMemorySize, W5_SMEM_BYTES);
+  if (e != cudaSuccess) {
+    cudaFree(d_tiles);
+    return cuda_fail(e, "wgram5 setup");
+  }
+  W5Args a;
+  a.P = P;
+  a.stride = stride;
+  a.nlines = nlines;
+  a.nsteps = (int)((stride + 31) / 32);
+  a.nslices = nslices;
+  for (int w = 0; w < 3; w++) {
+    a.dig[w] = dig[w];
+    for (int sl = 0; sl < 10; sl++) a.scale[w][sl] = scale[w][sl];
+  }
+  a.dig_stride = dig_stride;
+  a.tiles = d_tiles;
+  a.K = K;
+  a.ldk = ldk;
+  k_wgram5<<<ntiles, W5_THREADS, W5_SMEM_BYTES, s>>>(a);
+  count_launch();
+  e = cudaGetLastError();
+  cudaError_t e2 = cudaStreamSynchronize(s);
+  cudaFree(d_tiles);
+  if (e != cudaSuccess) return cuda_fail(e, "k_wgram5 launch");
+  if (e2 != cudaSuccess) return cuda_fail(e2, "k_wgram5");
+  return BSG_OK;
+}
+
 }  // namespace bsg

@@ -109,6 +109,11 @@ int line_counts(const uint8_t *P, int64_t stride, int nlines, int L, int32_t *cn
 int gram5_launch(const uint8_t *P, int64_t stride, int nlines, int64_t line_bytes, const void *d_tiles, int ntiles,
                  int *d_sums, cudaStream_t s);
 
+// weighted Gram for the GRM on tcgen05: tiles = (i0, j0, mode) int triplets on the host, K pre-zeroed, fills i >= j
+int wgram5_launch(const uint8_t *P, int64_t stride, int nlines, int nslices, const uint8_t *const dig[3],
+                  int64_t dig_stride, const double (*scale)[10], const int *h_tiles, int ntiles, double *K,
+                  int64_t ldk, cudaStream_t s);
+
 // ---- bsg_pmv.cu: packed matrix x vector on the integer tensor pipe ----------------------------
 struct PmvPlan;  // opaque, owned by a view
 }  // namespace bsg

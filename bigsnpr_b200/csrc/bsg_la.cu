@@ -755,27 +755,51 @@ int bsg_tcrossprod(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, i
   }
 
   // ---- tiles of the lower triangle
-  std::vector<WTile> tiles;
-  const int njb = (nr + TN - 1) / TN;
-  std::vector<uint8_t> na_jb(njb, 0);
-  for (int i = 0; i < nr; i++) na_jb[i / TN] |= na[i];
-  for (int i0 = 0; i0 < nr; i0 += TM) {
-    bool na_i = false;
-    for (int b = i0 / TN; b <= std::min(nr - 1, i0 + TM - 1) / TN; b++) na_i |= na_jb[b] != 0;
-    for (int j0 = 0; j0 <= std::min(nr - 1, i0 + TM - 1); j0 += TN) tiles.push_back(WTile{i0, j0, (na_i || na_jb[j0 / TN]) ? 1 : 0});
+  static int use_t5 = -1;
+  if (use_t5 < 0) {
+    const char *ev = getenv("BSG_GRM_TCGEN05");
+    use_t5 = (ev && ev[0] == '0') ? 0 : 1;
   }
-  WTile *d_tiles = nullptr;
-  BSG_TRY(mem.alloc(&d_tiles, tiles.size()));
-  BSG_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(WTile), cudaMemcpyHostToDevice, s));
-  a.tiles = d_tiles;
+  const int TNv = use_t5 ? 128 : TN;
+  const int njb = (nr + TNv - 1) / TNv;
+  std::vector<uint8_t> na_jb(njb, 0);
+  for (int i = 0; i < nr; i++) na_jb[i / TNv] |= na[i];
   double *dK = nullptr;
   BSG_TRY(mem.alloc(&dK, (size_t)nr * nr));
   BSG_CUDA(cudaMemsetAsync(dK, 0, (size_t)nr * nr * sizeof(double), s));
-  a.K = dK;
-  a.ldk = nr;
-  k_wgram<<<(unsigned)tiles.size(), THREADS, 0, s>>>(a);
-  count_launch();
-  BSG_CUDA(cudaGetLastError());
+  if (use_t5) {
+    // 128 x 128 tiles on tcgen05 / TMEM (bsg_gram5.cu); digits are laid out 16 bytes per packed word, in order
+    std::vector<int> trip;
+    for (int i0 = 0; i0 < nr; i0 += 128) {
+      const bool na_i = na_jb[i0 / 128] != 0;
+      for (int j0 = 0; j0 <= i0; j0 += 128) {
+        trip.push_back(i0);
+        trip.push_back(j0);
+        trip.push_back((na_i || na_jb[j0 / 128]) ? 1 : 0);
+      }
+    }
+    const uint8_t *digs[3] = {a.dig[0], a.dig[1], a.dig[2]};
+    BSG_TRY(wgram5_launch(P, stride, nr, nslices, digs, (int64_t)nchunks * 256, a.scale, trip.data(), (int)(trip.size() / 3),
+                          dK, nr, s));
+  } else {
+    std::vector<WTile> tiles;
+    for (int i0 = 0; i0 < nr; i0 += TM) {
+      bool na_i = false;
+      for (int b = i0 / TN; b <= std::min(nr - 1, i0 + TM - 1) / TN; b++) na_i |= na_jb[b] != 0;
+      for (int j0 = 0; j0 <= std::min(nr - 1, i0 + TM - 1); j0 += TN)
+        tiles.push_back(WTile{i0, j0, (na_i || na_jb[j0 / TN]) ? 1 : 0});
+    }
+    WTile *d_tiles = nullptr;
+    BSG_TRY(mem.alloc(&d_tiles, tiles.size()));
+    BSG_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(WTile), cudaMemcpyHostToDevice, s));
+    a.tiles = d_tiles;
+    a.K = dK;
+    a.ldk = nr;
+    k_wgram<<<(unsigned)tiles.size(), THREADS, 0, s>>>(a);
+    count_launch();
+    BSG_CUDA(cudaGetLastError());
+    BSG_CUDA(cudaStreamSynchronize(s));
+  }
 
   // ---- vector terms through the matvec engine:  r = A w2 ;  q = N w3 = (X~_{c=1,s=1} w3) - A w3 + sum(w3)
   double *d_r = nullptr, *d_q = nullptr, *d_t1 = nullptr;
