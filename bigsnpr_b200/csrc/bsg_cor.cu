@@ -463,12 +463,13 @@ static int to_dev(T **dst, const std::vector<T> &v, cudaStream_t s) {
 
 struct CorScratch {
   uint8_t *M = nullptr;
+  bool own_M = true;  // false: M aliases the handle's SNP-major copy (identity rows and columns)
   int *wlen = nullptr, *reach = nullptr;
   long long *boff = nullptr;
   double *thr = nullptr, *band = nullptr, *res = nullptr;
   uint8_t *keep = nullptr;
   ~CorScratch() {
-    void *p[] = {M, wlen, reach, boff, thr, band, res, keep};
+    void *p[] = {own_M ? M : nullptr, wlen, reach, boff, thr, band, res, keep};
     for (void *q : p)
       if (q) cudaFree(q);
   }
@@ -481,14 +482,29 @@ static int cor_common(bsg_bed *h, const int *ind_row, int nr, const int *ind_col
   BSG_TRY(upload_index(h, ind_row, nr, h->n, h->w_idx_row, &d_row));
   BSG_TRY(upload_index(h, ind_col, nc, h->m, h->w_idx_col, &d_col));
   build_window(pos, nc, size, w);
+  // identity rows and columns: the staged SNP-major copy already is the dense matrix (stride multiple of 128)
+  auto ident = [](const int *ind, int len, int lim) {
+    if (!ind) return true;
+    if (len != lim) return false;
+    for (int i = 0; i < len; i++)
+      if (ind[i] != i + 1) return false;
+    return true;
+  };
+  const bool direct = ident(ind_row, nr, h->n) && ident(ind_col, nc, h->m);
   int64_t stride = round_up(((int64_t)nr + 3) / 4, 64);
   if (stride < 64) stride = 64;
-  BSG_CUDA(cudaMalloc((void **)&sc.M, (size_t)stride * (nc > 0 ? nc : 1)));
-  if (nc > 0) {
-    int64_t work = (int64_t)nc * (stride / 4);
-    int grid = (int)std::min<int64_t>((work + 255) / 256, 148 * 32);
-    k_compact<<<grid, 256, 0, s>>>(h->A, h->strideA, d_row, nr, d_col, nc, sc.M, stride);
-    count_launch();
+  if (direct) {
+    sc.M = h->A;
+    sc.own_M = false;
+    stride = h->strideA;
+  } else {
+    BSG_CUDA(cudaMalloc((void **)&sc.M, (size_t)stride * (nc > 0 ? nc : 1)));
+    if (nc > 0) {
+      int64_t work = (int64_t)nc * (stride / 4);
+      int grid = (int)std::min<int64_t>((work + 255) / 256, 148 * 32);
+      k_compact<<<grid, 256, 0, s>>>(h->A, h->strideA, d_row, nr, d_col, nc, sc.M, stride);
+      count_launch();
+    }
   }
   BSG_TRY(to_dev(&sc.wlen, w.wlen, s));
   BSG_TRY(to_dev(&sc.boff, w.boff, s));

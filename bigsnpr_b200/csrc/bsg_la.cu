@@ -44,6 +44,34 @@ __global__ void k_dots(const double *__restrict__ V, int64_t ld, int ncols, cons
   }
 }
 
+// two-stage deterministic version for long vectors: part[j * nsplit + b] = partial dot of block b
+__global__ void k_dots_part(const double *__restrict__ V, int64_t ld, int ncols, const double *__restrict__ w, int N,
+                            int nsplit, double *__restrict__ part) {
+  __shared__ double sh[32];
+  const int j = blockIdx.y, b = blockIdx.x;
+  const double *v = V + (int64_t)j * ld;
+  const int chunk = (N + nsplit - 1) / nsplit;
+  const int i0 = b * chunk, i1 = min(N, i0 + chunk);
+  double acc = 0;
+  for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) acc += v[i] * w[i];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); k++) t += sh[k];
+    part[(int64_t)j * nsplit + b] = t;
+  }
+}
+__global__ void k_dots_final(const double *__restrict__ part, int ncols, int nsplit, double *__restrict__ h) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ncols) return;
+  double t = 0;
+  for (int b = 0; b < nsplit; b++) t += part[(int64_t)j * nsplit + b];
+  h[j] = t;
+}
+
 // w[i] -= sum_j V[i, j] * h[j]
 __global__ void k_axpys(const double *__restrict__ V, int64_t ld, int ncols, const double *__restrict__ h, int N,
                         double *__restrict__ w) {
@@ -343,9 +371,9 @@ __global__ void k_grm_weights(const double *__restrict__ center, const double *_
 }  // namespace wgram
 
 struct SvdWork {
-  double *V = nullptr, *w = nullptr, *tmp = nullptr, *h = nullptr, *S = nullptr, *Y = nullptr;
+  double *V = nullptr, *w = nullptr, *tmp = nullptr, *h = nullptr, *S = nullptr, *Y = nullptr, *part = nullptr;
   ~SvdWork() {
-    void *p[] = {V, w, tmp, h, S, Y};
+    void *p[] = {V, w, tmp, h, S, Y, part};
     for (void *q : p)
       if (q) cudaFree(q);
   }
@@ -415,6 +443,14 @@ int bsg_randomsvd_ex(bsg_bed *h, const int *ind_row, int nr, const int *ind_col,
   BSG_CUDA(cudaMalloc((void **)&W.h, (size_t)(ncv + 2) * sizeof(double)));
   BSG_CUDA(cudaMalloc((void **)&W.S, (size_t)ncv * ncv * sizeof(double)));
   BSG_CUDA(cudaMalloc((void **)&W.Y, (size_t)ld * ncv * sizeof(double)));
+  const int NSPLIT = 32;
+  BSG_CUDA(cudaMalloc((void **)&W.part, (size_t)(ncv + 2) * NSPLIT * sizeof(double)));
+  auto dots = [&](const double *Vp, int cnt, const double *wp) {  // W.h[j] = <V[:, j], w>, deterministic
+    dim3 g(NSPLIT, cnt);
+    k_dots_part<<<g, 256, 0, s>>>(Vp, ld, cnt, wp, N, NSPLIT, W.part);
+    k_dots_final<<<(cnt + 63) / 64, 64, 0, s>>>(W.part, cnt, NSPLIT, W.h);
+    count_launch(2);
+  };
   double *wv = nullptr;  // work vector of length N; the caller's buffer when results are reduced across ranks
   if (reduce_cb && z_dev) {
     wv = z_dev;
@@ -446,15 +482,14 @@ int bsg_randomsvd_ex(bsg_bed *h, const int *ind_row, int nr, const int *ind_col,
   auto orth = [&](int cnt, std::vector<double> &coef, double &nrm) -> int {
     coef.assign(cnt, 0.0);
     for (int pass = 0; pass < 2 && cnt > 0; pass++) {
-      k_dots<<<cnt, 512, 0, s>>>(W.V, ld, cnt, wv, N, W.h);
+      dots(W.V, cnt, wv);
       k_axpys<<<gblocks(N), TB, 0, s>>>(W.V, ld, cnt, W.h, N, wv);
-      count_launch(2);
+      count_launch();
       BSG_CUDA(cudaMemcpyAsync(hh.data(), W.h, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, s));
       BSG_CUDA(cudaStreamSynchronize(s));
       for (int j = 0; j < cnt; j++) coef[j] += hh[j];
     }
-    k_dots<<<1, 512, 0, s>>>(wv, ld, 1, wv, N, W.h);
-    count_launch();
+    dots(wv, 1, wv);
     BSG_CUDA(cudaMemcpyAsync(hh.data(), W.h, sizeof(double), cudaMemcpyDeviceToHost, s));
     BSG_CUDA(cudaStreamSynchronize(s));
     nrm = sqrt(hh[0]);
