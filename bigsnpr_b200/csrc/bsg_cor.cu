@@ -560,7 +560,8 @@ static int cor_common(bsg_bed *h, const int *ind_row, int nr, const int *ind_col
       const char *ev = getenv("BSG_GRAM5");
       use_g5 = (ev && ev[0] == '0') ? 0 : 1;
     }
-    const bool g5 = clean && use_g5;
+    const bool g5 = use_g5 != 0;  // tcgen05 tiles (128 x 128): missing-free tiles one product, the others six planes
+    (void)clean;
     const int TNv = g5 ? 128 : TN;
     // any-missing flag per column block
     const int njb = (nc + TNv - 1) / TNv;
@@ -615,7 +616,9 @@ static int cor_common(bsg_bed *h, const int *ind_row, int nr, const int *ind_col
       cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice, s);
       cudaMemcpyAsync(d_rbs, rbs.data(), rbs.size() * sizeof(RowBlock), cudaMemcpyHostToDevice, s);
       if (g5) {
-        int rc5 = gram5_launch(sc.M, stride, nc, stride, d_tiles, (int)tiles.size(), d_sums, s);
+        bool any0 = false, any1 = false;
+        for (const Tile &tl : tiles) (tl.mode ? any1 : any0) = true;
+        int rc5 = gram5_launch(sc.M, stride, nc, stride, d_tiles, (int)tiles.size(), d_sums, any0, any1, s);
         if (rc5) {
           cudaFree(d_tiles);
           cudaFree(d_rbs);

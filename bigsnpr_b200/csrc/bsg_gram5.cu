@@ -16,6 +16,7 @@
 //                      K = 32, u8 x u8 -> s32 accumulator in TMEM), tcgen05.commit -> frees the stage.
 //   4 epilogue warps : tcgen05.ld 32x32b.x32 of the 128 x 128 int32 accumulator, 16-byte stores of the tile sums.
 #include <stdint.h>
+#include <string.h>
 
 #include "bsg_gram.cuh"
 #include "bsg_internal.cuh"
@@ -86,6 +87,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gram5(const uint8_t *__restrict_
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint32_t tmem_base_sh;
   const Tile5 t = tiles[blockIdx.x];
+  if (t.mode != 0) return;  // tiles with missing values are done by the six-plane kernel
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar = sbase + STAGES * STAGE_BYTES;  // full[s] +8s, empty[s] +8(STAGES+s), done +8(2*STAGES)
@@ -198,20 +200,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_gram5(const uint8_t *__restrict_
 
 }  // namespace gram5
 
-// host wrapper: sums[tile] = 128 x 128 int32 Gram of lines [i0, i0+128) x [j0, j0+128) of P
-int gram5_launch(const uint8_t *P, int64_t stride, int nlines, int64_t line_bytes, const void *d_tiles, int ntiles,
-                 int *d_sums, cudaStream_t s) {
-  using namespace gram5;
-  if (ntiles == 0) return BSG_OK;
-  BSG_CUDA(cudaFuncSetAttribute(k_gram5, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  const int nsteps = (int)((line_bytes + 31) / 32);
-  k_gram5<<<ntiles, THREADS, SMEM_BYTES, s>>>(P, stride, nlines, nsteps, reinterpret_cast<const Tile5 *>(d_tiles), d_sums);
-  count_launch();
-  BSG_CUDA(cudaGetLastError());
-  return BSG_OK;
-}
-
-
 // ===================================================================================================
 // Weighted Gram on tcgen05 for bed_tcrossprodSelf:  K[i][j] += scale * sum_k fA(code(i,k)) * fB(code(j,k)) * d_k
 // One CTA per 128 x 128 tile of the lower triangle; passes = weight slices x plane products, each pass a
@@ -237,6 +225,8 @@ struct W5Args {
   const uint8_t *P;
   int64_t stride;
   int nlines, nsteps, nslices;
+  const gram::Tile *ctiles;  // KIND 1: correlation tiles {i0, j0, mode, out}
+  int *sums;                 // KIND 1: [tile.out + prod * 128 * 128 + row * 128 + col]
   const uint8_t *dig[3];  // W1, W2', W3 digits: [nslices][nwords * 16], 16 bytes per packed word in class order [c][r]
   int64_t dig_stride;     // bytes per slice
   double scale[3][10];
@@ -257,16 +247,34 @@ __device__ __forceinline__ void pass_info(int mode, int nslices, int pass, int &
   wsel = prod == 0 ? 0 : (prod == 3 ? 2 : 1);  // aa -> W1 ; an, na -> W2' ; nn -> W3
 }
 
+// planes of the pairwise-complete statistics (KIND 1), products in the order k_cor_from_sums reads them:
+// aa (xySum), bb (nona), ab (xSum), ba (ySum), hb, bh  with a = genotype (NA -> 0), b = valid, h = [genotype == 2]
+__device__ __forceinline__ uint32_t cor_plane(uint32_t x, int pl) {
+  const uint32_t n = x & (x >> 1) & 0x55555555u;
+  const uint32_t av = x & ~(n | (n << 1));
+  return pl == 0 ? av : (pl == 1 ? (~n & 0x55555555u) : ((av >> 1) & 0x55555555u));
+}
+
+template <int KIND>
 __global__ void __launch_bounds__(W5_THREADS, 1) k_wgram5(const W5Args a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint32_t tmem_base_sh;
-  const W5Tile t = a.tiles[blockIdx.x];
+  W5Tile t;
+  long long out_off = 0;
+  if (KIND == 0) {
+    t = a.tiles[blockIdx.x];
+  } else {
+    const gram::Tile ct = a.ctiles[blockIdx.x];
+    if (ct.mode == 0) return;  // missing-free tiles are done by k_gram5
+    t = W5Tile{ct.i0, ct.j0, 1};
+    out_off = ct.out;
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar = sbase + STAGES * STAGE_BYTES;
   // full[s] +8s | empty[s] +8(STAGES+s) | acc_full[b] +8(2*STAGES+b) | acc_empty[b] +8(2*STAGES+2+b)
   const uint32_t bar_accfull = bar + 8 * (2 * STAGES), bar_accempty = bar + 8 * (2 * STAGES + 2);
-  const int npass = t.mode == 0 ? a.nslices : 4 * a.nslices;
+  const int npass = KIND == 1 ? 6 : (t.mode == 0 ? a.nslices : 4 * a.nslices);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) {
@@ -300,12 +308,14 @@ __global__ void __launch_bounds__(W5_THREADS, 1) k_wgram5(const W5Args a) {
     int stage = 0;
     uint32_t phase = 0;
     for (int pass = 0; pass < npass; pass++) {
-      int prod, slice, wsel;
-      pass_info(t.mode, a.nslices, pass, prod, slice, wsel);
+      int prod = pass, slice = 0, wsel = 0;
+      if (KIND == 0) pass_info(t.mode, a.nslices, pass, prod, slice, wsel);
       // plane of this thread's operand: A uses the missing indicator for products na (2), nn (3); B for an (1), nn (3)
       const bool nplane = oper == 0 ? (prod >= 2) : (prod == 1 || prod == 3);
       const bool raw = t.mode == 0;  // no missing value in the tile: the packed word is the genotype plane
-      const uint8_t *dg = a.dig[wsel] + (int64_t)slice * a.dig_stride;
+      const uint8_t *dg = KIND == 0 ? a.dig[wsel] + (int64_t)slice * a.dig_stride : nullptr;
+      // KIND 1 planes per product: A = {a, b, a, b, h, b}, B = {a, b, b, a, b, h}
+      const int cpl = oper == 0 ? ((0x121010 >> (4 * prod)) & 0xF) : ((0x210110 >> (4 * prod)) & 0xF);
       uint4 cur0 = *reinterpret_cast<const uint4 *>(src), cur1 = *reinterpret_cast<const uint4 *>(src + 16);
       for (int st = 0; st < a.nsteps; st++) {
         uint4 nx0 = cur0, nx1 = cur1;
@@ -319,11 +329,15 @@ __global__ void __launch_bounds__(W5_THREADS, 1) k_wgram5(const W5Args a) {
 #pragma unroll
         for (int k16 = 0; k16 < 8; k16++) {
           uint32_t x = w[k16];
-          const uint32_t nmask = x & (x >> 1) & 0x55555555u;
-          if (nplane) x = nmask;
-          else if (!raw) x &= ~(nmask | (nmask << 1));
+          if (KIND == 1) {
+            x = cor_plane(x, cpl);
+          } else {
+            const uint32_t nmask = x & (x >> 1) & 0x55555555u;
+            if (nplane) x = nmask;
+            else if (!raw) x &= ~(nmask | (nmask << 1));
+          }
           uint32_t o[4];
-          if (oper == 0) {
+          if (oper == 0 || KIND == 1) {
 #pragma unroll
             for (int c = 0; c < 4; c++) o[c] = (x >> (2 * c)) & 0x03030303u;
           } else {
@@ -380,9 +394,9 @@ __global__ void __launch_bounds__(W5_THREADS, 1) k_wgram5(const W5Args a) {
     const int q4 = warp & 3;             // TMEM lane quarter of this warp
     const int i = t.i0 + q4 * 32 + lane; // output row of this thread
     for (int pass = 0; pass < npass; pass++) {
-      int prod, slice, wsel;
-      pass_info(t.mode, a.nslices, pass, prod, slice, wsel);
-      const double sc = a.scale[wsel][slice];
+      int prod = pass, slice = 0, wsel = 0;
+      if (KIND == 0) pass_info(t.mode, a.nslices, pass, prod, slice, wsel);
+      const double sc = KIND == 0 ? a.scale[wsel][slice] : 0.0;
       const int buf = pass & 1;
       const uint32_t use = (uint32_t)(pass >> 1);
       mbar_wait(bar_accfull + 8 * buf, use & 1);
@@ -400,10 +414,17 @@ __global__ void __launch_bounds__(W5_THREADS, 1) k_wgram5(const W5Args a) {
               "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (KIND == 0) {
 #pragma unroll
-        for (int e = 0; e < 32; e++) {
-          const int j = t.j0 + c0 + e;
-          if (i < a.nlines && j < a.nlines && i >= j) a.K[(int64_t)j * a.ldk + i] += sc * (double)(int)v[e];
+          for (int e = 0; e < 32; e++) {
+            const int j = t.j0 + c0 + e;
+            if (i < a.nlines && j < a.nlines && i >= j) a.K[(int64_t)j * a.ldk + i] += sc * (double)(int)v[e];
+          }
+        } else {
+          int *dst = a.sums + out_off + (int64_t)pass * (T5M * T5N) + (int64_t)(q4 * 32 + lane) * T5N + c0;
+#pragma unroll
+          for (int e4 = 0; e4 < 8; e4++)
+            *reinterpret_cast<uint4 *>(dst + 4 * e4) = make_uint4(v[4 * e4], v[4 * e4 + 1], v[4 * e4 + 2], v[4 * e4 + 3]);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -427,7 +448,7 @@ int wgram5_launch(const uint8_t *P, int64_t stride, int nlines, int nslices, con
   W5Tile *d_tiles = nullptr;
   BSG_CUDA(cudaMalloc((void **)&d_tiles, (size_t)ntiles * sizeof(W5Tile)));
   cudaError_t e = cudaMemcpyAsync(d_tiles, h_tiles, (size_t)ntiles * sizeof(W5Tile), cudaMemcpyHostToDevice, s);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_wgram5, cudaFuncAttributeMaxDynamicSharedMemorySize, W5_SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_wgram5<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, W5_SMEM_BYTES);
   if (e != cudaSuccess) {
     cudaFree(d_tiles);
     return cuda_fail(e, "wgram5 setup");
@@ -444,9 +465,11 @@ int wgram5_launch(const uint8_t *P, int64_t stride, int nlines, int nslices, con
   }
   a.dig_stride = dig_stride;
   a.tiles = d_tiles;
+  a.ctiles = nullptr;
+  a.sums = nullptr;
   a.K = K;
   a.ldk = ldk;
-  k_wgram5<<<ntiles, W5_THREADS, W5_SMEM_BYTES, s>>>(a);
+  k_wgram5<0><<<ntiles, W5_THREADS, W5_SMEM_BYTES, s>>>(a);
   count_launch();
   e = cudaGetLastError();
   cudaError_t e2 = cudaStreamSynchronize(s);
@@ -455,5 +478,37 @@ int wgram5_launch(const uint8_t *P, int64_t stride, int nlines, int nslices, con
   if (e2 != cudaSuccess) return cuda_fail(e2, "k_wgram5");
   return BSG_OK;
 }
+
+// host wrapper: sums[tile] = 128 x 128 int32 Gram of lines [i0, i0+128) x [j0, j0+128) of P
+int gram5_launch(const uint8_t *P, int64_t stride, int nlines, int64_t line_bytes, const void *d_tiles, int ntiles,
+                 int *d_sums, bool any_clean, bool any_na, cudaStream_t s) {
+  using namespace gram5;
+  if (ntiles == 0) return BSG_OK;
+  BSG_CUDA(cudaFuncSetAttribute(k_gram5, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  const int nsteps = (int)((line_bytes + 31) / 32);
+  if (any_clean) {
+    k_gram5<<<ntiles, THREADS, SMEM_BYTES, s>>>(P, stride, nlines, nsteps, reinterpret_cast<const Tile5 *>(d_tiles), d_sums);
+    count_launch();
+  }
+  if (any_na) {
+    using namespace wg5;
+    BSG_CUDA(cudaFuncSetAttribute(k_wgram5<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, W5_SMEM_BYTES));
+    W5Args a;
+    memset(&a, 0, sizeof a);
+    a.P = P;
+    a.stride = stride;
+    a.nlines = nlines;
+    a.nsteps = nsteps;
+    a.nslices = 1;
+    a.ctiles = reinterpret_cast<const gram::Tile *>(d_tiles);
+    a.sums = d_sums;
+    k_wgram5<1><<<ntiles, W5_THREADS, W5_SMEM_BYTES, s>>>(a);
+    count_launch();
+  }
+  BSG_CUDA(cudaGetLastError());
+  return BSG_OK;
+}
+
+
 
 }  // namespace bsg

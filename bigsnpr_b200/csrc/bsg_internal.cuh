@@ -107,7 +107,7 @@ int line_counts(const uint8_t *P, int64_t stride, int nlines, int L, int32_t *cn
 
 // ---- bsg_gram5.cu: 128 x 128 integer Gram tiles on tcgen05 / TMEM (tiles = gram::Tile array on the device)
 int gram5_launch(const uint8_t *P, int64_t stride, int nlines, int64_t line_bytes, const void *d_tiles, int ntiles,
-                 int *d_sums, cudaStream_t s);
+                 int *d_sums, bool any_clean, bool any_na, cudaStream_t s);
 
 // weighted Gram for the GRM on tcgen05: tiles = (i0, j0, mode) int triplets on the host, K pre-zeroed, fills i >= j
 int wgram5_launch(const uint8_t *P, int64_t stride, int nlines, int nslices, const uint8_t *const dig[3],
