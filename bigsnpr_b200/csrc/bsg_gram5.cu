@@ -27,6 +27,7 @@ namespace gram5 {
 constexpr int T5M = 128, T5N = 128;      // tile of line pairs
 constexpr int KSTAGE = 128;              // codes per line per stage (32 packed bytes) = 4 MMAs of K = 32
 constexpr int STAGES = 3;
+constexpr int PF = 3;                    // stages of register prefetch per producer thread
 constexpr int PROD_WARPS = 8;            // 256 producer threads: thread t expands line t (0..127 A, 128..255 B)
 constexpr int THREADS = (PROD_WARPS + 1) * 32;
 constexpr int OPER_BYTES = 128 * KSTAGE;  // 16 KB per operand and stage
@@ -120,30 +121,42 @@ __global__ void __launch_bounds__(THREADS, 1) k_gram5(const uint8_t *__restrict_
     const uint8_t *src = P + (int64_t)line * stride;
     // byte offset of this row inside an operand stage: (row / 8) * SBO + (row % 8) * 16; core matrix k16 at + k16 * LBO
     const uint32_t row_off = (uint32_t)oper * OPER_BYTES + (row >> 3) * SBO + (row & 7) * 16;
-    uint4 cur0 = *reinterpret_cast<const uint4 *>(src), cur1 = *reinterpret_cast<const uint4 *>(src + 16);
+    // register prefetch ring: PF stages of this line in flight (2 x LDG.128 each)
+    uint4 pf[PF][2];
+#pragma unroll
+    for (int u = 0; u < PF; u++) {
+      pf[u][0] = pf[u][1] = make_uint4(0, 0, 0, 0);
+      if (u < nsteps) {
+        pf[u][0] = *reinterpret_cast<const uint4 *>(src + (int64_t)u * 32);
+        pf[u][1] = *reinterpret_cast<const uint4 *>(src + (int64_t)u * 32 + 16);
+      }
+    }
     int stage = 0;
     uint32_t phase = 0;
-    for (int st = 0; st < nsteps; st++) {
-      uint4 nx0 = cur0, nx1 = cur1;
-      if (st + 1 < nsteps) {
-        nx0 = *reinterpret_cast<const uint4 *>(src + (int64_t)(st + 1) * 32);
-        nx1 = *reinterpret_cast<const uint4 *>(src + (int64_t)(st + 1) * 32 + 16);
-      }
-      mbar_wait(bar + 8 * (STAGES + stage), phase ^ 1);
-      const uint32_t dst = sbase + stage * STAGE_BYTES + row_off;
-      const uint32_t w[8] = {cur0.x, cur0.y, cur0.z, cur0.w, cur1.x, cur1.y, cur1.z, cur1.w};
+    for (int st0 = 0; st0 < nsteps; st0 += PF) {
 #pragma unroll
-      for (int k16 = 0; k16 < 8; k16++) {
-        const uint32_t x = w[k16];
-        sts128(dst + k16 * LBO, x & 0x03030303u, (x >> 2) & 0x03030303u, (x >> 4) & 0x03030303u, (x >> 6) & 0x03030303u);
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
-      mbar_arrive(bar + 8 * stage);
-      cur0 = nx0;
-      cur1 = nx1;
-      if (++stage == STAGES) {
-        stage = 0;
-        phase ^= 1;
+      for (int u = 0; u < PF; u++) {
+        const int st = st0 + u;
+        if (st >= nsteps) break;
+        const uint4 cur0 = pf[u][0], cur1 = pf[u][1];
+        if (st + PF < nsteps) {
+          pf[u][0] = *reinterpret_cast<const uint4 *>(src + (int64_t)(st + PF) * 32);
+          pf[u][1] = *reinterpret_cast<const uint4 *>(src + (int64_t)(st + PF) * 32 + 16);
+        }
+        mbar_wait(bar + 8 * (STAGES + stage), phase ^ 1);
+        const uint32_t dst = sbase + stage * STAGE_BYTES + row_off;
+        const uint32_t w[8] = {cur0.x, cur0.y, cur0.z, cur0.w, cur1.x, cur1.y, cur1.z, cur1.w};
+#pragma unroll
+        for (int k16 = 0; k16 < 8; k16++) {
+          const uint32_t x = w[k16];
+          sts128(dst + k16 * LBO, x & 0x03030303u, (x >> 2) & 0x03030303u, (x >> 4) & 0x03030303u, (x >> 6) & 0x03030303u);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+        mbar_arrive(bar + 8 * stage);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
     }
   } else if (lane == 0) {
@@ -316,49 +329,60 @@ __global__ void __launch_bounds__(W5_THREADS, 1) k_wgram5(const W5Args a) {
       const uint8_t *dg = KIND == 0 ? a.dig[wsel] + (int64_t)slice * a.dig_stride : nullptr;
       // KIND 1 planes per product: A = {a, b, a, b, h, b}, B = {a, b, b, a, b, h}
       const int cpl = oper == 0 ? ((0x121010 >> (4 * prod)) & 0xF) : ((0x210110 >> (4 * prod)) & 0xF);
-      uint4 cur0 = *reinterpret_cast<const uint4 *>(src), cur1 = *reinterpret_cast<const uint4 *>(src + 16);
-      for (int st = 0; st < a.nsteps; st++) {
-        uint4 nx0 = cur0, nx1 = cur1;
-        if (st + 1 < a.nsteps) {
-          nx0 = *reinterpret_cast<const uint4 *>(src + (int64_t)(st + 1) * 32);
-          nx1 = *reinterpret_cast<const uint4 *>(src + (int64_t)(st + 1) * 32 + 16);
+      uint4 pf[PF][2];
+#pragma unroll
+      for (int u = 0; u < PF; u++) {
+        pf[u][0] = pf[u][1] = make_uint4(0, 0, 0, 0);
+        if (u < a.nsteps) {
+          pf[u][0] = *reinterpret_cast<const uint4 *>(src + (int64_t)u * 32);
+          pf[u][1] = *reinterpret_cast<const uint4 *>(src + (int64_t)u * 32 + 16);
         }
-        mbar_wait(bar + 8 * (STAGES + stage), phase ^ 1);
-        const uint32_t dst = sbase + stage * STAGE_BYTES + row_off;
-        const uint32_t w[8] = {cur0.x, cur0.y, cur0.z, cur0.w, cur1.x, cur1.y, cur1.z, cur1.w};
+      }
+      for (int st0 = 0; st0 < a.nsteps; st0 += PF) {
 #pragma unroll
-        for (int k16 = 0; k16 < 8; k16++) {
-          uint32_t x = w[k16];
-          if (KIND == 1) {
-            x = cor_plane(x, cpl);
-          } else {
-            const uint32_t nmask = x & (x >> 1) & 0x55555555u;
-            if (nplane) x = nmask;
-            else if (!raw) x &= ~(nmask | (nmask << 1));
+        for (int u = 0; u < PF; u++) {
+          const int st = st0 + u;
+          if (st >= a.nsteps) break;
+          const uint4 cur0 = pf[u][0], cur1 = pf[u][1];
+          if (st + PF < a.nsteps) {
+            pf[u][0] = *reinterpret_cast<const uint4 *>(src + (int64_t)(st + PF) * 32);
+            pf[u][1] = *reinterpret_cast<const uint4 *>(src + (int64_t)(st + PF) * 32 + 16);
           }
-          uint32_t o[4];
-          if (oper == 0 || KIND == 1) {
+          mbar_wait(bar + 8 * (STAGES + stage), phase ^ 1);
+          const uint32_t dst = sbase + stage * STAGE_BYTES + row_off;
+          const uint32_t w[8] = {cur0.x, cur0.y, cur0.z, cur0.w, cur1.x, cur1.y, cur1.z, cur1.w};
 #pragma unroll
-            for (int c = 0; c < 4; c++) o[c] = (x >> (2 * c)) & 0x03030303u;
-          } else {
-            const uint4 d4 = __ldg(reinterpret_cast<const uint4 *>(dg + ((int64_t)st * 8 + k16) * 16));
-            const uint32_t d[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-              const uint32_t xc = x >> (2 * c);
-              const uint32_t m = (xc & 0x01010101u) * 0xFFu, hsel = ((xc >> 1) & 0x01010101u) * 0xFFu;
-              o[c] = (m & d[c]) | (hsel & (d[c] << 1));
+          for (int k16 = 0; k16 < 8; k16++) {
+            uint32_t x = w[k16];
+            if (KIND == 1) {
+              x = cor_plane(x, cpl);
+            } else {
+              const uint32_t nmask = x & (x >> 1) & 0x55555555u;
+              if (nplane) x = nmask;
+              else if (!raw) x &= ~(nmask | (nmask << 1));
             }
+            uint32_t o[4];
+            if (oper == 0 || KIND == 1) {
+#pragma unroll
+              for (int c = 0; c < 4; c++) o[c] = (x >> (2 * c)) & 0x03030303u;
+            } else {
+              const uint4 d4 = __ldg(reinterpret_cast<const uint4 *>(dg + ((int64_t)st * 8 + k16) * 16));
+              const uint32_t d[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+              for (int c = 0; c < 4; c++) {
+                const uint32_t xc = x >> (2 * c);
+                const uint32_t m = (xc & 0x01010101u) * 0xFFu, hsel = ((xc >> 1) & 0x01010101u) * 0xFFu;
+                o[c] = (m & d[c]) | (hsel & (d[c] << 1));
+              }
+            }
+            sts128(dst + k16 * LBO, o[0], o[1], o[2], o[3]);
           }
-          sts128(dst + k16 * LBO, o[0], o[1], o[2], o[3]);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(bar + 8 * stage);
-        cur0 = nx0;
-        cur1 = nx1;
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(bar + 8 * stage);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     }
