@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gram5(const uint8_t *__restrict_
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) {
-      mbar_init(bar + 8 * s, PROD_WARPS * 32);
+      mbar_init(bar + 8 * s, PROD_WARPS);  // one arrive per producer warp
       mbar_init(bar + 8 * (STAGES + s), 1);
     }
     mbar_init(bar + 8 * (2 * STAGES), 1);
@@ -152,7 +152,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_gram5(const uint8_t *__restrict_
           sts128(dst + k16 * LBO, x & 0x03030303u, (x >> 2) & 0x03030303u, (x >> 4) & 0x03030303u, (x >> 6) & 0x03030303u);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
-        mbar_arrive(bar + 8 * stage);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar + 8 * stage);
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
@@ -291,7 +292,7 @@ __global__ void __launch_bounds__(W5_THREADS, 1) k_wgram5(const W5Args a) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) {
-      mbar_init(bar + 8 * s, PROD_WARPS * 32);
+      mbar_init(bar + 8 * s, PROD_WARPS);  // one arrive per producer warp
       mbar_init(bar + 8 * (STAGES + s), 1);
     }
     for (int b = 0; b < 2; b++) {
@@ -378,7 +379,8 @@ __global__ void __launch_bounds__(W5_THREADS, 1) k_wgram5(const W5Args a) {
             sts128(dst + k16 * LBO, o[0], o[1], o[2], o[3]);
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_arrive(bar + 8 * stage);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar + 8 * stage);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
