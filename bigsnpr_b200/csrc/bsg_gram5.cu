@@ -25,9 +25,11 @@ namespace bsg {
 namespace gram5 {
 
 constexpr int T5M = 128, T5N = 128;      // tile of line pairs
-constexpr int KSTAGE = 128;              // codes per line per stage (32 packed bytes) = 4 MMAs of K = 32
+constexpr int KSTAGE = 256;              // codes per line per stage (64 packed bytes) = 8 MMAs of K = 32
+constexpr int SBYTES = KSTAGE / 4;       // packed bytes per line per stage
+constexpr int NW = KSTAGE / 16;          // packed words (= core matrices along K) per line per stage
 constexpr int STAGES = 3;
-constexpr int PF = 3;                    // stages of register prefetch per producer thread
+constexpr int PF = 2;                    // stages of register prefetch per producer thread
 constexpr int PROD_WARPS = 8;            // 256 producer threads: thread t expands line t (0..127 A, 128..255 B)
 constexpr int THREADS = (PROD_WARPS + 1) * 32;
 constexpr int OPER_BYTES = 128 * KSTAGE;  // 16 KB per operand and stage
@@ -122,14 +124,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_gram5(const uint8_t *__restrict_
     // byte offset of this row inside an operand stage: (row / 8) * SBO + (row % 8) * 16; core matrix k16 at + k16 * LBO
     const uint32_t row_off = (uint32_t)oper * OPER_BYTES + (row >> 3) * SBO + (row & 7) * 16;
     // register prefetch ring: PF stages of this line in flight (2 x LDG.128 each)
-    uint4 pf[PF][2];
+    uint4 pf[PF][NW / 4];
 #pragma unroll
     for (int u = 0; u < PF; u++) {
-      pf[u][0] = pf[u][1] = make_uint4(0, 0, 0, 0);
-      if (u < nsteps) {
-        pf[u][0] = *reinterpret_cast<const uint4 *>(src + (int64_t)u * 32);
-        pf[u][1] = *reinterpret_cast<const uint4 *>(src + (int64_t)u * 32 + 16);
-      }
+#pragma unroll
+      for (int v = 0; v < NW / 4; v++)
+        pf[u][v] = u < nsteps ? *reinterpret_cast<const uint4 *>(src + (int64_t)u * SBYTES + 16 * v) : make_uint4(0, 0, 0, 0);
     }
     int stage = 0;
     uint32_t phase = 0;
@@ -138,16 +138,20 @@ __global__ void __launch_bounds__(THREADS, 1) k_gram5(const uint8_t *__restrict_
       for (int u = 0; u < PF; u++) {
         const int st = st0 + u;
         if (st >= nsteps) break;
-        const uint4 cur0 = pf[u][0], cur1 = pf[u][1];
+        uint32_t w[NW];
+#pragma unroll
+        for (int v = 0; v < NW / 4; v++) {
+          w[4 * v] = pf[u][v].x; w[4 * v + 1] = pf[u][v].y; w[4 * v + 2] = pf[u][v].z; w[4 * v + 3] = pf[u][v].w;
+        }
         if (st + PF < nsteps) {
-          pf[u][0] = *reinterpret_cast<const uint4 *>(src + (int64_t)(st + PF) * 32);
-          pf[u][1] = *reinterpret_cast<const uint4 *>(src + (int64_t)(st + PF) * 32 + 16);
+#pragma unroll
+          for (int v = 0; v < NW / 4; v++)
+            pf[u][v] = *reinterpret_cast<const uint4 *>(src + (int64_t)(st + PF) * SBYTES + 16 * v);
         }
         mbar_wait(bar + 8 * (STAGES + stage), phase ^ 1);
         const uint32_t dst = sbase + stage * STAGE_BYTES + row_off;
-        const uint32_t w[8] = {cur0.x, cur0.y, cur0.z, cur0.w, cur1.x, cur1.y, cur1.z, cur1.w};
 #pragma unroll
-        for (int k16 = 0; k16 < 8; k16++) {
+        for (int k16 = 0; k16 < NW; k16++) {
           const uint32_t x = w[k16];
           sts128(dst + k16 * LBO, x & 0x03030303u, (x >> 2) & 0x03030303u, (x >> 4) & 0x03030303u, (x >> 6) & 0x03030303u);
         }
@@ -330,30 +334,32 @@ __global__ void __launch_bounds__(W5_THREADS, 1) k_wgram5(const W5Args a) {
       const uint8_t *dg = KIND == 0 ? a.dig[wsel] + (int64_t)slice * a.dig_stride : nullptr;
       // KIND 1 planes per product: A = {a, b, a, b, h, b}, B = {a, b, b, a, b, h}
       const int cpl = oper == 0 ? ((0x121010 >> (4 * prod)) & 0xF) : ((0x210110 >> (4 * prod)) & 0xF);
-      uint4 pf[PF][2];
+      uint4 pf[PF][NW / 4];
 #pragma unroll
       for (int u = 0; u < PF; u++) {
-        pf[u][0] = pf[u][1] = make_uint4(0, 0, 0, 0);
-        if (u < a.nsteps) {
-          pf[u][0] = *reinterpret_cast<const uint4 *>(src + (int64_t)u * 32);
-          pf[u][1] = *reinterpret_cast<const uint4 *>(src + (int64_t)u * 32 + 16);
-        }
+#pragma unroll
+        for (int v = 0; v < NW / 4; v++)
+          pf[u][v] = u < a.nsteps ? *reinterpret_cast<const uint4 *>(src + (int64_t)u * SBYTES + 16 * v) : make_uint4(0, 0, 0, 0);
       }
       for (int st0 = 0; st0 < a.nsteps; st0 += PF) {
 #pragma unroll
         for (int u = 0; u < PF; u++) {
           const int st = st0 + u;
           if (st >= a.nsteps) break;
-          const uint4 cur0 = pf[u][0], cur1 = pf[u][1];
+          uint32_t w[NW];
+#pragma unroll
+          for (int v = 0; v < NW / 4; v++) {
+            w[4 * v] = pf[u][v].x; w[4 * v + 1] = pf[u][v].y; w[4 * v + 2] = pf[u][v].z; w[4 * v + 3] = pf[u][v].w;
+          }
           if (st + PF < a.nsteps) {
-            pf[u][0] = *reinterpret_cast<const uint4 *>(src + (int64_t)(st + PF) * 32);
-            pf[u][1] = *reinterpret_cast<const uint4 *>(src + (int64_t)(st + PF) * 32 + 16);
+#pragma unroll
+            for (int v = 0; v < NW / 4; v++)
+              pf[u][v] = *reinterpret_cast<const uint4 *>(src + (int64_t)(st + PF) * SBYTES + 16 * v);
           }
           mbar_wait(bar + 8 * (STAGES + stage), phase ^ 1);
           const uint32_t dst = sbase + stage * STAGE_BYTES + row_off;
-          const uint32_t w[8] = {cur0.x, cur0.y, cur0.z, cur0.w, cur1.x, cur1.y, cur1.z, cur1.w};
 #pragma unroll
-          for (int k16 = 0; k16 < 8; k16++) {
+          for (int k16 = 0; k16 < NW; k16++) {
             uint32_t x = w[k16];
             if (KIND == 1) {
               x = cor_plane(x, cpl);
@@ -367,7 +373,7 @@ __global__ void __launch_bounds__(W5_THREADS, 1) k_wgram5(const W5Args a) {
 #pragma unroll
               for (int c = 0; c < 4; c++) o[c] = (x >> (2 * c)) & 0x03030303u;
             } else {
-              const uint4 d4 = __ldg(reinterpret_cast<const uint4 *>(dg + ((int64_t)st * 8 + k16) * 16));
+              const uint4 d4 = __ldg(reinterpret_cast<const uint4 *>(dg + ((int64_t)st * NW + k16) * 16));
               const uint32_t d[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
               for (int c = 0; c < 4; c++) {
@@ -483,7 +489,7 @@ int wgram5_launch(const uint8_t *P, int64_t stride, int nlines, int nslices, con
   a.P = P;
   a.stride = stride;
   a.nlines = nlines;
-  a.nsteps = (int)((stride + 31) / 32);
+  a.nsteps = (int)((stride + SBYTES - 1) / SBYTES);
   a.nslices = nslices;
   for (int w = 0; w < 3; w++) {
     a.dig[w] = dig[w];
@@ -511,7 +517,7 @@ int gram5_launch(const uint8_t *P, int64_t stride, int nlines, int64_t line_byte
   using namespace gram5;
   if (ntiles == 0) return BSG_OK;
   BSG_CUDA(cudaFuncSetAttribute(k_gram5, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  const int nsteps = (int)((line_bytes + 31) / 32);
+  const int nsteps = (int)((line_bytes + SBYTES - 1) / SBYTES);
   if (any_clean) {
     k_gram5<<<ntiles, THREADS, SMEM_BYTES, s>>>(P, stride, nlines, nsteps, reinterpret_cast<const Tile5 *>(d_tiles), d_sums);
     count_launch();
