@@ -25,7 +25,8 @@ namespace bsg {
 namespace gram5 {
 
 constexpr int T5M = 128, T5N = 128;      // tile of line pairs
-constexpr int KSTAGE = 256;              // codes per line per stage (64 packed bytes) = 8 MMAs of K = 32
+constexpr int KSTAGE = 128;              // codes per line per stage (32 packed bytes) = 4 MMAs of K = 32; 96 KB of
+                                         // stages -> 2 CTAs per SM (measured: 256-code stages halve occupancy, GRM 212 vs 135 ms)
 constexpr int SBYTES = KSTAGE / 4;       // packed bytes per line per stage
 constexpr int NW = KSTAGE / 16;          // packed words (= core matrices along K) per line per stage
 constexpr int STAGES = 3;
