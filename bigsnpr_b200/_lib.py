@@ -51,6 +51,8 @@ SIGNATURES = {
                           c_i64_p, C.POINTER(c_int_p), C.POINTER(c_dbl_p)]),
     "bsg_ld_scores": (C.c_int, [vp, c_int_p, C.c_int, c_int_p, C.c_int, C.c_double, c_dbl_p, c_dbl_p]),
     "bsg_free": (None, [vp]),
+    "bsg_clumping_chr": (C.c_int, [vp, c_int_p, C.c_int, c_int_p, C.c_int, c_dbl_p, c_dbl_p, c_int_p, c_dbl_p, C.c_double,
+                                   C.c_double, c_int_p]),
     "bsg_tcrossprod": (C.c_int, [vp, c_int_p, C.c_int, c_int_p, C.c_int, c_dbl_p, c_dbl_p, c_dbl_p]),
     "bsg_randomsvd": (C.c_int, [vp, c_int_p, C.c_int, c_int_p, C.c_int, c_dbl_p, c_dbl_p, C.c_int, C.c_double,
                                 C.c_int, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, c_int_p, c_int_p]),

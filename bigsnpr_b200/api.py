@@ -146,6 +146,23 @@ class Bed:
         return np.arange(1, self.ncol + 1, dtype=np.int32)
 
     @property
+    def map(self):
+        """`$map` of the RefClass (R/bed-class.R:87-93): chromosome (str) and physical.pos read lazily from the .bim."""
+        if getattr(self, "_map", None) is None:
+            if not self.bedfile or self.bedfile.startswith("<"):
+                raise ValueError("this handle has no .bim file: pass infos_chr / infos_pos")
+            chrom, pos = [], []
+            with open(self.bedfile[:-4] + ".bim") as f:
+                for line in f:
+                    p = line.split()
+                    chrom.append(p[0])
+                    pos.append(float(p[3]))
+            off = getattr(self, "col_offset", 0)
+            self._map = {"chromosome": np.array(chrom)[off:off + self.ncol],
+                         "physical.pos": np.array(pos)[off:off + self.ncol]}
+        return self._map
+
+    @property
     def has_na(self):
         return bool(lib().bsg_has_na(self._h))
 
@@ -498,3 +515,53 @@ def bed_randomSVD(obj_bed, fun_scaling=bed_scaleBinom, ind_row=..., ind_col=...,
     check(lib().bsg_randomsvd(obj_bed._h, _pi(ind_row), n, _pi(ind_col), m, _pd(center), _pd(scale), int(k), float(tol),
                               int(maxit), _pd(d), _pd(u), _pd(v), _pd(c_out), _pd(s_out), C.byref(niter), C.byref(nops)))
     return {"d": d, "u": u.T, "v": v.T, "niter": niter.value, "nops": nops.value, "center": c_out, "scale": s_out}
+
+
+def bed_clumping_chr(obj_bed, ind_row, ind_col, center, scale, ordInd, rankInd, pos, size, thr, ncores=1):
+    """src/clumping-bed.cpp:11-91 -> keep (int32 0/1 per column of ind_col).  rankInd is implied by ordInd."""
+    ind_row, ind_col, ordInd = _i32(ind_row), _i32(ind_col), _i32(ordInd)
+    center, scale, pos = _f64(center), _f64(scale), _f64(pos)
+    for v in (center, scale, pos, ordInd):
+        if v.size != ind_col.size:
+            raise ValueError(ERROR_DIM)
+    keep = np.full(ind_col.size, -1, dtype=np.int32)
+    check(lib().bsg_clumping_chr(obj_bed._h, _pi(ind_row), ind_row.size, _pi(ind_col), ind_col.size, _pd(center),
+                                 _pd(scale), _pi(ordInd), _pd(pos), float(size), float(thr), _pi(keep)))
+    return keep
+
+
+def bed_clumping(obj_bed, ind_row=..., S=None, thr_r2=0.2, size=None, exclude=None, ncores=1, infos_chr=None,
+                 infos_pos=None):
+    """LD clumping on a bed object (R/bed-clumping.R:7-74): sorted 1-based indices of the variants kept."""
+    _assert_bed(obj_bed)
+    if ind_row is None:
+        raise ValueError("'ind.row' can't be `NULL`.")
+    ind_row = obj_bed.rows_along() if ind_row is ... else _i32(ind_row)
+    if size is None:
+        size = 100 / thr_r2
+    if infos_chr is None:
+        infos_chr = obj_bed.map["chromosome"]
+    if infos_pos is None:
+        infos_pos = obj_bed.map["physical.pos"]
+    infos_chr, infos_pos = np.asarray(infos_chr), _f64(infos_pos)
+    m = obj_bed.ncol
+    if S is not None:
+        _assert_lengths(infos_chr, S)
+    noexcl = np.setdiff1d(np.arange(1, m + 1), np.asarray([] if exclude is None else exclude, dtype=np.int64))
+    kept = []
+    for chrom in sorted(set(infos_chr[noexcl - 1].tolist())):
+        ind_chr = noexcl[infos_chr[noexcl - 1] == chrom].astype(np.int32)
+        st = bed_colstats(obj_bed, ind_row, ind_chr, ncores)
+        with np.errstate(all="ignore"):
+            center = st["sumX"] / st["nb_nona_col"]
+            scale = np.sqrt(st["denoX"])
+        S_chr = np.minimum(st["sumX"], 2 * st["nb_nona_col"] - st["sumX"]) if S is None else np.asarray(S)[ind_chr - 1]
+        ordv = (np.argsort(-np.asarray(S_chr, dtype=np.float64), kind="stable") + 1).astype(np.int32)
+        pos_chr = infos_pos[ind_chr - 1]
+        if np.any(np.diff(pos_chr) < 0):
+            raise ValueError("'pos.chr' is not sorted.")
+        keep = bed_clumping_chr(obj_bed, ind_row, ind_chr, center, scale, ordv, None, pos_chr, size * 1000.0, thr_r2, ncores)
+        if not np.all((keep == 0) | (keep == 1)):
+            raise RuntimeError("clumping left undecided variants")
+        kept.append(ind_chr[keep == 1])
+    return np.sort(np.concatenate(kept)) if kept else np.zeros(0, dtype=np.int32)

@@ -319,12 +319,16 @@ struct RowBlock {
 };
 
 // fp64 epilogue per pair (j0, j0-1-k), same operation order as src/corr.cpp:77-80 / src/ld-scores.cpp:63-66
-template <bool LD>
+// KIND 0: correlation (r, keep by threshold) ; 1: LD (r^2) ; 2: clumping conflict flag: the reference's scaled dot
+// product r = sum_i x~_ij x~_ij0 with x~ = (g - c) / s, missing -> 0 (src/clumping-bed.cpp:69-75), written from the
+// same integer sums: r = (aa - c_j ab - c_j0 ba + c_j0 c_j bb) / (s_j0 s_j); keep = r^2 > thr.
+template <int KIND>
 __global__ void k_cor_from_sums(const int *__restrict__ sums, const Tile *__restrict__ tiles,
                                 const RowBlock *__restrict__ rbs, int ib0, int j0_begin, int j0_end,
                                 const int *__restrict__ wlen, const long long *__restrict__ boff,
                                 const int32_t *__restrict__ cnt, int nrow, int npad, const double *__restrict__ thr,
-                                double *__restrict__ band, uint8_t *__restrict__ keep, int tn) {
+                                double *__restrict__ band, uint8_t *__restrict__ keep, int tn,
+                                const double *__restrict__ center, const double *__restrict__ scale, double thr_r2) {
   const long long first = boff[j0_begin], total = boff[j0_end] - first;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     // locate j0 by binary search on boff
@@ -360,10 +364,16 @@ __global__ void k_cor_from_sums(const int *__restrict__ sums, const Tile *__rest
       xySum = (double)aa;
     }
     (void)nona_d;
+    if (KIND == 2) {
+      const double cx = center[j0], cy = center[j];
+      const double r = (xySum - cy * xSum - cx * ySum + cx * cy * (double)nona) / (scale[j0] * scale[j]);
+      keep[o] = (r * r > thr_r2) ? 1 : 0;
+      continue;
+    }
     const double num = xySum - xSum * ySum / nona;
     const double deno_x = xxSum - xSum * xSum / nona;
     const double deno_y = yySum - ySum * ySum / nona;
-    if (LD) {
+    if (KIND == 1) {
       band[o] = num * num / (deno_x * deno_y);
     } else {
       double r = num / sqrt(deno_x * deno_y);
@@ -475,8 +485,14 @@ struct CorScratch {
   }
 };
 
+struct ClumpParams {
+  const double *center = nullptr, *scale = nullptr;  // host, per selected column
+  double thr = 0;
+};
+
 static int cor_common(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, double size,
-                      const double *pos, const double *thr, bool ld, Window &w, CorScratch &sc) {
+                      const double *pos, const double *thr, bool ld, Window &w, CorScratch &sc,
+                      const ClumpParams *clump = nullptr) {
   cudaStream_t s = h->stream;
   const int *d_row = nullptr, *d_col = nullptr;
   BSG_TRY(upload_index(h, ind_row, nr, h->n, h->w_idx_row, &d_row));
@@ -508,19 +524,29 @@ static int cor_common(bsg_bed *h, const int *ind_row, int nr, const int *ind_col
   }
   BSG_TRY(to_dev(&sc.wlen, w.wlen, s));
   BSG_TRY(to_dev(&sc.boff, w.boff, s));
-  BSG_CUDA(cudaMalloc((void **)&sc.band, (size_t)(w.total ? w.total : 1) * sizeof(double)));
-  if (!ld) {
-    std::vector<double> t(thr, thr + nr);
-    if (t.empty()) t.push_back(0.0);
-    BSG_TRY(to_dev(&sc.thr, t, s));
+  double *d_cc = nullptr, *d_cs = nullptr;
+  if (clump) {
+    std::vector<double> c(clump->center, clump->center + nc), sv(clump->scale, clump->scale + nc);
+    BSG_TRY(to_dev(&d_cc, c, s));
+    BSG_TRY(to_dev(&d_cs, sv, s));
+    sc.thr = d_cc;   // owned by the scratch (freed with it)
+    sc.res = d_cs;
     BSG_CUDA(cudaMalloc((void **)&sc.keep, (size_t)(w.total ? w.total : 1)));
+  } else {
+    BSG_CUDA(cudaMalloc((void **)&sc.band, (size_t)(w.total ? w.total : 1) * sizeof(double)));
+    if (!ld) {
+      std::vector<double> t(thr, thr + nr);
+      if (t.empty()) t.push_back(0.0);
+      BSG_TRY(to_dev(&sc.thr, t, s));
+      BSG_CUDA(cudaMalloc((void **)&sc.keep, (size_t)(w.total ? w.total : 1)));
+    }
   }
   static int use_popc = -1;
   if (use_popc < 0) {
     const char *ev = getenv("BSG_COR_POPC");
     use_popc = (ev && ev[0] == '1') ? 1 : 0;
   }
-  if (nc > 0 && use_popc) {
+  if (nc > 0 && use_popc && !clump) {
     if (ld)
       k_cor_pairs<true><<<nc, 256, 0, s>>>(sc.M, stride, nr, nc, sc.wlen, sc.boff, nullptr, sc.band, nullptr);
     else
@@ -630,12 +656,15 @@ static int cor_common(bsg_bed *h, const int *ind_row, int nr, const int *ind_col
       }
       const long long npairs = w.boff[j0_end] - w.boff[j0_begin];
       const int eg = (int)std::min<long long>((npairs + 255) / 256, 148 * 16);
-      if (ld)
-        k_cor_from_sums<true><<<eg, 256, 0, s>>>(d_sums, d_tiles, d_rbs, ib_start, j0_begin, j0_end, sc.wlen, sc.boff, d_cnt,
-                                                 nr, npad, nullptr, sc.band, nullptr, TNv);
+      if (clump)
+        k_cor_from_sums<2><<<eg, 256, 0, s>>>(d_sums, d_tiles, d_rbs, ib_start, j0_begin, j0_end, sc.wlen, sc.boff, d_cnt, nr,
+                                              npad, nullptr, nullptr, sc.keep, TNv, d_cc, d_cs, clump->thr);
+      else if (ld)
+        k_cor_from_sums<1><<<eg, 256, 0, s>>>(d_sums, d_tiles, d_rbs, ib_start, j0_begin, j0_end, sc.wlen, sc.boff, d_cnt, nr,
+                                              npad, nullptr, sc.band, nullptr, TNv, nullptr, nullptr, 0.0);
       else
-        k_cor_from_sums<false><<<eg, 256, 0, s>>>(d_sums, d_tiles, d_rbs, ib_start, j0_begin, j0_end, sc.wlen, sc.boff, d_cnt,
-                                                  nr, npad, sc.thr, sc.band, sc.keep, TNv);
+        k_cor_from_sums<0><<<eg, 256, 0, s>>>(d_sums, d_tiles, d_rbs, ib_start, j0_begin, j0_end, sc.wlen, sc.boff, d_cnt, nr,
+                                              npad, sc.thr, sc.band, sc.keep, TNv, nullptr, nullptr, 0.0);
       count_launch(2);
       cudaError_t e2 = cudaStreamSynchronize(s);
       cudaFree(d_tiles);
@@ -745,6 +774,55 @@ int bsg_ld_scores(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, in
   count_launch();
   BSG_CUDA(cudaMemcpyAsync(out, sc.res, (size_t)nc * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   BSG_CUDA(cudaStreamSynchronize(h->stream));
+  return BSG_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
+
+// bed_clumping_chr: src/clumping-bed.cpp:11-91 (+ which_to_check, src/clumping-utils.h:12-43).
+// ordInd: 1-based column positions by decreasing priority (R: order(S, decreasing = TRUE)); keep[nc] receives 0 / 1.
+// All pair statistics inside the window come from the Gram tiles; the greedy pass in rank order runs on the host.
+int bsg_clumping_chr(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, const double *center,
+                     const double *scale, const int *ordInd, const double *pos, double size, double thr, int *keep) {
+  if (!h || !center || !scale || !ordInd || !pos || !keep) return fail(BSG_ERR_ARG, "null argument");
+  BSG_TRY(bind_device(h));
+  if (!ind_row) nr = h->n;
+  if (!ind_col) nc = h->m;
+  Window w;
+  CorScratch sc;
+  ClumpParams cp;
+  cp.center = center;
+  cp.scale = scale;
+  cp.thr = thr;
+  BSG_TRY(cor_common(h, ind_row, nr, ind_col, nc, size, pos, nullptr, false, w, sc, &cp));
+  std::vector<uint8_t> conflict((size_t)w.total);
+  if (w.total)
+    BSG_CUDA(cudaMemcpyAsync(conflict.data(), sc.keep, (size_t)w.total, cudaMemcpyDeviceToHost, h->stream));
+  BSG_CUDA(cudaStreamSynchronize(h->stream));
+  std::vector<int> rank(nc);
+  for (int k = 0; k < nc; k++) {
+    int j = ordInd[k] - 1;
+    if (j < 0 || j >= nc) return fail(BSG_ERR_BOUNDS, "Tested subscript out of bounds (ordInd).");
+    rank[j] = k;
+  }
+  for (int j = 0; j < nc; j++) keep[j] = -1;
+  for (int k = 0; k < nc; k++) {
+    const int j0 = ordInd[k] - 1;
+    int keep_j0 = 1;
+    // left neighbours: pairs (j0, j) of j0's own window; right neighbours: j0 is in the window of j
+    for (int t = 0; t < w.wlen[j0] && keep_j0; t++) {
+      const int j = j0 - 1 - t;
+      if (rank[j] < k && keep[j] == 1 && conflict[(size_t)(w.boff[j0] + t)]) keep_j0 = 0;
+    }
+    for (int j = j0 + 1; j < nc && keep_j0; j++) {
+      const int t = j - 1 - j0;
+      if (t >= w.wlen[j]) break;  // positions are sorted: once j0 leaves the window of j it stays out
+      if (rank[j] < k && keep[j] == 1 && conflict[(size_t)(w.boff[j] + t)]) keep_j0 = 0;
+    }
+    keep[j0] = keep_j0;
+  }
   return BSG_OK;
 }
 

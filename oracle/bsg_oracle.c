@@ -555,6 +555,67 @@ int orc_ld_scores(int kind, const uint8_t *mat, int n_tot, int m_tot, const doub
   return ORC_OK;
 }
 
+/* src/clumping-utils.h:12-43  which_to_check : neighbours of j0 inside the window with a better rank that are
+ * not (yet) pruned, alternating right / left by increasing distance. */
+static int which_to_check(int j0, const int *keep, const int *rankInd, const double *pos, int m, double size,
+                          int *out) {
+  int cnt = 0;
+  double pos_min = pos[j0] - size, pos_max = pos[j0] + size;
+  int not_min = 1, not_max = 1;
+  for (int k = 1; not_max || not_min; k++) {
+    if (not_max) {
+      int j = j0 + k;
+      not_max = (j < m) && (pos[j] <= pos_max);
+      if (not_max && (rankInd[j0] > rankInd[j]) && (keep[j] != 0)) out[cnt++] = j;
+    }
+    if (not_min) {
+      int j = j0 - k;
+      not_min = (j >= 0) && (pos[j] >= pos_min);
+      if (not_min && (rankInd[j0] > rankInd[j]) && (keep[j] != 0)) out[cnt++] = j;
+    }
+  }
+  return cnt;
+}
+
+/* src/clumping-bed.cpp:11-91  bed_clumping_chr : greedy clumping in rank order on scaled dot products
+ * r = sum_i macc(i, j) * macc(i, j0) (missing -> 0 after scaling).  Restated for one thread: the reference's
+ * OpenMP version spin-waits on keep[] so that its result is the same for any ncores
+ * (tests/testthat/test-2-bed-clumping-SVD.R:83). keep must come in filled with -1. */
+int orc_bed_clumping_chr(const uint8_t *bed, int n_tot, int m_tot, const int *ind_row, int nr, const int *ind_col,
+                         int nc, const double *center, const double *scale, const int *ordInd,
+                         const int *rankInd, const double *pos, double size, double thr, int *keep) {
+  acc_t a;
+  int rc = acc_init(&a, 0, bed, n_tot, m_tot, NULL, ind_row, nr, ind_col, nc);
+  if (rc) { acc_free(&a); return rc; }
+  double *ls = build_lookup_scale(nc, center, scale);
+  int *chk = (int *)malloc((size_t)(nc ? nc : 1) * sizeof(int));
+  if (!ls || !chk) { free(ls); free(chk); acc_free(&a); return ORC_ERR_ALLOC; }
+  size_t n = nr, m = nc;
+  for (size_t k = 0; k < m; k++) {
+    size_t j0 = (size_t)ordInd[k] - 1;
+    int nb_check = which_to_check((int)j0, keep, rankInd, pos, (int)m, size, chk);
+    int keep_j0 = 1;
+    for (int k2 = 0; k2 < nb_check; k2++) {
+      int jk = chk[k2];
+      if (keep[jk] == 0) continue; /* pruned: nothing to check (one thread: never -1 here) */
+      size_t j = (size_t)jk;
+      double r = 0;
+      for (size_t i = 0; i < n; i++)
+        r += ls[bed_get(&a, i, j) + 4 * j] * ls[bed_get(&a, i, j0) + 4 * j0];
+      double r2 = r * r;
+      if (r2 > thr) {
+        keep_j0 = 0;
+        break;
+      }
+    }
+    keep[j0] = keep_j0;
+  }
+  free(ls);
+  free(chk);
+  acc_free(&a);
+  return ORC_OK;
+}
+
 /* Synthetic .bed generator, the CPU twin of the device generator
  * (bigsnpr_b200/csrc/bsg_core.cu: k_synth): per-SNP maf ~ U(0.02, 0.5), g ~ Binomial(2, maf), missing with
  * probability na_rate; written in the .bed bit layout of src/write-plink.cpp:29-47 (pads = 00). */

@@ -483,6 +483,61 @@ def bed_randomSVD(obj, fun_scaling=bed_scaleBinom, ind_row=None, ind_col=None, k
     return {"d": d[:k], "u": u[:, :k], "v": vt[:k].T, "center": ms["center"], "scale": ms["scale"]}
 
 
+def read_bim(bedfile):
+    """chromosome (as str) and physical position columns of the .bim (NAMES.MAP, R/utils.R:50-51)."""
+    chrom, pos = [], []
+    with open(bedfile[:-4] + ".bim") as f:
+        for line in f:
+            p = line.split()
+            chrom.append(p[0])
+            pos.append(float(p[3]))
+    return np.array(chrom), np.array(pos)
+
+
+def bed_clumping_chr(obj, ind_row, ind_col, center, scale, ordInd, rankInd, pos, size, thr):
+    """src/clumping-bed.cpp:11-91 -> keep (int32 0/1 per column of ind_col)."""
+    ind_row, ind_col = _i32(ind_row), _i32(ind_col)
+    keep = np.full(ind_col.size, -1, dtype=np.int32)
+    center, scale, pos = _f64(center), _f64(scale), _f64(pos)
+    ordInd, rankInd = _i32(ordInd), _i32(rankInd)
+    with np.errstate(all="ignore"):
+        _chk(lib().orc_bed_clumping_chr(_p(obj.bytes, C.c_uint8), obj.nrow, obj.ncol, _p(ind_row, C.c_int),
+                                        ind_row.size, _p(ind_col, C.c_int), ind_col.size, _p(center, C.c_double),
+                                        _p(scale, C.c_double), _p(ordInd, C.c_int), _p(rankInd, C.c_int),
+                                        _p(pos, C.c_double), C.c_double(size), C.c_double(thr), _p(keep, C.c_int)))
+    return keep
+
+
+def bed_clumping(obj, ind_row=None, S=None, thr_r2=0.2, size=None, exclude=None, infos_chr=None, infos_pos=None,
+                 clump_chr=bed_clumping_chr):
+    """R/bed-clumping.R:7-74 (bed_clumping + bedClumpingChr) -> sorted 1-based indices of the kept variants."""
+    if size is None:
+        size = 100 / thr_r2
+    if infos_chr is None or infos_pos is None:
+        infos_chr, infos_pos = read_bim(obj.bedfile)
+    ind_row = obj.rows_along() if ind_row is None else _i32(ind_row)
+    m = obj.ncol
+    noexcl = np.setdiff1d(np.arange(1, m + 1), np.asarray([] if exclude is None else exclude, dtype=np.int64))
+    kept = []
+    for chrom in sorted(set(infos_chr[noexcl - 1].tolist())):  # split(ind.noexcl, infos.chr[ind.noexcl])
+        ind_chr = noexcl[infos_chr[noexcl - 1] == chrom].astype(np.int32)
+        st = bed_colstats(obj, ind_row, ind_chr)
+        with np.errstate(all="ignore"):
+            center = st["sumX"] / st["nb_nona_col"]
+            scale = np.sqrt(st["denoX"])
+        S_chr = np.minimum(st["sumX"], 2 * st["nb_nona_col"] - st["sumX"]) if S is None else np.asarray(S)[ind_chr - 1]
+        ordv = np.argsort(-np.asarray(S_chr, dtype=np.float64), kind="stable") + 1  # order(S.chr, decreasing = TRUE)
+        rank = np.empty_like(ordv)
+        rank[ordv - 1] = np.arange(1, ordv.size + 1)  # match(seq_along(ord), ord)
+        pos_chr = infos_pos[ind_chr - 1]
+        if np.any(np.diff(pos_chr) < 0):
+            raise OracleError("'pos.chr' is not sorted.")
+        keep = clump_chr(obj, ind_row, ind_chr, center, scale, ordv, rank, pos_chr, size * 1000.0, thr_r2)
+        assert np.all((keep == 0) | (keep == 1))
+        kept.append(ind_chr[keep == 1])
+    return np.sort(np.concatenate(kept)) if kept else np.zeros(0, dtype=np.int32)
+
+
 def synth_bed(n, m, seed=20250924, na_rate=0.0, col_offset=0) -> "OracleBed":
     """CPU twin of the device synthetic generator (same counter-based RNG), as an OracleBed."""
     nb = (n + 3) // 4

@@ -323,3 +323,24 @@ def test_randomsvd_and_grm(B, gbed, gbed_na, oracle, obed, obed_na):
         assert np.max(np.abs(svd["u"].mean(0))) < 1.5e-8  # expect_equal tolerance of the reference, tol = 1e-4
     with pytest.raises(ValueError, match="can't be `NULL`"):
         B.bed_randomSVD(gbed, ind_row=None)
+
+
+def test_clumping_identical_to_oracle(B, gbed, gbed_na, oracle, obed, obed_na, rng):
+    # tests/testthat/test-2-bed-clumping-SVD.R:28-49,62-70,83: kept indices identical; window rescaling invariance;
+    # `exclude`; ncores accepted.  (clumping.rds pins snp_clumping with a GWAS-derived S: not reproducible here.)
+    for g, o in ((gbed, obed), (gbed_na, obed_na)):
+        want = oracle.bed_clumping(o)
+        got = B.bed_clumping(g, ncores=2)
+        assert np.array_equal(got, want)
+        for kw in (dict(thr_r2=0.05), dict(thr_r2=0.5, size=50), dict(exclude=np.arange(1, 101))):
+            assert np.array_equal(B.bed_clumping(g, **kw), oracle.bed_clumping(o, **kw))
+        S = rng.uniform(size=o.ncol)
+        assert np.array_equal(B.bed_clumping(g, S=S), oracle.bed_clumping(o, S=S))
+        ir = rng.choice(o.nrow, o.nrow // 2, replace=False) + 1
+        assert np.array_equal(B.bed_clumping(g, ind_row=ir), oracle.bed_clumping(o, ind_row=ir))
+        chrom, pos = g.map["chromosome"], g.map["physical.pos"]
+        k2 = B.bed_clumping(g, infos_chr=chrom, infos_pos=pos * 1e6, size=500 * 1e6)
+        assert np.array_equal(k2, want)
+    assert B.bed_clumping(gbed, exclude=np.arange(1, 101)).min() > 100
+    with pytest.raises(ValueError, match="can't be `NULL`"):
+        B.bed_clumping(gbed, ind_row=None)
