@@ -214,6 +214,19 @@ SEXP _bigsnpr_ld_scores(SEXP obj, SEXP rowInd, SEXP colInd, SEXP size, SEXP pos,
   return out;
 }
 
+/* _bigsnpr_bed_clumping_chr: src/clumping-bed.cpp:11-91 (12 arguments, keep is the integer FBM BM2 written in place;
+ * rankInd is implied by ordInd).  BM2$address_rw is bigstatsr's XPtr<FBM_RW>: the shim writes through as.integer
+ * storage obtained from R -- here via the helper `fbm_int_ptr`. */
+extern int *fbm_int_ptr(SEXP BM2); /* provided by the package glue: pointer to the mmap'ed int matrix of an FBM */
+SEXP _bigsnpr_bed_clumping_chr(SEXP obj_bed, SEXP BM2, SEXP ind_row, SEXP ind_col, SEXP center, SEXP scale, SEXP ordInd,
+                               SEXP rankInd, SEXP pos, SEXP size, SEXP thr, SEXP ncores) {
+  bsg_bed *h = handle_of(obj_bed);
+  int nr = LENGTH(ind_row), nc = LENGTH(ind_col);
+  chk(bsg_clumping_chr(h, INTEGER(ind_row), nr, INTEGER(ind_col), nc, REAL(center), REAL(scale), INTEGER(ordInd), REAL(pos),
+                       Rf_asReal(size), Rf_asReal(thr), fbm_int_ptr(BM2)));
+  return R_NilValue;
+}
+
 /* new entry points: R/bed-tcrossprodSelf.R's block loop and R/autoSVD.R's bed_randomSVD collapse to one call each */
 SEXP _bigsnpr_bed_tcrossprod_gpu(SEXP obj_bed, SEXP ind_row, SEXP ind_col, SEXP center, SEXP scale) {
   bsg_bed *h = handle_of(obj_bed);
@@ -257,6 +270,7 @@ static const R_CallMethodDef CallEntries[] = {
     {"_bigsnpr_snp_colstats", (DL_FUNC)&_bigsnpr_snp_colstats, 4},
     {"_bigsnpr_corMat", (DL_FUNC)&_bigsnpr_corMat, 8},
     {"_bigsnpr_ld_scores", (DL_FUNC)&_bigsnpr_ld_scores, 6},
+    {"_bigsnpr_bed_clumping_chr", (DL_FUNC)&_bigsnpr_bed_clumping_chr, 12},
     {"_bigsnpr_bed_tcrossprod_gpu", (DL_FUNC)&_bigsnpr_bed_tcrossprod_gpu, 5},
     {"_bigsnpr_bed_randomSVD_gpu", (DL_FUNC)&_bigsnpr_bed_randomSVD_gpu, 7},
     {NULL, NULL, 0}};

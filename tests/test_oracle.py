@@ -187,3 +187,25 @@ def test_grm_matches_svd(oracle, obed_na):
     ev = np.linalg.eigvalsh(K)[::-1][:10]
     svd = oracle.bed_randomSVD(obed_na, ind_col=ind_col, k=10)
     np.testing.assert_allclose(np.sqrt(ev), svd["d"], rtol=1e-10)
+
+
+def test_clumping_relational(oracle, obed, obed_na):
+    # tests/testthat/test-2-bed-clumping-SVD.R:34-39,47-49: rescaling positions and window together changes nothing,
+    # excluded variants never come back, pruning is monotone in the threshold; kept variants are pairwise below thr.
+    chrom, pos = oracle.read_bim(obed.bedfile)
+    k = oracle.bed_clumping(obed)
+    assert len(k) == 4270 and k.min() >= 1 and k.max() <= obed.ncol and np.all(np.diff(k) > 0)
+    assert np.array_equal(oracle.bed_clumping(obed, infos_chr=chrom, infos_pos=pos * 1e6, size=500 * 1e6), k)
+    assert np.array_equal(oracle.bed_clumping(obed, infos_chr=chrom, infos_pos=pos / 1e6, size=500 / 1e6), k)
+    assert oracle.bed_clumping(obed, exclude=np.arange(1, 101)).min() > 100
+    assert len(oracle.bed_clumping(obed, thr_r2=0.05)) < len(k) < len(oracle.bed_clumping(obed, thr_r2=0.8))
+    # no pair of kept variants inside the window exceeds the threshold (r2 of the scaled dot product)
+    kn = oracle.bed_clumping(obed_na, thr_r2=0.3)
+    st = oracle.bed_colstats(obed_na, obed_na.rows_along(), kn)
+    X = oracle.read_bed_scaled(obed_na, obed_na.rows_along(), kn, st["sumX"] / st["nb_nona_col"], np.sqrt(st["denoX"]))
+    R2 = (X.T @ X) ** 2
+    chrom_n, pos_n = oracle.read_bim(obed_na.bedfile)
+    same = chrom_n[kn - 1][:, None] == chrom_n[kn - 1][None, :]
+    near = np.abs(pos_n[kn - 1][:, None] - pos_n[kn - 1][None, :]) <= (100 / 0.3) * 1000
+    off = ~np.eye(len(kn), dtype=bool)
+    assert np.all(R2[same & near & off] <= 0.3)
