@@ -132,10 +132,11 @@ def run_reference(args, wl):
 
     n = wl["n"]
     threads = ref.max_threads()
-    # calibrate on 2,000 columns, then size a step to ~min(4 s, 150 s / (K + W))
-    rate0, _, _ = cpu_port_rate(n, 2000, SEED, steps=1, warmup=1, threads=threads)
-    per_step = min(4.0, 150.0 / max(1, args.steps + args.warmup))
-    m_s = int(max(2000, min(wl["m"], rate0 * per_step / n)))
+    # calibrate warm on 20,000 columns (the first OpenMP regions of a process are slow), then size a step to
+    # ~min(4 s, 150 s / (K + W)), at most the whole per-GPU matrix
+    rate0, _, _ = cpu_port_rate(n, 20000, SEED, steps=2, warmup=2, threads=threads)
+    per_step = max(0.5, min(4.0, 150.0 / max(1, args.steps + args.warmup)))
+    m_s = int(max(20000, min(wl["m"], rate0 * per_step / n)))
     rate, sec_step, _ = cpu_port_rate(n, m_s, SEED, steps=args.steps, warmup=args.warmup, threads=threads)
     sample = "first %d of %d SNP columns of the synthetic %d-sample matrix (%.2e genotypes per step)" % (
         m_s, wl["m"], n, float(n) * m_s)
@@ -333,9 +334,9 @@ def main():
             from oracle import ref
 
             threads = ref.max_threads()
-            r0, _, _ = cpu_port_rate(n, 2000, SEED, steps=1, warmup=1, threads=threads)
-            m_s = int(max(2000, min(m_loc, r0 * 12.0 / n)))  # ~12 s of CPU work
-            r1, sec, _ = cpu_port_rate(n, m_s, SEED, steps=1, warmup=0, threads=threads)
+            r0, _, _ = cpu_port_rate(n, 20000, SEED, steps=2, warmup=2, threads=threads)
+            m_s = int(max(20000, min(m_loc, r0 * 12.0 / n)))  # ~12 s of CPU work (capped at the whole matrix)
+            r1, sec, _ = cpu_port_rate(n, m_s, SEED, steps=1, warmup=1, threads=threads)
             cpu_baseline = {"value": r1, "unit": "genotypes/s", "cores": threads, "kind": "port",
                             "sample": "bed_pMatVec4 port (oracle/bsg_oracle.c, -O2 -fopenmp) on the first %d of %d "
                                       "columns, %d samples, %.1f s" % (m_s, m_loc, n, sec)}
