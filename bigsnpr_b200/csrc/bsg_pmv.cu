@@ -62,7 +62,6 @@ struct Args {
   const uint8_t *na_flags;  // per physical line (null = assume missing values anywhere)
   int use_na;            // 0: matrix has no missing value, skip the NA plane
   long long *part;       // [nlines_pad][16] zeroed accumulators: 8 raw-plane slices, 8 NA-plane slices
-  int pfd;               // L2 prefetch distance in chunks (0 = off)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -218,44 +217,23 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_pmv(const Args a) {
   uint32_t phase = 0;
 
   if (warp == CW) {
-    // ============ producer warp: one bulk copy of the digit block(s) per chunk, plus L2 prefetch of the
-    // genotype lines PFD chunks ahead of the consumers (the warp is otherwise idle) ============
-    constexpr int LPL = (GROUP + 31) / 32;  // lines prefetched per lane
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-      const int group = item / a.ksplit, ks = item - group * a.ksplit;
-      const int c0 = ks * a.chunks_per_split;
-      const int c1 = min(a.nchunks, c0 + a.chunks_per_split);
-      const uint8_t *lp[LPL];
-      if (a.pfd > 0) {
-#pragma unroll
-        for (int t = 0; t < LPL; t++) {
-          int l = min(group * GROUP + lane + 32 * t, a.nlines - 1);
-          const int phys = a.lines ? a.lines[l] : l;
-          lp[t] = a.P + (int64_t)phys * a.stride;
-        }
-#pragma unroll 1
-        for (int c = c0; c < min(c1, c0 + a.pfd); c++)
-#pragma unroll
-          for (int t = 0; t < LPL; t++)
-            if (lane + 32 * t < GROUP) asm volatile("prefetch.global.L2 [%0];" ::"l"(lp[t] + (int64_t)c * SEG));
-      }
-      for (int c = c0; c < c1; c++) {
-        const uint32_t full = bar_base + 8 * stage, empty = bar_base + 8 * (STAGES + stage);
-        if (a.pfd > 0 && c + a.pfd < c1) {
-#pragma unroll
-          for (int t = 0; t < LPL; t++)
-            if (lane + 32 * t < GROUP) asm volatile("prefetch.global.L2 [%0];" ::"l"(lp[t] + (int64_t)(c + a.pfd) * SEG));
-        }
-        mbar_wait(empty, phase ^ 1);
-        if (lane == 0) {
+    // ============ producer warp: one bulk copy of the digit block(s) per chunk ============
+    if (lane == 0) {
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int group = item / a.ksplit, ks = item - group * a.ksplit;
+        const int c0 = ks * a.chunks_per_split;
+        const int c1 = min(a.nchunks, c0 + a.chunks_per_split);
+        for (int c = c0; c < c1; c++) {
+          const uint32_t full = bar_base + 8 * stage, empty = bar_base + 8 * (STAGES + stage);
+          mbar_wait(empty, phase ^ 1);
           mbar_expect_tx(full, stage_tx);
           const uint32_t dst = smem_base + stage * STAGE_BYTES;
           bulk_g2s(dst, a.dig1 + (int64_t)c * DIG, DIG, full);
           if (two_dig) bulk_g2s(dst + DIG, a.dig2 + (int64_t)c * DIG, DIG, full);
-        }
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     }
@@ -780,14 +758,6 @@ static int run_pmv(bsg_view *v, const uint8_t *P, int64_t stride, int L, const i
   a.dig2 = dig2;
   a.na_flags = na_flags;
   a.use_na = use_na;
-  {
-    static int pfd = -1;
-    if (pfd < 0) {
-      const char *ev = getenv("BSG_PMV_PFD");
-      pfd = ev ? std::max(0, std::min(64, atoi(ev))) : 0;
-    }
-    a.pfd = pfd;
-  }
   BSG_TRY(v->s_part.ensure((size_t)a.nlines_pad * 16 * sizeof(long long)));
   a.part = v->s_part.as<long long>();
   BSG_CUDA(cudaMemsetAsync(a.part, 0, (size_t)a.nlines_pad * 16 * sizeof(long long), s));
