@@ -13,6 +13,8 @@ and error behaviour, so the parity tests read like the reference's testthat file
     bed_ld_scores / snp_ld_scores  R/ld-scores.R:3-72
     bed_tcrossprodSelf       R/bed-tcrossprodSelf.R:21-52
     bed_randomSVD            R/autoSVD.R:205-219
+    prod_and_rowSumsSq / bed_projectSelfPCA   src/bed-fun.cpp:103-133, R/bed-projectPCA.R:31-58,196-227
+    multLinReg / bed_pcadapt / snp_pcadapt    src/multLinReg.cpp:8-95, R/pcadapt.R:3-27,61-81
 
 Everything computes on the GPU through libbsgpu; there is no CPU path here.
 """
@@ -515,6 +517,71 @@ def bed_randomSVD(obj_bed, fun_scaling=bed_scaleBinom, ind_row=..., ind_col=...,
     check(lib().bsg_randomsvd(obj_bed._h, _pi(ind_row), n, _pi(ind_col), m, _pd(center), _pd(scale), int(k), float(tol),
                               int(maxit), _pd(d), _pd(u), _pd(v), _pd(c_out), _pd(s_out), C.byref(niter), C.byref(nops)))
     return {"d": d, "u": u.T, "v": v.T, "niter": niter.value, "nops": nops.value, "center": c_out, "scale": s_out}
+
+
+def prod_and_rowSumsSq(obj_bed, ind_row, ind_col, center, scale, V):
+    """src/bed-fun.cpp:103-133 -> (XV (nr, K), rowSumsSq (nr)); V has one row per selected column (:116)."""
+    ind_row, ind_col = _i32(ind_row), _i32(ind_col)
+    center, scale = _f64(center), _f64(scale)
+    V = np.asarray(V, dtype=np.float64)
+    V = np.asfortranarray(V.reshape(V.shape[0], -1))
+    if center.size != ind_col.size or scale.size != ind_col.size or V.shape[0] != ind_col.size:
+        raise ValueError(ERROR_DIM)
+    K = V.shape[1]
+    XV = np.empty((ind_row.size, K), dtype=np.float64, order="F")
+    rss = np.empty(ind_row.size, dtype=np.float64)
+    check(lib().bsg_prod_and_rowsumssq(obj_bed._h, _pi(ind_row), ind_row.size, _pi(ind_col), ind_col.size, _pd(center),
+                                       _pd(scale), V.ctypes.data_as(_lib.c_dbl_p), K,
+                                       XV.ctypes.data_as(_lib.c_dbl_p), _pd(rss)))
+    return XV, rss
+
+
+def bed_projectSelfPCA(obj_svd, obj_bed, ind_row, ind_col=None, ncores=1):
+    """R/bed-projectPCA.R:196-227: project the samples `ind_row` of the same file on the PCs of `obj_svd`
+    (dict with v, d, center, scale).  Returns obj.svd.ref, simple_proj (= XV) and X_norm (row sums of squares);
+    the OADP correction is bigutilsr::pca_OADP_proj2 applied to (XV, X_norm, d) on the host (un-vendored R code)."""
+    _assert_bed(obj_bed)
+    v = np.asarray(obj_svd["v"], dtype=np.float64)
+    if ind_col is None:
+        ind_col = obj_svd.get("subset", None)
+    if ind_col is None:
+        raise ValueError("'ind.col' can't be `NULL`.")
+    ind_row, ind_col = _i32(ind_row), _i32(ind_col)
+    _assert_lengths(np.arange(v.shape[0]), ind_col)
+    XV, x_norm = prod_and_rowSumsSq(obj_bed, ind_row, ind_col, obj_svd["center"], obj_svd["scale"], v)
+    return {"obj.svd.ref": obj_svd, "simple_proj": XV, "X_norm": x_norm}
+
+
+def multLinReg(obj, ind_row, ind_col, U, ncores=1):
+    """src/multLinReg.cpp:64-95 -> t-scores (nc, K), NaN where the reference gives NA."""
+    ind_row, ind_col = _i32(ind_row), _i32(ind_col)
+    U = np.asarray(U, dtype=np.float64)
+    U = np.asfortranarray(U.reshape(U.shape[0], -1))
+    if U.shape[0] != ind_row.size:
+        raise ValueError(ERROR_DIM)
+    K = U.shape[1]
+    out = np.empty((ind_col.size, K), dtype=np.float64, order="F")
+    check(lib().bsg_multlinreg(obj._h, _pi(ind_row), ind_row.size, _pi(ind_col), ind_col.size,
+                               U.ctypes.data_as(_lib.c_dbl_p), K, out.ctypes.data_as(_lib.c_dbl_p)))
+    return out
+
+
+def bed_pcadapt(obj_bed, U_row, ind_row=..., ind_col=..., ncores=1):
+    """R/pcadapt.R:3-27,73-81 up to the t-scores: the Mahalanobis distance (bigutilsr::dist_ogk) and the genomic
+    control that follow are host-side R code on the (nc x K) matrix returned here.  K == 1 returns the reference's
+    score (t - median(t))^2 directly."""
+    _assert_bed(obj_bed)
+    ind_row, ind_col = _ind(obj_bed, *_dflt(obj_bed, ind_row, ind_col))
+    U = np.asarray(U_row, dtype=np.float64)
+    U = U.reshape(U.shape[0], -1)
+    _assert_lengths(np.arange(U.shape[0]), ind_row)
+    t = multLinReg(obj_bed, ind_row, ind_col, U, ncores)
+    if U.shape[1] == 1:
+        return {"tscores": t, "score": (t[:, 0] - np.median(t[:, 0])) ** 2}
+    return {"tscores": t}
+
+
+snp_pcadapt = bed_pcadapt  # R/pcadapt.R:61-68 (FBM.code256 handles share the packed kernels)
 
 
 def bed_clumping_chr(obj_bed, ind_row, ind_col, center, scale, ordInd, rankInd, pos, size, thr, ncores=1):

@@ -564,6 +564,7 @@ void bsg_close(bsg_bed *h) {
   DevBuf *bufs[] = {&h->w_idx_row, &h->w_idx_col, &h->w_center, &h->w_scale, &h->w_x, &h->w_out, &h->w_tmp0,
                     &h->w_tmp1, &h->w_tmp2, &h->w_tmp3, &h->w_part, &h->w_dig1, &h->w_dig2, &h->w_misc};
   for (DevBuf *b : bufs) b->release();
+  for (DevBuf &b : h->w_proj) b.release();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);

@@ -76,6 +76,7 @@ struct bsg_bed {
   // scratch reused across calls
   bsg::DevBuf w_idx_row, w_idx_col, w_center, w_scale, w_x, w_out, w_tmp0, w_tmp1, w_tmp2, w_tmp3,
       w_part, w_dig1, w_dig2, w_misc;
+  bsg::DevBuf w_proj[8];  // projection / multLinReg work arrays (grow-only, reused across calls)
 };
 
 namespace bsg {
@@ -99,6 +100,11 @@ int counts_rows(bsg_bed *h, const int *d_row, int nr, const int *d_col, int nc, 
 int read_dense(bsg_bed *h, const int *d_row, int nr, const int *d_col, int nc, int na_val, int *d_out, cudaStream_t s);
 int read_dense_scaled(bsg_bed *h, const int *d_row, int nr, const int *d_col, int nc, const double *d_center,
                       const double *d_scale, double *d_out, cudaStream_t s);
+
+// ---- bsg_stats.cu: 4 x nc code counts of (ind_row, ind_col) on the device (h->w_tmp0), on h->stream
+int col_counts_dev(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, int32_t **d_out);
+int simple_rowsumssq(bsg_bed *h, const int *d_row, int nr, const int *d_col, int nc, const double *d_center,
+                     const double *d_scale, double *d_out, cudaStream_t s);
 
 // ---- bsg_cor.cu: dense sub-matrix of a packed matrix, per-line code counts ------------------------
 int compact_lines(const uint8_t *src, int64_t src_stride, const int *code_idx, int ncodes, const int *line_idx,

@@ -618,8 +618,17 @@ int bsg_randomsvd(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, in
 // ---------------------------------------------------------------------------------------------------
 // fp64 path: device decode of column blocks + cuBLAS DSYRK.  Used when no sample-major copy is resident or the
 // scaling is degenerate (zero / negative scale, negative center, non-finite weights).
+__global__ void k_mirror_lower(double *K, int n) {  // K[j, i] (upper) = K[i, j] (lower), column-major
+  const int64_t total = (int64_t)n * n;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t % n), j = (int)(t / n);
+    if (i > j) K[(int64_t)i * n + j] = K[t];
+  }
+}
+
+// K (host) and / or K_dev (caller's device buffer, nr x nr) receive the result
 static int tcrossprod_dsyrk(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, const double *center,
-                            const double *scale, double *K) {
+                            const double *scale, double *K, double *K_dev) {
   cudaStream_t s = h->stream;
   const int *d_row = nullptr, *d_col = nullptr;
   BSG_TRY(upload_index(h, ind_row, nr, h->n, h->w_idx_row, &d_row));
@@ -637,16 +646,16 @@ static int tcrossprod_dsyrk(bsg_bed *h, const int *ind_row, int nr, const int *i
   BSG_CUDA(cudaMemcpyAsync(h->w_scale.p, scale, (size_t)nc * sizeof(double), cudaMemcpyHostToDevice, s));
   // block of columns sized to ~1 GB of decoded doubles
   int blk = (int)std::max<int64_t>(64, std::min<int64_t>(nc > 0 ? nc : 1, ((int64_t)1 << 27) / std::max(nr, 1)));
-  double *dK = nullptr, *dX = nullptr;
-  BSG_CUDA(cudaMalloc((void **)&dK, (size_t)std::max(nr, 1) * std::max(nr, 1) * sizeof(double)));
+  double *dK = K_dev, *dX = nullptr;
+  if (!K_dev) BSG_CUDA(cudaMalloc((void **)&dK, (size_t)std::max(nr, 1) * std::max(nr, 1) * sizeof(double)));
   cudaError_t e = cudaMalloc((void **)&dX, (size_t)std::max(nr, 1) * blk * sizeof(double));
   if (e != cudaSuccess) {
-    cudaFree(dK);
+    if (!K_dev) cudaFree(dK);
     return cuda_fail(e, "GRM block");
   }
   cublasHandle_t cb = nullptr;
   if (cublasCreate(&cb) != CUBLAS_STATUS_SUCCESS) {
-    cudaFree(dK);
+    if (!K_dev) cudaFree(dK);
     cudaFree(dX);
     return fail(BSG_ERR_CUDA, "cublasCreate failed");
   }
@@ -662,19 +671,18 @@ static int tcrossprod_dsyrk(bsg_bed *h, const int *ind_row, int nr, const int *i
         cublasDsyrk(cb, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, nr, b, &one, dX, nr, &one, dK, nr) != CUBLAS_STATUS_SUCCESS)
       rc = fail(BSG_ERR_CUDA, "cublasDsyrk failed");
   }
-  if (!rc) {
-    cudaError_t e2 = cudaMemcpyAsync(K, dK, (size_t)nr * nr * sizeof(double), cudaMemcpyDeviceToHost, s);
+  if (!rc && nr > 0) {
+    k_mirror_lower<<<(int)std::min<int64_t>(((int64_t)nr * nr + 255) / 256, 148 * 32), 256, 0, s>>>(dK, nr);
+    count_launch();
+    cudaError_t e2 = cudaGetLastError();
+    if (e2 == cudaSuccess && K) e2 = cudaMemcpyAsync(K, dK, (size_t)nr * nr * sizeof(double), cudaMemcpyDeviceToHost, s);
     if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(s);
     if (e2 != cudaSuccess) rc = cuda_fail(e2, "GRM download");
   }
   cublasDestroy(cb);
-  cudaFree(dK);
+  if (!K_dev) cudaFree(dK);
   cudaFree(dX);
-  if (rc) return rc;
-  // mirror the lower triangle
-  for (int j = 0; j < nr; j++)
-    for (int i = j + 1; i < nr; i++) K[(size_t)i * nr + j] = K[(size_t)j * nr + i];
-  return BSG_OK;
+  return rc;
 }
 
 
@@ -699,9 +707,11 @@ struct DevPtrs {
 
 extern "C" {
 
-int bsg_tcrossprod(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, const double *center,
-                   const double *scale, double *K) {
-  if (!h || !K) return fail(BSG_ERR_ARG, "null argument");
+}  // extern "C"
+
+static int tcrossprod_impl(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, const double *center,
+                           const double *scale, double *K, double *K_dev) {
+  if (!h || (!K && !K_dev)) return fail(BSG_ERR_ARG, "null argument");
   if (!center || !scale) return fail(BSG_ERR_DIM, "Incompatibility between dimensions.");
   BSG_TRY(bind_device(h));
   if (!ind_row) nr = h->n;
@@ -713,7 +723,7 @@ int bsg_tcrossprod(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, i
     const char *es = getenv("BSG_GRM_SLICES");
     if (es) nslices = std::min(9, std::max(2, atoi(es)));
   }
-  if (force_dsyrk || !h->B || nr == 0 || nc == 0) return tcrossprod_dsyrk(h, ind_row, nr, ind_col, nc, center, scale, K);
+  if (force_dsyrk || !h->B || nr == 0 || nc == 0) return tcrossprod_dsyrk(h, ind_row, nr, ind_col, nc, center, scale, K, K_dev);
   using namespace wgram;
   cudaStream_t s = h->stream;
   DevPtrs mem;
@@ -736,7 +746,7 @@ int bsg_tcrossprod(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, i
   BSG_CUDA(cudaMemcpyAsync(stats, d_stats, sizeof stats, cudaMemcpyDeviceToHost, s));
   BSG_CUDA(cudaMemcpyAsync(hW3.data(), W3, (size_t)nc * sizeof(double), cudaMemcpyDeviceToHost, s));
   BSG_CUDA(cudaStreamSynchronize(s));
-  if (stats[4] != 0.0) return tcrossprod_dsyrk(h, ind_row, nr, ind_col, nc, center, scale, K);
+  if (stats[4] != 0.0) return tcrossprod_dsyrk(h, ind_row, nr, ind_col, nc, center, scale, K, K_dev);
   double sumW3 = 0;
   for (int j = 0; j < nc; j++) sumW3 += hW3[j];
 
@@ -799,8 +809,8 @@ int bsg_tcrossprod(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, i
   const int njb = (nr + TNv - 1) / TNv;
   std::vector<uint8_t> na_jb(njb, 0);
   for (int i = 0; i < nr; i++) na_jb[i / TNv] |= na[i];
-  double *dK = nullptr;
-  BSG_TRY(mem.alloc(&dK, (size_t)nr * nr));
+  double *dK = K_dev;
+  if (!K_dev) BSG_TRY(mem.alloc(&dK, (size_t)nr * nr));
   BSG_CUDA(cudaMemsetAsync(dK, 0, (size_t)nr * nr * sizeof(double), s));
   if (use_t5) {
     // 128 x 128 tiles on tcgen05 / TMEM (bsg_gram5.cu); digits are laid out 16 bytes per packed word, in order
@@ -868,13 +878,28 @@ int bsg_tcrossprod(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, i
   if (!rc) {
     k_grm_finish<<<(int)std::min<int64_t>(((int64_t)nr * nr + 255) / 256, 148 * 32), 256, 0, s>>>(dK, nr, nr, d_r, d_q, sumW3);
     count_launch();
-    cudaError_t e2 = cudaMemcpyAsync(K, dK, (size_t)nr * nr * sizeof(double), cudaMemcpyDeviceToHost, s);
+    cudaError_t e2 = cudaGetLastError();
+    if (e2 == cudaSuccess && K) e2 = cudaMemcpyAsync(K, dK, (size_t)nr * nr * sizeof(double), cudaMemcpyDeviceToHost, s);
     if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(s);
     if (e2 != cudaSuccess) rc = cuda_fail(e2, "GRM download");
   }
   cudaStreamSynchronize(s);
   bsg_view_destroy(v0);
   return rc;
+}
+
+extern "C" {
+
+int bsg_tcrossprod(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, const double *center,
+                   const double *scale, double *K) {
+  if (!K) return fail(BSG_ERR_ARG, "null argument");
+  return tcrossprod_impl(h, ind_row, nr, ind_col, nc, center, scale, K, nullptr);
+}
+
+int bsg_tcrossprod_dev(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, const double *center,
+                       const double *scale, double *K_dev) {
+  if (!K_dev) return fail(BSG_ERR_ARG, "null argument");
+  return tcrossprod_impl(h, ind_row, nr, ind_col, nc, center, scale, nullptr, K_dev);
 }
 
 }  // extern "C"

@@ -125,6 +125,13 @@ __device__ __forceinline__ void slot_load(Slot &s, const uint8_t *pa, const uint
   s.bhi = ldg_stream(pb + off + 64);
 }
 
+// Second plane of the packed codes, one bit per code at the low bit of its 2-bit field: MODE 1 / 2 = missing
+// value flag (code 3: both bits set), MODE 3 = the high bit alone (codes 2 and 3; sums of squares need it).
+template <int MODE>
+__device__ __forceinline__ uint32_t plane2(uint32_t x) {
+  return MODE == 3 ? (x >> 1) : (x & (x >> 1));
+}
+
 // One chunk of the warp's 32 lines (two 16-line sub-tiles t0 / t1).  Word w of the lane (w < 4: lo bytes,
 // w >= 4: hi bytes) holds 16 codes of each of its 4 lines; d = digits of slice g for those 16 codes (one
 // LDS.128 per word, shared by both sub-tiles), register c <-> codes 4r+c (r = byte of the register).
@@ -153,10 +160,10 @@ __device__ __forceinline__ void chunk_mma(const Slot &t0, const Slot &t1, uint32
     mma_u8s8(acc16[1], a1 & 0x30303030u, b1 & 0x30303030u, a1t & 0x30303030u, b1t & 0x30303030u, d.z, d.w);
     if (MODE != 0) {
       uint4 dn = d;
-      if (MODE == 2) dn = lds128(dig_addr + DIG + w * 512);
+      if (MODE >= 2) dn = lds128(dig_addr + DIG + w * 512);
       // bit 2p of x & (x >> 1) is set iff code p == 3
-      const uint32_t a0n = a0 & (a0 >> 1), b0n = b0 & (b0 >> 1), a0nt = a0t & (a0t >> 1), b0nt = b0t & (b0t >> 1);
-      const uint32_t a1n = a1 & (a1 >> 1), b1n = b1 & (b1 >> 1), a1nt = a1t & (a1t >> 1), b1nt = b1t & (b1t >> 1);
+      const uint32_t a0n = plane2<MODE>(a0), b0n = plane2<MODE>(b0), a0nt = plane2<MODE>(a0t), b0nt = plane2<MODE>(b0t);
+      const uint32_t a1n = plane2<MODE>(a1), b1n = plane2<MODE>(b1), a1nt = plane2<MODE>(a1t), b1nt = plane2<MODE>(b1t);
       mma_u8s8(accn1[0], a0n & 0x01010101u, b0n & 0x01010101u, a0nt & 0x01010101u, b0nt & 0x01010101u, dn.x, dn.y);
       mma_u8s8(accn1[1], a1n & 0x01010101u, b1n & 0x01010101u, a1nt & 0x01010101u, b1nt & 0x01010101u, dn.x, dn.y);
       mma_u8s8(accn16[0], a0n & 0x10101010u, b0n & 0x10101010u, a0nt & 0x10101010u, b0nt & 0x10101010u, dn.z, dn.w);
@@ -180,9 +187,9 @@ __device__ __forceinline__ void tile_mma(const Slot &sl, const uint4 (&b1)[8], u
     mma_u8s8(acc16, a & 0x30303030u, bq & 0x30303030u, at & 0x30303030u, bt & 0x30303030u, b1[w].z, b1[w].w);
     if (MODE != 0) {
       uint4 d = b1[w];
-      if (MODE == 2) d = lds128(dig2_addr + w * 512);
-      const uint32_t an = a & (a >> 1), bn = bq & (bq >> 1);
-      const uint32_t ant = at & (at >> 1), bnt = bt & (bt >> 1);
+      if (MODE >= 2) d = lds128(dig2_addr + w * 512);
+      const uint32_t an = plane2<MODE>(a), bn = plane2<MODE>(bq);
+      const uint32_t ant = plane2<MODE>(at), bnt = plane2<MODE>(bt);
       mma_u8s8(accn1, an & 0x01010101u, bn & 0x01010101u, ant & 0x01010101u, bnt & 0x01010101u, d.x, d.y);
       mma_u8s8(accn16, an & 0x10101010u, bn & 0x10101010u, ant & 0x10101010u, bnt & 0x10101010u, d.z, d.w);
     }
@@ -210,7 +217,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_pmv(const Args a) {
 
   const int ngroups = a.nlines_pad / GROUP;
   const int nitems = ngroups * a.ksplit;
-  constexpr bool two_dig = MODE == 2;
+  constexpr bool two_dig = MODE >= 2;
   const uint32_t stage_tx = DIG + (two_dig ? DIG : 0);
 
   int stage = 0;
@@ -256,7 +263,9 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_pmv(const Args a) {
       }
       // does any of this warp's 32 lines hold a missing value?  (warp-uniform)
       bool tile_na = false;
-      if (MODE != 0) {
+      if (MODE == 3) {
+        tile_na = true;  // the high-bit plane is populated everywhere
+      } else if (MODE != 0) {
         if (a.na_flags) {
           int l = min(group * GROUP + warp * 32 + lane, a.nlines - 1);
           const int phys = a.lines ? a.lines[l] : l;
@@ -363,11 +372,15 @@ struct Scal {          // device-resident scalars of one call
 
 // mode 0: v0 = x                      (Xt.y, identity scaling handled in finish)
 // mode 1: v0 = x / s, v1 = (c - 3) * x / s   (X.y with scaling)
+// mode 2: v0 = x, v1 = second vector passed in the `center` slot   (two independent planes, bsg_pmv planes API)
 __device__ __forceinline__ void make_vals(int mode, const double *x, const double *center, const double *scale, int k,
                                           double &v0, double &v1) {
   if (mode == 0) {
     v0 = x[k];
     v1 = 0;
+  } else if (mode == 2) {
+    v0 = x[k];
+    v1 = center[k];
   } else {
     double z = x[k] / scale[k];
     v0 = z;
@@ -691,6 +704,24 @@ __global__ void k_finish_prod(const long long *__restrict__ part, int ksplit, in
   }
 }
 
+// planes API:  full_l = cR * R_l + cP * P_l + add0,  R = raw-plane sum against vector 1 (exponent e[0]),
+// P = second-plane sum against vector 2 (e[1]);  optional second output fullB_l = cRb * R_l + cPb * P_l.
+__global__ void k_finish_planes(const long long *__restrict__ part, int nlines, const Scal *sc, int have_p, int p_same,
+                                double cR, double cP, double add0, double *__restrict__ full, double cRb, double cPb,
+                                double *__restrict__ fullB) {
+  int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= nlines) return;
+  if (sc->nonfinite) {
+    full[l] = nan("");
+    if (fullB) fullB[l] = nan("");
+    return;
+  }
+  const double R = combine8(part, l, 1, 0, sc->e[0]);
+  const double P = have_p ? combine8(part, l, 0, 1, sc->e[p_same ? 0 : 1]) : 0.0;
+  full[l] = (cR * R + cP * P) + add0;
+  if (fullB) fullB[l] = cRb * R + cPb * P;
+}
+
 __global__ void k_gather(const double *__restrict__ full, const int *__restrict__ idx, int len, double *__restrict__ out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < len) out[i] = full[idx[i]];
@@ -710,6 +741,8 @@ static int launch_cap(int64_t work, int block, int cap) {
   return (int)g;
 }
 
+static int launch_cap_pub_impl(int64_t work) { return launch_cap(work, 256, 148 * 16); }
+
 static int hb_bits(int maxmult) {
   int b = 0;
   while ((1 << b) < maxmult) b++;
@@ -719,7 +752,7 @@ static int hb_bits(int maxmult) {
 // shared launcher of the tensor-pipe kernel + scratch sizing
 static int run_pmv(bsg_view *v, const uint8_t *P, int64_t stride, int L, const int *lines, int nlines,
                    const uint8_t *dig1, const uint8_t *dig2, const uint8_t *na_flags, int use_na, Args *out_args,
-                   cudaStream_t s) {
+                   cudaStream_t s, bool plane_hi = false) {
   // variant: BSG_PMV_VARIANT = "<consumer warps>x<ring chunks>" (tuning knob; default chosen from measurements)
   static int var_cw = 0, var_r = 0, var_s = 0;
   if (!var_cw) {
@@ -761,11 +794,13 @@ static int run_pmv(bsg_view *v, const uint8_t *P, int64_t stride, int L, const i
   BSG_TRY(v->s_part.ensure((size_t)a.nlines_pad * 16 * sizeof(long long)));
   a.part = v->s_part.as<long long>();
   BSG_CUDA(cudaMemsetAsync(a.part, 0, (size_t)a.nlines_pad * 16 * sizeof(long long), s));
-  const int mode = !use_na ? 0 : (dig2 ? 2 : 1);
+  const int mode = plane_hi ? 3 : (!use_na ? 0 : (dig2 ? 2 : 1));
+  if (plane_hi && !dig2) return fail(BSG_ERR_ARG, "high-bit plane needs its own digits");
   void (*kern)(const Args) = nullptr;
 #define PMV_PICK(CWv, Rv, Sv)                                                                   \
   if (var_cw == CWv && var_r == Rv && var_s == Sv)                                              \
-    kern = mode == 0 ? k_pmv<0, CWv, Rv, Sv> : (mode == 1 ? k_pmv<1, CWv, Rv, Sv> : k_pmv<2, CWv, Rv, Sv>);
+    kern = mode == 0 ? k_pmv<0, CWv, Rv, Sv>                                                    \
+                     : (mode == 1 ? k_pmv<1, CWv, Rv, Sv> : (mode == 2 ? k_pmv<2, CWv, Rv, Sv> : k_pmv<3, CWv, Rv, Sv>));
   PMV_PICK(11, 2, 0)
   PMV_PICK(11, 2, 1)
   PMV_PICK(11, 2, 2)
@@ -792,6 +827,8 @@ static int run_pmv(bsg_view *v, const uint8_t *P, int64_t stride, int L, const i
 }
 
 }  // namespace pmv
+
+static int launch_cap_pub(int64_t work) { return pmv::launch_cap_pub_impl(work); }
 
 // =============================================================================================
 // views
@@ -1102,6 +1139,312 @@ int bsg_cprodvec(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int
   bsg_view *v = nullptr;
   BSG_TRY(cached_view(h, ind_row, nr, ind_col, nc, center, scale, &v));
   return bsg_view_cprodvec(v, x, out);
+}
+
+}  // extern "C"
+
+// =============================================================================================
+// planes API: the two integer plane sums of the tensor-pipe kernel against caller-chosen vectors.
+//   dir 0: lines = samples (copy B), vectors run over the selected SNP columns   (X-side sums)
+//   dir 1: lines = SNP columns (copy A), vectors run over the selected samples   (Xt-side sums)
+//   R_l = sum_t code(l, t) x1[t]   (code 3 for a missing value)
+//   P_l = sum_t plane(l, t) x2[t]  plane = missing-value flag (PLANE_NA) or high bit of the code (PLANE_HI)
+// out = cR R + cP P + add0, outB = cRb R + cPb P (optional), both in the caller's index order.
+// =============================================================================================
+namespace bsg {
+enum { PLANE_NONE = 0, PLANE_NA = 1, PLANE_HI = 2 };
+struct PlaneOut {
+  double cR, cP, add0;
+  double *out;
+  double cRb, cPb;
+  double *outB;
+};
+
+static int view_planes_dev(bsg_view *v, int dir, const double *x1, const double *x2, int plane, const PlaneOut &o,
+                           cudaStream_t s) {
+  using namespace pmv;
+  bsg_bed *h = v->h;
+  if (dir == 0 && !h->B) return fail(BSG_ERR_ARG, "planes over samples need the sample-major copy");
+  if (plane == PLANE_NA && !h->has_na) plane = PLANE_NONE;
+  const bool same = plane == PLANE_NA && x2 == x1;          // one digit block serves both planes
+  const bool two = plane != PLANE_NONE && !same;
+  Scal *sc = v->s_scal.as<Scal>();
+  const int L = dir == 0 ? h->m : h->n;                      // contraction length in the staged copy
+  const int len = dir == 0 ? v->nc : v->nr;                  // vector length (selection order)
+  const int *idx = dir == 0 ? v->d_col : v->d_row;
+  const bool ident = dir == 0 ? v->col_identity : v->row_identity;
+  const int hb = hb_bits(dir == 0 ? v->col_maxmult : v->row_maxmult);
+  const int64_t stride = dir == 0 ? h->strideB : h->strideA;
+  const int nchunks = (int)(stride / SEG);
+  const int mode = two ? 2 : 0;
+  BSG_TRY(v->s_dig1.ensure((size_t)nchunks * DIG));
+  if (two) BSG_TRY(v->s_dig2.ensure((size_t)nchunks * DIG));
+  uint8_t *dig1 = v->s_dig1.as<uint8_t>(), *dig2 = two ? v->s_dig2.as<uint8_t>() : nullptr;
+  if (ident) {
+    BSG_CUDA(cudaMemsetAsync(sc, 0, sizeof(Scal), s));
+    k_prep1<<<SUMCZ_BLOCKS, 256, 0, s>>>(mode, x1, x2, nullptr, len, hb, sc);
+    k_prep2<<<launch_cap((int64_t)nchunks * 32, 128, 1184), 128, 0, s>>>(mode, x1, x2, nullptr, L, nchunks, sc, dig1, dig2, 0);
+    count_launch(2);
+  } else {
+    BSG_TRY(v->s_q0.ensure((size_t)L * sizeof(long long)));
+    long long *Q0 = v->s_q0.as<long long>(), *Q1 = nullptr;
+    if (two) {
+      BSG_TRY(v->s_q1.ensure((size_t)L * sizeof(long long)));
+      Q1 = v->s_q1.as<long long>();
+    }
+    k_scal_reset<<<1, 1, 0, s>>>(sc);
+    k_maxabs<<<launch_cap(len, 256, 592), 256, 0, s>>>(mode, x1, x2, nullptr, len, sc);
+    k_pick_exp<<<1, 1, 0, s>>>(sc, hb);
+    BSG_CUDA(cudaMemsetAsync(Q0, 0, (size_t)L * sizeof(long long), s));
+    if (Q1) BSG_CUDA(cudaMemsetAsync(Q1, 0, (size_t)L * sizeof(long long), s));
+    k_quantise<<<launch_cap(len, 256, 592), 256, 0, s>>>(mode, x1, x2, nullptr, len, idx, sc, Q0, Q1);
+    k_digits<<<launch_cap((int64_t)nchunks * 256, 256, 1184), 256, 0, s>>>(Q0, L, nchunks, dig1);
+    if (Q1) k_digits<<<launch_cap((int64_t)nchunks * 256, 256, 1184), 256, 0, s>>>(Q1, L, nchunks, dig2);
+    count_launch(5 + (Q1 ? 1 : 0));
+  }
+  Args a;
+  int nlines;
+  if (dir == 0) {
+    nlines = v->row_identity ? h->n : v->nru;
+    BSG_TRY(run_pmv(v, h->B, stride, L, v->d_rows_unique, nlines, dig1, dig2, h->naB, plane != PLANE_NONE, &a, s,
+                    plane == PLANE_HI));
+  } else {
+    nlines = v->nc;
+    BSG_TRY(run_pmv(v, h->A, stride, L, v->d_col, nlines, dig1, dig2, h->naA, plane != PLANE_NONE, &a, s,
+                    plane == PLANE_HI));
+  }
+  const bool gather = dir == 0 && !v->row_identity;
+  double *full = o.out, *fullB = o.outB;
+  if (gather) {
+    BSG_TRY(v->s_full.ensure((size_t)nlines * 2 * sizeof(double)));
+    full = v->s_full.as<double>();
+    fullB = o.outB ? full + nlines : nullptr;
+  }
+  k_finish_planes<<<(nlines + 255) / 256, 256, 0, s>>>(a.part, nlines, sc, plane != PLANE_NONE, same ? 1 : 0, o.cR, o.cP,
+                                                       o.add0, full, o.cRb, o.cPb, fullB);
+  count_launch();
+  if (gather) {
+    k_gather<<<(v->nr + 255) / 256, 256, 0, s>>>(full, v->d_row_gather, v->nr, o.out);
+    if (o.outB) k_gather<<<(v->nr + 255) / 256, 256, 0, s>>>(fullB, v->d_row_gather, v->nr, o.outB);
+    count_launch(o.outB ? 2 : 1);
+  }
+  BSG_CUDA(cudaGetLastError());
+  return BSG_OK;
+}
+
+// per selected column: a = (1 - 2c)/s^2, w = 1/s^2, nv = (5 - 6c + c^2)/s^2 and block partials of T = sum c^2/s^2
+__global__ void k_rss_weights(const double *__restrict__ center, const double *__restrict__ scale, int nc,
+                              double *__restrict__ a, double *__restrict__ w, double *__restrict__ nv,
+                              double *__restrict__ tpart) {
+  __shared__ double sh[32];
+  double t = 0;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nc; j += gridDim.x * blockDim.x) {
+    const double c = center ? center[j] : 0.0, sc = scale ? scale[j] : 1.0;
+    const double w0 = 1.0 / (sc * sc);
+    w[j] = w0;
+    a[j] = (1.0 - 2.0 * c) * w0;
+    nv[j] = (5.0 - 6.0 * c + c * c) * w0;
+    t += c * c * w0;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tt = 0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); k++) tt += sh[k];
+    tpart[blockIdx.x] = tt;
+  }
+}
+
+__global__ void k_rss_final(int nr, const double *__restrict__ t1, const double *__restrict__ t2,
+                            const double *__restrict__ tpart, int nparts, double *__restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nr) return;
+  double T = 0;
+  for (int k = 0; k < nparts; k++) T += tpart[k];
+  out[i] = (t1[i] + (t2 ? t2[i] : 0.0)) + T;
+}
+
+__global__ void k_or_flag(const pmv::Scal *sc, int *flag) {
+  if (sc->nonfinite) *flag = 1;
+}
+
+__global__ void k_square(const double *__restrict__ x, int64_t len, double *__restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = x[i] * x[i];
+}
+
+// t-scores of multLinReg (src/multLinReg.cpp:44-51) from exact column counts and the plane sums:
+//   xySum = R - 3N,  ySum = Y - N(u),  yySum = YY - N(u^2);  tscores[j + nc k]
+__global__ void k_tscores(int nc, int K, const int32_t *__restrict__ cnt4, const double *__restrict__ G,
+                          const double *__restrict__ Nu, const double *__restrict__ Nuu, const double *__restrict__ Y,
+                          const double *__restrict__ YY, double *__restrict__ out) {
+  const int64_t total = (int64_t)nc * K;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(t % nc), k = (int)(t / nc);
+    const int c1 = cnt4[4 * j + 1], c2 = cnt4[4 * j + 2];
+    const int nona = cnt4[4 * j] + c1 + c2;
+    const double xSum = (double)c1 + 2.0 * c2, xxSum = (double)c1 + 4.0 * c2;
+    const double xySum = G[t];
+    const double ySum = Y[k] - (Nu ? Nu[t] : 0.0), yySum = YY[k] - (Nuu ? Nuu[t] : 0.0);
+    const double deno_x = xxSum - xSum * xSum / nona;
+    const double num = xySum - xSum * ySum / nona;
+    const double deno_y = yySum - ySum * ySum / nona;
+    const double deno = deno_x * deno_y - num * num;
+    out[t] = (deno == 0 || nona < 2) ? nan("") : num * sqrt((nona - 2) / deno);
+  }
+}
+
+// work arrays of the two entry points below live on the handle (grow-only): no cudaMalloc / cudaFree per call
+struct ProjScratch {
+  bsg_bed *h;
+  int next = 0;
+  template <class T>
+  int alloc(T **out, size_t count) {
+    if (next >= 8) return fail(BSG_ERR_ARG, "projection scratch exhausted");
+    DevBuf &b = h->w_proj[next++];
+    BSG_TRY(b.ensure((count ? count : 1) * sizeof(T)));
+    *out = b.as<T>();
+    return BSG_OK;
+  }
+};
+}  // namespace bsg
+
+extern "C" {
+
+// prod_and_rowSumsSq (src/bed-fun.cpp:103-133): XV = X~ V (nr x K) and rowSumsSq_i = sum_j X~_ij^2.
+// XV is K applications of the X.y engine; the sums of squares come from two more passes over the same bytes:
+//   sum_j [x present] ((x - c)/s)^2 = R(a) + 2 H(w) - N(nv) + T
+// with x^2 = code + 2 hi - 5 na for the staged codes, a = (1 - 2c)/s^2, w = 1/s^2, nv = (5 - 6c + c^2)/s^2,
+// T = sum_j c^2/s^2, and R / H / N the raw, high-bit and missing-value plane sums.
+int bsg_prod_and_rowsumssq(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, const double *center,
+                           const double *scale, const double *V, int K, double *XV, double *rowSumsSq) {
+  if (!h || !XV || !rowSumsSq || (!V && K > 0)) return fail(BSG_ERR_ARG, "null argument");
+  if (!center || !scale) return fail(BSG_ERR_DIM, "Incompatibility between dimensions.");
+  if (K < 0) return fail(BSG_ERR_ARG, "negative length");
+  bsg_view *v = nullptr;
+  BSG_TRY(cached_view(h, ind_row, nr, ind_col, nc, center, scale, &v));
+  nr = v->nr;
+  nc = v->nc;
+  cudaStream_t s = h->stream;
+  ProjScratch mem{h};
+  const int NP = 64;
+  double *dV = nullptr, *dXV = nullptr, *d_rows = nullptr, *d_cols = nullptr;
+  BSG_TRY(mem.alloc(&dV, (size_t)nc * K));
+  BSG_TRY(mem.alloc(&dXV, (size_t)nr * K));
+  BSG_TRY(mem.alloc(&d_rows, 3 * (size_t)nr));            // rowSumsSq | pass 1 | pass 2
+  BSG_TRY(mem.alloc(&d_cols, 3 * (size_t)nc + NP + 2));   // a | w | nv | partials of T | flag
+  double *d_rs = d_rows;
+  if (nr == 0) return BSG_OK;
+  BSG_CUDA(cudaMemcpyAsync(dV, V, (size_t)nc * K * sizeof(double), cudaMemcpyHostToDevice, s));
+  if (nc == 0) {
+    BSG_CUDA(cudaStreamSynchronize(s));
+    memset(XV, 0, (size_t)nr * K * sizeof(double));
+    memset(rowSumsSq, 0, (size_t)nr * sizeof(double));
+    return BSG_OK;
+  }
+  int *d_bad = reinterpret_cast<int *>(d_cols + 3 * (size_t)nc + NP);  // any pass saw a non-finite quantity
+  BSG_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), s));
+  for (int k = 0; k < K; k++) {
+    BSG_TRY(bsg_view_prodvec_dev(v, dV + (size_t)k * nc, dXV + (size_t)k * nr, s));
+    if (h->B) {
+      k_or_flag<<<1, 1, 0, s>>>(v->s_scal.as<pmv::Scal>(), d_bad);
+      count_launch();
+    }
+  }
+  bool need_simple = !h->B;
+  if (h->B) {
+    double *d_a = d_cols, *d_w = d_cols + nc, *d_n = d_cols + 2 * (size_t)nc, *d_tp = d_cols + 3 * (size_t)nc;
+    double *d_t1 = d_rows + nr, *d_t2 = nullptr;
+    k_rss_weights<<<NP, 256, 0, s>>>(v->d_center, v->d_scale, nc, d_a, d_w, d_n, d_tp);
+    count_launch();
+    PlaneOut o1{1.0, 2.0, 0.0, d_t1, 0, 0, nullptr};
+    BSG_TRY(view_planes_dev(v, 0, d_a, d_w, PLANE_HI, o1, s));
+    if (h->has_na) {
+      d_t2 = d_rows + 2 * (size_t)nr;
+      PlaneOut o2{0.0, -1.0, 0.0, d_t2, 0, 0, nullptr};
+      BSG_TRY(view_planes_dev(v, 0, d_n, d_n, PLANE_NA, o2, s));
+    }
+    k_rss_final<<<(nr + 255) / 256, 256, 0, s>>>(nr, d_t1, d_t2, d_tp, NP, d_rs);
+    count_launch();
+    k_or_flag<<<1, 1, 0, s>>>(v->s_scal.as<pmv::Scal>(), d_bad);
+    count_launch();
+    int bad = 0;  // zero / non-finite scale: the table arithmetic of the accessor kernels gives the reference's Inf / NaN
+    BSG_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, s));
+    BSG_CUDA(cudaStreamSynchronize(s));
+    if (bad) {
+      need_simple = true;
+      for (int k = 0; k < K; k++)
+        BSG_TRY(simple_prodvec(h, v->d_row, nr, v->d_col, nc, v->d_center, v->d_scale, dV + (size_t)k * nc,
+                               dXV + (size_t)k * nr, s));
+    }
+  }
+  if (need_simple) BSG_TRY(simple_rowsumssq(h, v->d_row, nr, v->d_col, nc, v->d_center, v->d_scale, d_rs, s));
+  BSG_CUDA(cudaMemcpyAsync(XV, dXV, (size_t)nr * K * sizeof(double), cudaMemcpyDeviceToHost, s));
+  BSG_CUDA(cudaMemcpyAsync(rowSumsSq, d_rs, (size_t)nr * sizeof(double), cudaMemcpyDeviceToHost, s));
+  BSG_CUDA(cudaStreamSynchronize(s));
+  return BSG_OK;
+}
+
+// multLinReg (src/multLinReg.cpp:8-95): t-scores of genotype ~ U[, k] per SNP over the samples where the
+// genotype is present.  U is nr x K column-major, tscores nc x K column-major, NA_REAL is written as NaN.
+int bsg_multlinreg(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, const double *U, int K,
+                   double *tscores) {
+  if (!h || !tscores || (!U && K > 0)) return fail(BSG_ERR_ARG, "null argument");
+  if (K < 0) return fail(BSG_ERR_ARG, "negative length");
+  bsg_view *v = nullptr;
+  BSG_TRY(cached_view(h, ind_row, nr, ind_col, nc, nullptr, nullptr, &v));
+  nr = v->nr;
+  nc = v->nc;
+  if (nc == 0 || K == 0) return BSG_OK;
+  cudaStream_t s = h->stream;
+  ProjScratch mem{h};
+  double *dU, *dUU = nullptr, *dG, *dNu = nullptr, *dNuu = nullptr, *dY, *dOut;
+  BSG_TRY(mem.alloc(&dU, (size_t)nr * K));
+  BSG_TRY(mem.alloc(&dG, (size_t)nc * K));
+  BSG_TRY(mem.alloc(&dOut, (size_t)nc * K));
+  BSG_TRY(mem.alloc(&dY, 2 * (size_t)K));
+  std::vector<double> ysum(2 * (size_t)K, 0.0);
+  for (int k = 0; k < K; k++) {
+    double y = 0, yy = 0;
+    for (int i = 0; i < nr; i++) {
+      const double u = U[(size_t)k * nr + i];
+      y += u;
+      yy += u * u;
+    }
+    ysum[k] = y;
+    ysum[K + k] = yy;
+  }
+  BSG_CUDA(cudaMemcpyAsync(dU, U, (size_t)nr * K * sizeof(double), cudaMemcpyHostToDevice, s));
+  BSG_CUDA(cudaMemcpyAsync(dY, ysum.data(), 2 * (size_t)K * sizeof(double), cudaMemcpyHostToDevice, s));
+  const bool na = h->has_na != 0;
+  if (na) {
+    BSG_TRY(mem.alloc(&dUU, (size_t)nr * K));
+    BSG_TRY(mem.alloc(&dNu, (size_t)nc * K));
+    BSG_TRY(mem.alloc(&dNuu, (size_t)nc * K));
+    k_square<<<launch_cap_pub((int64_t)nr * K), 256, 0, s>>>(dU, (int64_t)nr * K, dUU);
+    count_launch();
+  }
+  for (int k = 0; k < K; k++) {
+    const double *u = dU + (size_t)k * nr;
+    PlaneOut o1{1.0, na ? -3.0 : 0.0, 0.0, dG + (size_t)k * nc, 0.0, 1.0, na ? dNu + (size_t)k * nc : nullptr};
+    BSG_TRY(view_planes_dev(v, 1, u, u, na ? PLANE_NA : PLANE_NONE, o1, s));
+    if (na) {
+      const double *uu = dUU + (size_t)k * nr;
+      PlaneOut o2{0.0, 1.0, 0.0, dNuu + (size_t)k * nc, 0, 0, nullptr};
+      BSG_TRY(view_planes_dev(v, 1, uu, uu, PLANE_NA, o2, s));
+    }
+  }
+  BSG_CUDA(cudaStreamSynchronize(s));  // the counts helper stages its index upload from host memory
+  int32_t *d_cnt = nullptr;
+  BSG_TRY(col_counts_dev(h, ind_row, nr, ind_col, nc, &d_cnt));
+  k_tscores<<<launch_cap_pub((int64_t)nc * K), 256, 0, s>>>(nc, K, d_cnt, dG, dNu, dNuu, dY, dY + K, dOut);
+  count_launch();
+  BSG_CUDA(cudaGetLastError());
+  BSG_CUDA(cudaMemcpyAsync(tscores, dOut, (size_t)nc * K * sizeof(double), cudaMemcpyDeviceToHost, s));
+  BSG_CUDA(cudaStreamSynchronize(s));
+  return BSG_OK;
 }
 
 double bsg_last_kernel_ms(void) {

@@ -45,7 +45,7 @@ __global__ void k_cprodvec_simple(const uint8_t *__restrict__ A, int64_t strideA
 __global__ void k_prodvec_simple(const uint8_t *__restrict__ A, int64_t strideA, const int *__restrict__ rows,
                                  int nr, const int *__restrict__ cols, int nc, const double *__restrict__ center,
                                  const double *__restrict__ scale, const double *__restrict__ x,
-                                 double *__restrict__ part, int cols_per_split) {
+                                 double *__restrict__ part, int cols_per_split, int square) {
   __shared__ double tab[128][4];
   __shared__ int scol[128];
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -58,11 +58,20 @@ __global__ void k_prodvec_simple(const uint8_t *__restrict__ A, int64_t strideA,
     __syncthreads();
     if (threadIdx.x < nb) {
       int j = jb + threadIdx.x;
-      double c = center ? center[j] : 0.0, s = scale ? scale[j] : 1.0, xv = x[j];
-      tab[threadIdx.x][0] = xv * ((0.0 - c) / s);
-      tab[threadIdx.x][1] = xv * ((1.0 - c) / s);
-      tab[threadIdx.x][2] = xv * ((2.0 - c) / s);
-      tab[threadIdx.x][3] = xv * 0.0;
+      double c = center ? center[j] : 0.0, s = scale ? scale[j] : 1.0;
+      const double t0 = (0.0 - c) / s, t1 = (1.0 - c) / s, t2 = (2.0 - c) / s;
+      if (square) {  // row sums of squares (src/bed-fun.cpp:126)
+        tab[threadIdx.x][0] = t0 * t0;
+        tab[threadIdx.x][1] = t1 * t1;
+        tab[threadIdx.x][2] = t2 * t2;
+        tab[threadIdx.x][3] = 0.0;
+      } else {
+        const double xv = x[j];
+        tab[threadIdx.x][0] = xv * t0;
+        tab[threadIdx.x][1] = xv * t1;
+        tab[threadIdx.x][2] = xv * t2;
+        tab[threadIdx.x][3] = xv * 0.0;
+      }
       scol[threadIdx.x] = cols ? cols[j] : j;
     }
     __syncthreads();
@@ -173,8 +182,8 @@ int simple_cprodvec(bsg_bed *h, const int *d_row, int nr, const int *d_col, int 
   return BSG_OK;
 }
 
-int simple_prodvec(bsg_bed *h, const int *d_row, int nr, const int *d_col, int nc, const double *d_center,
-                   const double *d_scale, const double *d_x, double *d_out, cudaStream_t s) {
+static int simple_prodvec_any(bsg_bed *h, const int *d_row, int nr, const int *d_col, int nc, const double *d_center,
+                              const double *d_scale, const double *d_x, double *d_out, cudaStream_t s, int square) {
   int gx = (nr + 255) / 256;
   int nsplit = (148 * 8 + gx - 1) / gx;
   int max_split = (nc + 127) / 128;
@@ -188,11 +197,22 @@ int simple_prodvec(bsg_bed *h, const int *d_row, int nr, const int *d_col, int n
   if (nr == 0) return BSG_OK;
   dim3 grid(gx, nsplit);
   k_prodvec_simple<<<grid, 256, 0, s>>>(h->A, h->strideA, d_row, nr, d_col, nc, d_center, d_scale, d_x,
-                                        h->w_part.as<double>(), cps);
+                                        h->w_part.as<double>(), cps, square);
   k_sum_splits<<<gx, 256, 0, s>>>(h->w_part.as<double>(), nr, nsplit, d_out);
   count_launch(2);
   BSG_CUDA(cudaGetLastError());
   return BSG_OK;
+}
+
+int simple_prodvec(bsg_bed *h, const int *d_row, int nr, const int *d_col, int nc, const double *d_center,
+                   const double *d_scale, const double *d_x, double *d_out, cudaStream_t s) {
+  return simple_prodvec_any(h, d_row, nr, d_col, nc, d_center, d_scale, d_x, d_out, s, 0);
+}
+
+// rowSumsSq[i] = sum_j X~[i, j]^2  (src/bed-fun.cpp:123-127) with the same accessor kernel
+int simple_rowsumssq(bsg_bed *h, const int *d_row, int nr, const int *d_col, int nc, const double *d_center,
+                     const double *d_scale, double *d_out, cudaStream_t s) {
+  return simple_prodvec_any(h, d_row, nr, d_col, nc, d_center, d_scale, nullptr, d_out, s, 1);
 }
 
 int counts_cols(bsg_bed *h, const int *d_row, int nr, const int *d_col, int nc, int32_t *d_out4, cudaStream_t s) {

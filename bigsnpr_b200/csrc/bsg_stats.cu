@@ -60,7 +60,7 @@ static bool host_identity(const int *ind, int len, int limit) {
 }
 
 // counts for (ind_row, ind_col) into d_out4 [4 x nc]; uses the counts cached at staging when all rows are taken
-static int col_counts_dev(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, int32_t **d_out) {
+int col_counts_dev(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, int32_t **d_out) {
   cudaStream_t s = h->stream;
   const int *d_row = nullptr, *d_col = nullptr;
   BSG_TRY(upload_index(h, ind_col, nc, h->m, h->w_idx_col, &d_col));

@@ -56,10 +56,12 @@ class ShardedMatVec:
         mine = self.local.cprodvec(y)
         if self.world == 1:
             return mine
-        sizes = [shard_bounds(self.m_total, self.world, r) for r in range(self.world)]
-        parts = [torch.empty(e - b, dtype=mine.dtype, device=mine.device) for b, e in sizes]
-        dist.all_gather(parts, mine, group=self.group)
-        return torch.cat(parts)
+        sizes = [e - b for b, e in (shard_bounds(self.m_total, self.world, r) for r in range(self.world))]
+        pad = torch.zeros(max(sizes), dtype=mine.dtype, device=mine.device)
+        pad[: mine.numel()] = mine
+        parts = [torch.empty_like(pad) for _ in sizes]
+        dist.all_gather(parts, pad, group=self.group)
+        return torch.cat([t[:k] for t, k in zip(parts, sizes)])
 
 
 class LocalGpu:
@@ -116,3 +118,158 @@ def randomsvd_sharded(obj_bed, m_total, k=10, tol=1e-4, maxit=1000, group=None):
                                   pd(u), pd(v), pd(c_out), pd(s_out), C.byref(niter), C.byref(nops), z.data_ptr(),
                                   C.cast(reduce_cb, C.c_void_p), None, int(m_total)))
     return {"d": d, "u": u.T, "v": v.T, "niter": niter.value, "nops": nops.value, "center": c_out, "scale": s_out}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# The other rows of SURVEY.md section 8e.  Everything below is host-side composition: the per-shard work is one
+# C-ABI call on the rank's own handle; what crosses ranks is stated per function.
+# ---------------------------------------------------------------------------------------------------------
+def _world(group=None):
+    import torch.distributed as dist
+
+    if not dist.is_initialized():
+        return 1, 0
+    return dist.get_world_size(group), dist.get_rank(group)
+
+
+def _coll_device(group=None):
+    """Device collectives run on: the current CUDA device under NCCL, the CPU under gloo."""
+    import torch
+    import torch.distributed as dist
+
+    if dist.is_initialized() and dist.get_backend(group) == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def gather_columns(local, m_total, group=None):
+    """Concatenate per-rank column slices (last axis = this rank's columns, shard_bounds order) on every rank.
+    Used for colstats / column counts / Xt.y: results are disjoint slices, so this is a gather, not a reduction."""
+    import torch
+    import torch.distributed as dist
+
+    world, _ = _world(group)
+    local = np.ascontiguousarray(local)
+    if world == 1:
+        return local
+    dev = _coll_device(group)
+    lead = local.shape[:-1]
+    sizes = [e - b for b, e in (shard_bounds(m_total, world, r) for r in range(world))]
+    width = max(sizes)  # shards differ by at most one column: pad to equal size, trim after the gather
+    mine = torch.zeros((width,) + lead, dtype=torch.from_numpy(local).dtype, device=dev)
+    mine[: local.shape[-1]] = torch.from_numpy(np.moveaxis(local, -1, 0).copy()).to(dev)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    out = torch.cat([t[:k] for t, k in zip(parts, sizes)])
+    return np.moveaxis(out.cpu().numpy(), 0, -1)
+
+
+def sum_over_ranks(local, group=None):
+    """Element-wise sum of equally-shaped arrays (by-row counts: 4 x n int32 partial counts per column shard)."""
+    import torch
+    import torch.distributed as dist
+
+    world, _ = _world(group)
+    if world == 1:
+        return np.asarray(local)
+    t = torch.from_numpy(np.ascontiguousarray(local)).to(_coll_device(group))
+    dist.all_reduce(t, group=group)
+    return t.cpu().numpy()
+
+
+def sharded_colstats(local_stats, m_total, group=None):
+    """bed_colstats over column shards: every field is per column -> gather."""
+    return {k: gather_columns(np.asarray(v), m_total, group) for k, v in local_stats.items()}
+
+
+def sharded_counts(local_counts, m_total, byrow=False, group=None):
+    """bed_counts over column shards.  By column: gather of the 4 x m_local blocks.  By row: each rank counted
+    its own columns for every sample -> all-reduce (sum) of 4 x n integers."""
+    if byrow:
+        return sum_over_ranks(np.asarray(local_counts, dtype=np.int64), group).astype(np.int32)
+    return gather_columns(np.asarray(local_counts), m_total, group)
+
+
+def tcrossprod_sharded(obj_bed, center, scale, ind_row=None, group=None):
+    """GRM over column shards: K = sum_g X~_g X~_g^T.  Each rank accumulates its K_g on the device
+    (bsg_tcrossprod_dev, no host copy) and one all-reduce of n^2 doubles sums them in place over NVLink.
+    Returns the n x n torch tensor on this rank's GPU (replicated)."""
+    import torch
+    import torch.distributed as dist
+
+    from . import _lib
+
+    L = _lib.lib()
+    n = obj_bed.nrow if ind_row is None else len(ind_row)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    K = torch.empty((n, n), dtype=torch.float64, device=dev)
+    center = np.ascontiguousarray(center, dtype=np.float64)
+    scale = np.ascontiguousarray(scale, dtype=np.float64)
+    ir = None if ind_row is None else np.ascontiguousarray(ind_row, dtype=np.int32)
+    _lib.check(L.bsg_tcrossprod_dev(obj_bed._h, None if ir is None else ir.ctypes.data_as(_lib.c_int_p), n, None,
+                                    obj_bed.ncol, center.ctypes.data_as(_lib.c_dbl_p),
+                                    scale.ctypes.data_as(_lib.c_dbl_p), K.data_ptr()))
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(K, group=group)
+    return K
+
+
+def halo_bounds(pos, size_bp, begin, end, right=False):
+    """Columns a shard [begin, end) has to see for the windowed pair statistics.
+
+    The reference pairs j < j0 iff pos[j] >= pos[j0] - size (src/corr.cpp:44-46, src/ld-scores.cpp:36-38).
+    Left halo (correlation columns begin..end-1 need their earlier partners): lo = first j with
+    pos[j] >= pos[begin] - size.  Right halo (LD scores also collect the pairs in which a column is the EARLIER
+    member): hi = one past the last j0 with pos[j0] - size <= pos[end-1].  Both use the same floating-point
+    expression as the pair test, so the shard sees exactly the reference's pairs."""
+    pos = np.asarray(pos, dtype=np.float64)
+    if end <= begin:
+        return begin, end
+    lo = int(np.searchsorted(pos, pos[begin] - size_bp, side="left"))
+    lo = min(lo, begin)
+    hi = end
+    if right:
+        hi = max(end, int(np.searchsorted(pos - size_bp, pos[end - 1], side="right")))
+    return lo, hi
+
+
+def cor_sharded(cor_fn, pos, size_bp, m_total, group=None, gather=True):
+    """Windowed correlation matrix over column shards, no data-path collective.
+
+    `cor_fn(lo, hi)` returns the CSC pieces (p, i, x) of corMat restricted to global columns [lo, hi) (local
+    0-based row indices).  The rank computes [lo, end) with the left halo, keeps the columns it owns and
+    re-bases the row indices; with gather=True the pieces are concatenated on every rank (host objects, like the
+    reference's list of columns)."""
+    import torch.distributed as dist
+
+    world, rank = _world(group)
+    b, e = shard_bounds(m_total, world, rank)
+    lo, _ = halo_bounds(pos, size_bp, b, e)
+    p, i, x = cor_fn(lo, e)
+    k0 = b - lo
+    s0, s1 = int(p[k0]), int(p[-1])
+    p_own = np.asarray(p[k0:], dtype=np.int64) - s0
+    i_own = np.asarray(i[s0:s1], dtype=np.int64) + lo
+    x_own = np.asarray(x[s0:s1], dtype=np.float64)
+    if not gather or world == 1:
+        return p_own, i_own, x_own
+    pieces = [None] * world
+    dist.all_gather_object(pieces, (p_own, i_own, x_own), group=group)
+    P, I, X, off = [np.zeros(1, dtype=np.int64)], [], [], 0
+    for pp, ii, xx in pieces:
+        P.append(pp[1:] + off)
+        off += int(pp[-1])
+        I.append(ii)
+        X.append(xx)
+    return np.concatenate(P), np.concatenate(I), np.concatenate(X)
+
+
+def ld_scores_sharded(ld_fn, pos, size_bp, m_total, group=None):
+    """LD scores over column shards.  `ld_fn(lo, hi)` returns the scores of global columns [lo, hi) computed on
+    that range alone.  With halos on both sides every pair a shard's column belongs to is inside the range, so the
+    kept middle part is complete and the result is a gather (instead of the all-reduce of boundary terms)."""
+    world, rank = _world(group)
+    b, e = shard_bounds(m_total, world, rank)
+    lo, hi = halo_bounds(pos, size_bp, b, e, right=True)
+    ld = np.asarray(ld_fn(lo, hi), dtype=np.float64)
+    return gather_columns(ld[b - lo:e - lo], m_total, group)

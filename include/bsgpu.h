@@ -133,11 +133,29 @@ int bsg_clumping_chr(bsg_bed *h, const int *ind_row, int nr, const int *ind_col,
                      const double *scale, const int *ordInd, const double *pos, double size, double thr,
                      int *keep);
 
+/* ---- PCA projection / pcadapt ------------------------------------------- */
+/* _bigsnpr_prod_and_rowSumsSq: src/bed-fun.cpp:103-133 (R: part_prod, R/bed-projectPCA.R:31-58).
+ * V is nc x K column-major; XV (nr x K column-major) = X~ V and rowSumsSq[nr] = sum_j X~_ij^2 with the
+ * bedAccScaled semantics (missing value -> 0).  center / scale length nc, else
+ * "Incompatibility between dimensions." */
+int bsg_prod_and_rowsumssq(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc,
+                           const double *center, const double *scale, const double *V, int K,
+                           double *XV, double *rowSumsSq);
+/* _bigsnpr_multLinReg: src/multLinReg.cpp:8-95 (R: pcadapt0, R/pcadapt.R:3-27).  U is nr x K column-major;
+ * tscores is nc x K column-major (the reference returns transpose(res)); NA_REAL is written as NaN.
+ * Works on .bed handles and on FBM.code256 handles alike (the reference dispatches on the class, :72-92). */
+int bsg_multlinreg(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, const double *U, int K,
+                   double *tscores);
+
 /* ---- Gram product --------------------------------------------------------------------------------- */
 /* bed_tcrossprodSelf's block loop collapsed into one call: R/bed-tcrossprodSelf.R:38-49 +
  * src/bed-mat-acc.cpp:30-49.  K is nr x nr; center/scale are the per-column scaling (length nc). */
 int bsg_tcrossprod(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc,
                    const double *center, const double *scale, double *K);
+/* Same product, result left in the caller's DEVICE buffer K_dev (nr x nr doubles, full symmetric matrix) so
+ * column shards can be summed in place by one all-reduce (GRM row). */
+int bsg_tcrossprod_dev(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc,
+                       const double *center, const double *scale, double *K_dev);
 
 /* ---- truncated SVD ----------------------------------------------------------------------------------- */
 /* bed_randomSVD: R/autoSVD.R:205-219 -> bigstatsr::big_randomSVD -> RSpectra::svds.  The Lanczos

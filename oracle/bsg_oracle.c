@@ -363,6 +363,59 @@ int orc_prod_and_rowSumsSq(const uint8_t *bed, int n_tot, int m_tot, const int *
   return ORC_OK;
 }
 
+/* src/multLinReg.cpp:8-60  multLinReg : per SNP and per column k of U, the t-score of the simple linear
+ * regression of the genotype on U[,k] over the samples where the genotype is present.  The sums run in sample
+ * order in fp64 like the reference; the statistic is written with the reference's operation order (:44-51).
+ * `tscores` is nc x K column-major (the reference returns transpose(res), :56).  NA_REAL is written as NaN. */
+int orc_multLinReg(int kind, const uint8_t *mat, int n_tot, int m_tot, const double *code256,
+                   const int *ind_row, int nr, const int *ind_col, int nc, const double *U /* nr x K */,
+                   int K, int ncores, double *tscores /* nc x K */) {
+  acc_t a;
+  int rc = acc_init(&a, kind, mat, n_tot, m_tot, code256, ind_row, nr, ind_col, nc);
+  if (rc) { acc_free(&a); return rc; }
+  if (ncores < 1) ncores = 1;
+  const size_t n = nr, m = nc;
+  int failed = 0;
+#pragma omp parallel num_threads(ncores)
+  {
+    double *sums = (double *)malloc((size_t)(K > 0 ? K : 1) * 3 * sizeof(double));
+    if (!sums) {
+#pragma omp atomic write
+      failed = 1;
+    }
+#pragma omp for
+    for (size_t j = 0; j < m; j++) {
+      if (!sums) continue;
+      double *xy = sums, *ys = sums + K, *yy = sums + 2 * (size_t)K;
+      for (int k = 0; k < 3 * K; k++) sums[k] = 0;
+      int nona = (int)n;
+      double xSum = 0, xxSum = 0;
+      for (size_t i = 0; i < n; i++) {
+        const double x = acc_get3(&a, i, j);
+        if (x == 3) { nona--; continue; }
+        xSum += x;
+        xxSum += x * x;
+        for (int k = 0; k < K; k++) {
+          const double y = U[i + n * (size_t)k];
+          xy[k] += x * y;
+          ys[k] += y;
+          yy[k] += y * y;
+        }
+      }
+      const double deno_x = xxSum - xSum * xSum / nona;
+      for (int k = 0; k < K; k++) {
+        const double num = xy[k] - xSum * ys[k] / nona;
+        const double deno_y = yy[k] - ys[k] * ys[k] / nona;
+        const double deno = deno_x * deno_y - num * num;
+        tscores[j + m * (size_t)k] = (deno == 0 || nona < 2) ? NAN : num * sqrt((nona - 2) / deno);
+      }
+    }
+    free(sums);
+  }
+  acc_free(&a);
+  return failed ? ORC_ERR_ALLOC : ORC_OK;
+}
+
 /* src/colstats.cpp:8-35  snp_colstats : FBM.code256 column sums, no NA handling. */
 int orc_snp_colstats(const uint8_t *bk, int n_tot, int m_tot, const double *code256,
                      const int *ind_row, int nr, const int *ind_col, int nc, int ncores,

@@ -291,6 +291,21 @@ def corMat(obj, rowInd, colInd, size, thr, pos, fill_diag=True, ncores=1):
     return p, i, x
 
 
+def multLinReg(obj, ind_row, ind_col, U, ncores=1):
+    """src/multLinReg.cpp:8-95 -> t-scores (nc, K); NA_REAL is NaN."""
+    ind_row, ind_col = _i32(ind_row), _i32(ind_col)
+    U = np.asfortranarray(np.asarray(U, dtype=np.float64).reshape(len(U), -1))
+    if U.shape[0] != ind_row.size:
+        raise OracleError(ERR_MSG[1])
+    kind, mat, n, m, code = _kind_args(obj)
+    K = U.shape[1]
+    out = np.zeros((ind_col.size, K), dtype=np.float64, order="F")
+    with np.errstate(all="ignore"):
+        _chk(lib().orc_multLinReg(kind, mat, n, m, code, _p(ind_row, C.c_int), ind_row.size, _p(ind_col, C.c_int),
+                                  ind_col.size, _p(U, C.c_double), K, int(ncores), _p(out, C.c_double)))
+    return out
+
+
 def ld_scores(obj, rowInd, colInd, size, pos, ncores=1):
     """src/ld-scores.cpp:11-78,83-105."""
     rowInd, colInd = _i32(rowInd), _i32(colInd)

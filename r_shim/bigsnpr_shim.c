@@ -227,6 +227,34 @@ SEXP _bigsnpr_bed_clumping_chr(SEXP obj_bed, SEXP BM2, SEXP ind_row, SEXP ind_co
   return R_NilValue;
 }
 
+/* _bigsnpr_prod_and_rowSumsSq: src/bed-fun.cpp:103-133 (6 arguments) -> list(XV, rowSumsSq) */
+SEXP _bigsnpr_prod_and_rowSumsSq(SEXP obj_bed, SEXP ind_row, SEXP ind_col, SEXP center, SEXP scale, SEXP V) {
+  bsg_bed *h = handle_of(obj_bed);
+  int nr = LENGTH(ind_row), nc = LENGTH(ind_col), K = Rf_ncols(V);
+  if (LENGTH(center) != nc || LENGTH(scale) != nc || Rf_nrows(V) != nc) Rf_error("Incompatibility between dimensions.");
+  SEXP XV = PROTECT(Rf_allocMatrix(REALSXP, nr, K)), rss = PROTECT(Rf_allocVector(REALSXP, nr));
+  chk(bsg_prod_and_rowsumssq(h, INTEGER(ind_row), nr, INTEGER(ind_col), nc, REAL(center), REAL(scale), REAL(V), K, REAL(XV),
+                             REAL(rss)));
+  SEXP res = PROTECT(Rf_allocVector(VECSXP, 2));
+  SET_VECTOR_ELT(res, 0, XV);
+  SET_VECTOR_ELT(res, 1, rss);
+  UNPROTECT(3);
+  return res;
+}
+
+/* _bigsnpr_multLinReg: src/multLinReg.cpp:64-95 (5 arguments; `obj` is a bed or an FBM.code256 environment) */
+SEXP _bigsnpr_multLinReg(SEXP obj, SEXP ind_row, SEXP ind_col, SEXP U, SEXP ncores) {
+  bsg_bed *h = handle_of(obj);
+  int nr = LENGTH(ind_row), nc = LENGTH(ind_col), K = Rf_ncols(U);
+  if (Rf_nrows(U) != nr) Rf_error("Incompatibility between dimensions.");
+  SEXP t = PROTECT(Rf_allocMatrix(REALSXP, nc, K));
+  chk(bsg_multlinreg(h, INTEGER(ind_row), nr, INTEGER(ind_col), nc, REAL(U), K, REAL(t)));
+  for (R_xlen_t i = 0; i < XLENGTH(t); i++)
+    if (ISNAN(REAL(t)[i])) REAL(t)[i] = NA_REAL; /* the library writes NaN where the reference writes NA_REAL */
+  UNPROTECT(1);
+  return t;
+}
+
 /* new entry points: R/bed-tcrossprodSelf.R's block loop and R/autoSVD.R's bed_randomSVD collapse to one call each */
 SEXP _bigsnpr_bed_tcrossprod_gpu(SEXP obj_bed, SEXP ind_row, SEXP ind_col, SEXP center, SEXP scale) {
   bsg_bed *h = handle_of(obj_bed);
@@ -271,6 +299,8 @@ static const R_CallMethodDef CallEntries[] = {
     {"_bigsnpr_corMat", (DL_FUNC)&_bigsnpr_corMat, 8},
     {"_bigsnpr_ld_scores", (DL_FUNC)&_bigsnpr_ld_scores, 6},
     {"_bigsnpr_bed_clumping_chr", (DL_FUNC)&_bigsnpr_bed_clumping_chr, 12},
+    {"_bigsnpr_prod_and_rowSumsSq", (DL_FUNC)&_bigsnpr_prod_and_rowSumsSq, 6},
+    {"_bigsnpr_multLinReg", (DL_FUNC)&_bigsnpr_multLinReg, 5},
     {"_bigsnpr_bed_tcrossprod_gpu", (DL_FUNC)&_bigsnpr_bed_tcrossprod_gpu, 5},
     {"_bigsnpr_bed_randomSVD_gpu", (DL_FUNC)&_bigsnpr_bed_randomSVD_gpu, 7},
     {NULL, NULL, 0}};

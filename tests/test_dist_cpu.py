@@ -82,3 +82,92 @@ def test_sharded_matvec_gloo_world2():
         assert p.exitcode == 0
     for rank, e1, e2, e3 in res:
         assert e1 < 1e-12 and e2 == 0.0 and e3 == 0.0, (rank, e1, e2, e3)
+
+
+# ---- the other section-8e rows: stats / counts / GRM / windowed correlation / LD scores over column shards ----
+def _worker_rows(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from bigsnpr_b200 import dist as D
+        from oracle import ref
+
+        o = ref.OracleBed(os.path.join(ROOT, "tests", "golden", "example-missing.bed"))
+        m = o.ncol  # 500: not a multiple of the world size 3, shards differ by one column
+        pos = np.cumsum(np.random.default_rng(5).integers(1, 4000, size=m)).astype(np.float64)
+        b, e = D.shard_bounds(m, world, rank)
+        cols = lambda lo, hi: np.arange(lo + 1, hi + 1, dtype=np.int32)  # noqa: E731
+        errs = {}
+
+        rows = np.arange(1, o.nrow + 1, dtype=np.int32)
+        st = D.sharded_colstats(ref.bed_colstats(o, rows, cols(b, e)), m)
+        want = ref.bed_colstats(o, rows, cols(0, m))
+        errs["colstats"] = max(float(np.max(np.abs(np.asarray(st[k], dtype=float) - np.asarray(want[k], dtype=float))))
+                               for k in want)
+        cc = D.sharded_counts(ref.bed_counts(o, ind_col=cols(b, e)), m)
+        errs["col_counts"] = int(np.max(np.abs(cc - ref.bed_counts(o, ind_col=cols(0, m)))))
+        rc = D.sharded_counts(ref.bed_counts(o, ind_col=cols(b, e), byrow=True), m, byrow=True)
+        errs["row_counts"] = int(np.max(np.abs(rc - ref.bed_counts(o, ind_col=cols(0, m), byrow=True))))
+
+        # GRM: sum of the shards' K (the GPU path all-reduces the device tensor; same reduction here on CPU)
+        Kl, _, _ = ref.bed_tcrossprodSelf(o, ind_col=cols(b, e))
+        K = D.sum_over_ranks(Kl)
+        Kw, _, _ = ref.bed_tcrossprodSelf(o, ind_col=cols(0, m))
+        errs["grm"] = float(np.max(np.abs(K - Kw)) / np.max(np.abs(Kw)))
+
+        size_kb = 30.0
+        cor_fn = lambda lo, hi: ref.cor0(o, ind_col=cols(lo, hi), size=size_kb, alpha=0.5, infos_pos=pos[lo:hi])  # noqa: E731
+        p, i, x = D.cor_sharded(cor_fn, pos, size_kb * 1000.0, m)
+        pw, iw, xw = ref.cor0(o, ind_col=cols(0, m), size=size_kb, alpha=0.5, infos_pos=pos)
+        same = np.array_equal(p, pw) and np.array_equal(i, iw) and np.array_equal(x, xw, equal_nan=True)
+        errs["cor_identical"] = bool(same)
+        errs["cor_nnz"] = int(pw[-1])
+
+        ld_fn = lambda lo, hi: ref.ld0(o, ind_col=cols(lo, hi), size=size_kb, infos_pos=pos[lo:hi])  # noqa: E731
+        ld = D.ld_scores_sharded(ld_fn, pos, size_kb * 1000.0, m)
+        ldw = ref.ld0(o, ind_col=cols(0, m), size=size_kb, infos_pos=pos)
+        errs["ld"] = float(np.nanmax(np.abs(ld - ldw)))
+        lo, hi = D.halo_bounds(pos, size_kb * 1000.0, b, e, right=True)
+        errs["halo"] = (b - lo, hi - e)
+        q.put((rank, errs))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_halo_bounds_cover_the_reference_window():
+    from bigsnpr_b200.dist import halo_bounds
+
+    rng = np.random.default_rng(2)
+    pos = np.cumsum(rng.integers(0, 50, size=400)).astype(np.float64)
+    size = 333.0
+    for b, e in ((0, 100), (100, 250), (250, 400), (399, 400)):
+        lo, hi = halo_bounds(pos, size, b, e, right=True)
+        for j0 in range(b, e):  # every partner the reference pairs with a shard column is inside [lo, hi)
+            part = [j for j in range(400) if (j < j0 and pos[j] >= pos[j0] - size) or (j > j0 and pos[j0] >= pos[j] - size)]
+            assert all(lo <= j < hi for j in part)
+        assert lo == 0 or not (pos[lo - 1] >= pos[b] - size)
+        assert hi == 400 or not (pos[e - 1] >= pos[hi] - size)
+
+
+def test_sharded_rows_gloo_world3():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world = 3
+    procs = [ctx.Process(target=_worker_rows, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=60) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, e in res:
+        assert e["colstats"] == 0.0 and e["col_counts"] == 0 and e["row_counts"] == 0, (rank, e)
+        assert e["grm"] < 1e-12, (rank, e)
+        assert e["cor_identical"] and e["cor_nnz"] > 500, (rank, e)
+        assert e["ld"] < 1e-10, (rank, e)
+    assert any(e["halo"][0] > 0 for _, e in res) and any(e["halo"][1] > 0 for _, e in res)

@@ -344,3 +344,86 @@ def test_clumping_identical_to_oracle(B, gbed, gbed_na, oracle, obed, obed_na, r
     assert B.bed_clumping(gbed, exclude=np.arange(1, 101)).min() > 100
     with pytest.raises(ValueError, match="can't be `NULL`"):
         B.bed_clumping(gbed, ind_row=None)
+
+
+def test_prod_and_rowSumsSq_and_projection(B, gbed, gbed_na, oracle, obed, obed_na, rng):
+    # src/bed-fun.cpp:103-133 against the oracle; tests/testthat/test-2-pca-project.R:8-22,43-55:
+    # simple_proj[ind.row, ] == predict(obj.svd) (1e-4), dimension and NULL errors
+    for g, o in ((gbed_na, obed_na), (gbed, obed)):
+        n, m = o.nrow, o.ncol
+        sc = oracle.bed_scaleBinom(o)
+        for ir, ic in ((np.arange(1, n + 1), np.arange(1, m + 1)),
+                       (rng.choice(n, n // 2, replace=False) + 1, rng.choice(m, m // 3, replace=False) + 1),
+                       (rng.integers(1, n + 1, size=37), rng.integers(1, m + 1, size=211))):  # multisets
+            c, s = sc["center"][ic - 1], sc["scale"][ic - 1]
+            V = rng.normal(size=(ic.size, 4))
+            XV, rss = B.prod_and_rowSumsSq(g, ir, ic, c, s, V)
+            XVo, rsso = oracle.prod_and_rowSumsSq(o, ir, ic, c, s, V)
+            _close(XV, XVo, tol=1e-11)
+            _close(rss, rsso, tol=1e-12)
+        # identity scaling and a vector V
+        ic = np.arange(1, m + 1)
+        XV, rss = B.prod_and_rowSumsSq(g, np.arange(1, n + 1), ic, np.zeros(m), np.ones(m), rng.normal(size=m))
+        dense = oracle.read_bed_scaled(o, np.arange(1, n + 1), ic, np.zeros(m), np.ones(m))
+        assert np.array_equal(rss, (dense ** 2).sum(1))  # integer-valued: exact
+    # handle without the sample-major copy: accessor kernels, same numbers
+    g1 = B.Bed(os.path.join(GOLDEN, "example-missing.bed"), layouts=B.LAYOUT_SNP_MAJOR)
+    sc = oracle.bed_scaleBinom(obed_na)
+    ir, ic = np.arange(1, obed_na.nrow + 1), np.arange(1, obed_na.ncol + 1)
+    V = rng.normal(size=(ic.size, 2))
+    XV, rss = B.prod_and_rowSumsSq(g1, ir, ic, sc["center"], sc["scale"], V)
+    XVo, rsso = oracle.prod_and_rowSumsSq(obed_na, ir, ic, sc["center"], sc["scale"], V)
+    _close(XV, XVo, tol=1e-11)
+    _close(rss, rsso, tol=1e-12)
+    # zero scale: the reference's Inf / NaN pattern (table arithmetic), not a crash
+    s0 = sc["scale"].copy(); s0[3] = 0.0
+    with np.errstate(all="ignore"):
+        XV, rss = B.prod_and_rowSumsSq(gbed_na, ir, ic, sc["center"], s0, V)
+        XVo, rsso = oracle.prod_and_rowSumsSq(obed_na, ir, ic, sc["center"], s0, V)
+    assert np.array_equal(np.isfinite(rss), np.isfinite(rsso)) and np.array_equal(np.isfinite(XV), np.isfinite(XVo))
+    with pytest.raises(ValueError, match="Incompatibility between dimensions."):
+        B.prod_and_rowSumsSq(gbed_na, ir, ic, sc["center"][1:], sc["scale"][1:], V)
+    # projection of the training samples reproduces the PC scores u d
+    ind_row = np.sort(rng.choice(obed.nrow, 400, replace=False)) + 1
+    svd = B.bed_randomSVD(gbed, ind_row=ind_row, k=6)
+    with pytest.raises(ValueError, match="'ind.col' can't be `NULL`."):
+        B.bed_projectSelfPCA(svd, gbed, ind_row=ind_row)
+    with pytest.raises(ValueError, match="Incompatibility between dimensions."):
+        B.bed_projectSelfPCA(svd, gbed, ind_row=ind_row, ind_col=np.arange(1, 6))
+    proj = B.bed_projectSelfPCA(svd, gbed, ind_row=np.arange(1, obed.nrow + 1), ind_col=np.arange(1, obed.ncol + 1))
+    np.testing.assert_allclose(proj["simple_proj"][ind_row - 1], svd["u"] * svd["d"], rtol=0, atol=1e-4 * svd["d"][0])
+    assert proj["X_norm"].shape == (obed.nrow,) and np.all(proj["X_norm"] > 0)
+
+
+def test_multLinReg_pcadapt(B, gbed, gbed_na, oracle, obed, obed_na, rng):
+    # src/multLinReg.cpp:8-95 against the oracle (bed and FBM.code256 handles), R/pcadapt.R:3-27
+    for g, o in ((gbed_na, obed_na), (gbed, obed)):
+        n, m = o.nrow, o.ncol
+        for ir, ic, K in ((np.arange(1, n + 1), np.arange(1, m + 1), 3),
+                          (rng.choice(n, n // 2, replace=False) + 1, rng.choice(m, m // 4, replace=False) + 1, 1),
+                          (rng.integers(1, n + 1, size=150), rng.integers(1, m + 1, size=97), 2)):
+            U = np.linalg.qr(rng.normal(size=(ir.size, K)))[0]
+            t = B.multLinReg(g, ir, ic, U)
+            to = oracle.multLinReg(o, ir, ic, U, ncores=2)
+            assert np.array_equal(np.isnan(t), np.isnan(to))
+            ok = ~np.isnan(to)
+            assert np.max(np.abs(t[ok] - to[ok]) / (1.0 + np.abs(to[ok]))) < 1e-9
+    # FBM.code256 handle == bed handle; constant column -> NA (deno == 0)
+    G = rng.integers(0, 4, size=(120, 40)).astype(np.uint8)
+    G[:, 5] = 1
+    G[:119, 6] = 3  # one genotype present: nona < 2 -> NA
+    G[:118, 7] = 3  # two present: a perfect fit, deno is 0 up to rounding -> NA or 0, not comparable
+    gf, of = B.Bed.from_fbm(G), oracle.OracleFBM(G)
+    ir, ic = np.arange(1, 121), np.arange(1, 41)
+    U = np.linalg.qr(rng.normal(size=(120, 2)))[0]
+    t, to = B.multLinReg(gf, ir, ic, U), oracle.multLinReg(of, ir, ic, U)
+    assert np.isnan(to[5]).all() and np.isnan(to[6]).all() and np.isnan(t[5]).all() and np.isnan(t[6]).all()
+    assert np.all(np.isnan(t[7]) | (np.abs(t[7]) < 1e-6))
+    t[7] = to[7] = np.nan
+    assert np.array_equal(np.isnan(t), np.isnan(to))
+    ok = ~np.isnan(to)
+    assert np.max(np.abs(t[ok] - to[ok]) / (1.0 + np.abs(to[ok]))) < 1e-9
+    res = B.bed_pcadapt(gbed, U_row=np.linalg.qr(rng.normal(size=(obed.nrow, 1)))[0][:, 0])
+    assert res["tscores"].shape == (obed.ncol, 1) and res["score"].shape == (obed.ncol,)
+    with pytest.raises(ValueError, match="Incompatibility between dimensions."):
+        B.bed_pcadapt(gbed, U_row=np.ones((10, 2)))
