@@ -163,6 +163,9 @@ def main():
     ap.add_argument("--na-rate", type=float, default=0.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-svd", action="store_true", help="skip the bed_randomSVD wall-time leg")
+    ap.add_argument("--layout", choices=("auto", "snp"), default="auto",
+                    help="snp: stage the SNP-major copy only (X.y runs on the transposing kernel k_pmvT)")
+    ap.add_argument("--no-single-copy", action="store_true", help="skip the extra leg timing X.y on the SNP-major copy alone")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -197,7 +200,8 @@ def main():
         per = (wl["m"] + world - 1) // world
         col0 = rank * per
         m_loc = max(0, min(wl["m"], col0 + per) - col0)
-    g = B.Bed.synthetic(n, m_loc, seed=SEED, na_rate=args.na_rate, col_offset=col0, device=local)
+    g = B.Bed.synthetic(n, m_loc, seed=SEED, na_rate=args.na_rate, col_offset=col0, device=local,
+                        layouts=B.LAYOUT_SNP_MAJOR if args.layout == "snp" else B.LAYOUT_AUTO)
     layouts = g.layouts
     sc = B.bed_scaleBinom(g)
     view = B.View(g, center=sc["center"], scale=sc["scale"])
@@ -269,7 +273,8 @@ def main():
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "kernel": "bsg::pmv::k_pmv",
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                "kernel": "bsg::pmv::k_pmv" if (layouts & 2) else "bsg::pmvt::k_pmvT",
                 "kernel_ms": kern_ms, "launches_timed": cnt.value, "algorithmic_bytes_per_launch": alg_bytes,
                 "peak_source": peak_src, "kernel_share_of_step": (kern_ms * args.steps / ms) if ms > 0 else None}
 
@@ -304,6 +309,33 @@ def main():
     e2e_val = float(tg.item()) * e2e_steps / float(te.item())
     # agreement of the two paths (device-resident vs host call) on this rank's data
     chk = float((out.cpu() - outh).abs().max().item()) if world == 1 else None
+
+    # ---------------- extra leg: the same product from the SNP-major copy alone (k_pmvT) ----------------
+    single_copy = None
+    if (layouts & 2) and not args.no_single_copy:
+        _lib.check(L.bsg_set_prodvec_path(1))
+        try:
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+            L.bsg_set_kernel_timing(1)
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ksc = max(3, min(args.steps, 20))
+            s0.record()
+            for _ in range(ksc):
+                step()
+            s1.record()
+            torch.cuda.synchronize()
+            c2, t2 = C.c_int(0), C.c_double(0)
+            _lib.check(L.bsg_kernel_time_stats(C.byref(c2), C.byref(t2)))
+            L.bsg_set_kernel_timing(0)
+            kms = t2.value / max(c2.value, 1)
+            single_copy = {"kernel": "bsg::pmvt::k_pmvT", "steps": ksc, "ms_per_step": s0.elapsed_time(s1) / ksc,
+                           "kernel_ms": kms, "achieved": alg_bytes / (kms / 1e3) / 1e9 if kms > 0 else None,
+                           "frac": (alg_bytes / (kms / 1e3) / 1e9 / peak) if kms > 0 else None,
+                           "note": "X.y read from the SNP-major copy only (no sample-major copy needed); this rank"}
+        finally:
+            _lib.check(L.bsg_set_prodvec_path(0))
 
     # ---------------- second headline metric: bed_randomSVD wall time (not part of `value`) ----------------
     svd_info = None
@@ -358,7 +390,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_val, "unit": "genotypes/s", "h2d_bytes_per_step": 3 * 8 * m_loc,
                     "d2h_bytes_per_step": 8 * n, "steps": e2e_steps, "max_abs_diff_vs_resident": chk},
-            "clocks": clocks, "gpu_launches": launches, "svd": svd_info,
+            "clocks": clocks, "gpu_launches": launches, "svd": svd_info, "single_copy": single_copy,
         }
         print(json.dumps(line), flush=True)
     view.close()

@@ -53,6 +53,7 @@ SIGNATURES = {
     "bsg_free": (None, [vp]),
     "bsg_clumping_chr": (C.c_int, [vp, c_int_p, C.c_int, c_int_p, C.c_int, c_dbl_p, c_dbl_p, c_int_p, c_dbl_p, C.c_double,
                                    C.c_double, c_int_p]),
+    "bsg_set_prodvec_path": (C.c_int, [C.c_int]),
     "bsg_prod_and_rowsumssq": (C.c_int, [vp, c_int_p, C.c_int, c_int_p, C.c_int, c_dbl_p, c_dbl_p, c_dbl_p, C.c_int,
                                          c_dbl_p, c_dbl_p]),
     "bsg_multlinreg": (C.c_int, [vp, c_int_p, C.c_int, c_int_p, C.c_int, c_dbl_p, C.c_int, c_dbl_p]),

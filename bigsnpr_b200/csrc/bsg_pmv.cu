@@ -828,6 +828,245 @@ static int run_pmv(bsg_view *v, const uint8_t *P, int64_t stride, int L, const i
 
 }  // namespace pmv
 
+// =============================================================================================
+// k_pmvT: X.y straight from the SNP-major copy (no sample-major copy needed).
+//
+// The contraction now runs ACROSS lines (SNPs) while the bytes of a line run along samples, so the IMMA k index
+// has to be assembled from 4 different lines.  A CTA owns TBYTES sample-bytes (4 TBYTES samples) of every line,
+// 64 bytes per warp, and walks a range of lines 32 at a time: every warp stages its own 32 x 64 B strip with
+// cp.async into a private multi-stage ring (no block barrier in the loop), laid out so the fragment reads are
+// conflict free; every thread reads one 32-bit word from 4 consecutive lines and transposes the 4 x 4 bytes with
+// 8 PRMTs.  A transposed word holds, for 4 lines, the
+// byte of 4 samples: masking the 2-bit fields gives the A fragments of 4 IMMAs (sample 4b + c, c = 0..3; field c
+// enters as 4^c x code, removed by an exact shift in the epilogue).  B = the 8 signed base-256 digits
+// of the quantised vector, 32 lines per step, laid out [step][slice][32] so a B register is one aligned word.
+// Per warp and step: 16 IMMAs over 32 lines x 64 bytes; accumulators: 4 (byte) x 4 (field) x 4 registers.
+// Missing values: a second launch with the flag plane (PLANE 1) and the matching digit block.
+// =============================================================================================
+namespace pmvt {
+using namespace pmv;
+constexpr int TLINES = 32, TBYTES = 512, TWARPS = 8, TSTAGES = 6;
+constexpr int WSTAGE_BYTES = TLINES * 64;                  // one warp's strip of a step: 32 lines x 64 B
+constexpr int TSMEM = TWARPS * TSTAGES * WSTAGE_BYTES;     // 96 KB -> 2 CTAs per SM
+constexpr int MAX_LINES_PER_ITEM = 1 << 16;                // 64 x 3 x 128 x 2^16 < 2^31
+
+struct TArgs {
+  const uint8_t *P;
+  int64_t stride;
+  const int *lines;   // physical line of selected column t (null = identity)
+  int nlines;
+  const uint8_t *dig; // [steps][8][32]
+  int lines_per_split, ksplit, nblocks, n;
+  long long *part;    // [n][16]
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+  return r;
+}
+
+template <int PLANE, bool LINES>
+__global__ void __launch_bounds__(TWARPS * 32, 2) k_pmvT(const TArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+  const int blk = blockIdx.x % a.nblocks, ks = blockIdx.x / a.nblocks;
+  const int64_t byte0 = (int64_t)blk * TBYTES + 64 * warp;  // this warp's 64 sample-bytes of every line
+  const int l0 = ks * a.lines_per_split, l1 = min(a.nlines, l0 + a.lines_per_split);
+  const int nsteps = (l1 - l0 + TLINES - 1) / TLINES;
+  // Every warp runs its own cp.async pipeline over its own strip (no block-level barrier in the loop):
+  // TSTAGES stages of 32 lines x 64 B.  Word (row = 16 hf + 4 qq + r, column wc = 8 sl + gg) of a stage lives at
+  // word offset ((((r 2 + hf) 2 + sl) 4 + qq) 8 + gg): the 32 lanes of one fragment read (fixed r, hf, sl) hit 32
+  // consecutive words, and a 16-byte granule (4 consecutive gg of one row) stays contiguous for cp.async.
+  const uint32_t wbase = smem_u32(smem) + warp * (TSTAGES * WSTAGE_BYTES);
+
+  // loader role of the lane: rows 8 i + (lane >> 2), granule lane & 3.  Out-of-range rows / byte columns are
+  // clamped to valid memory instead of predicated: their digits are zero, resp. their samples are never stored.
+  const int lrow = lane >> 2, lch = lane & 3;
+  const int64_t colb = (byte0 + 16 * lch < a.stride) ? byte0 + 16 * lch : 0;
+  uint32_t dst_off[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int row = 8 * i + lrow;
+    const int hf = row >> 4, qq = (row >> 2) & 3, r = row & 3, sl = lch >> 1, hc = lch & 1;
+    dst_off[i] = (uint32_t)((((((r * 2 + hf) * 2 + sl) * 4 + qq) * 8) + 4 * hc) * 4);
+  }
+  const int full_steps = (l1 - l0) / TLINES;  // steps whose 32 lines all exist
+  const int64_t stride8 = 8 * a.stride;
+  // general issue: any step, clamped rows, optional line list
+  auto issue = [&](int step, int stage) {
+    const uint32_t dst = wbase + stage * WSTAGE_BYTES;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int t = min(l0 + step * TLINES + 8 * i + lrow, l1 - 1);
+      const int phys = LINES ? a.lines[t] : t;
+      cp_async16(dst + dst_off[i], a.P + colb + (int64_t)phys * a.stride, 16);
+    }
+  };
+
+  int acc[4][4][4];
+#pragma unroll
+  for (int j = 0; j < 4; j++)
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+      for (int k = 0; k < 4; k++) acc[j][c][k] = 0;
+
+#pragma unroll
+  for (int st = 0; st < TSTAGES - 1; st++) {
+    if (st < nsteps) issue(st, st);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  // B registers of the step: slice g, lines 4q..4q+3 and 16+4q..16+4q+3
+  const uint8_t *dg = a.dig + (int64_t)(l0 / TLINES) * 256 + g * 32 + 4 * q;
+  uint32_t nb0 = 0, nb1 = 0;
+  if (nsteps > 0) {
+    nb0 = *reinterpret_cast<const uint32_t *>(dg);
+    nb1 = *reinterpret_cast<const uint32_t *>(dg + 16);
+  }
+  const uint32_t rd_base = wbase + (uint32_t)((q * 8 + g) * 4);  // + ((r 2 + hf) 2 + sl) * 128 bytes
+
+  auto compute = [&](uint32_t st_base, uint32_t b0, uint32_t b1) {
+    uint32_t W[2][2][4];  // [slot g / g+8][lines lo / hi][byte]
+#pragma unroll
+    for (int sl = 0; sl < 2; sl++)
+#pragma unroll
+      for (int hf = 0; hf < 2; hf++) {
+        const uint32_t ad = st_base + (hf * 2 + sl) * 128;
+        const uint32_t x0 = lds32(ad), x1 = lds32(ad + 512), x2 = lds32(ad + 1024), x3 = lds32(ad + 1536);
+        const uint32_t t0 = prmt(x0, x1, 0x5140), t1 = prmt(x2, x3, 0x5140);
+        const uint32_t t2 = prmt(x0, x1, 0x7362), t3 = prmt(x2, x3, 0x7362);
+        W[sl][hf][0] = prmt(t0, t1, 0x5410);
+        W[sl][hf][1] = prmt(t0, t1, 0x7632);
+        W[sl][hf][2] = prmt(t2, t3, 0x5410);
+        W[sl][hf][3] = prmt(t2, t3, 0x7632);
+      }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      uint32_t wa = W[0][0][j], wb = W[1][0][j], wc2 = W[0][1][j], wd = W[1][1][j];
+      if (PLANE == 1) {  // missing-value flag at the low bit of each 2-bit field
+        wa = wa & (wa >> 1) & 0x55555555u;
+        wb = wb & (wb >> 1) & 0x55555555u;
+        wc2 = wc2 & (wc2 >> 1) & 0x55555555u;
+        wd = wd & (wd >> 1) & 0x55555555u;
+      } else if (PLANE == 2) {  // high bit of the code (codes 2 and 3), for the sums of squares
+        wa = (wa >> 1) & 0x55555555u;
+        wb = (wb >> 1) & 0x55555555u;
+        wc2 = (wc2 >> 1) & 0x55555555u;
+        wd = (wd >> 1) & 0x55555555u;
+      }
+      // field c of every byte enters as 4^c x code (exact, undone in the epilogue): no shifts in the loop
+      mma_u8s8(acc[j][0], wa & 0x03030303u, wb & 0x03030303u, wc2 & 0x03030303u, wd & 0x03030303u, b0, b1);
+      mma_u8s8(acc[j][1], wa & 0x0C0C0C0Cu, wb & 0x0C0C0C0Cu, wc2 & 0x0C0C0C0Cu, wd & 0x0C0C0C0Cu, b0, b1);
+      mma_u8s8(acc[j][2], wa & 0x30303030u, wb & 0x30303030u, wc2 & 0x30303030u, wd & 0x30303030u, b0, b1);
+      mma_u8s8(acc[j][3], wa & 0xC0C0C0C0u, wb & 0xC0C0C0C0u, wc2 & 0xC0C0C0C0u, wd & 0xC0C0C0C0u, b0, b1);
+    }
+  };
+
+  int step = 0;
+  uint32_t rd_stage = 0, wr_stage = (TSTAGES - 1) * WSTAGE_BYTES;  // byte offsets of the stage read / refilled
+  const uint8_t *dgn = dg + 256;
+  // main loop (identity line order): the refilled step is entirely in range -> running pointers, no branches
+  if (!LINES) {
+    const int main_end = min(nsteps, full_steps - (TSTAGES - 1));
+    const uint8_t *psrc = a.P + colb + (int64_t)(l0 + (TSTAGES - 1) * TLINES + lrow) * a.stride;
+    for (; step < main_end; step++) {
+      asm volatile("cp.async.wait_group %0;" ::"n"(TSTAGES - 2) : "memory");
+      __syncwarp();
+      {
+        const uint32_t dst = wbase + wr_stage;
+        cp_async16(dst + dst_off[0], psrc, 16);
+        cp_async16(dst + dst_off[1], psrc + stride8, 16);
+        cp_async16(dst + dst_off[2], psrc + 2 * stride8, 16);
+        cp_async16(dst + dst_off[3], psrc + 3 * stride8, 16);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        psrc += 4 * stride8;
+      }
+      const uint32_t b0 = nb0, b1 = nb1;
+      nb0 = *reinterpret_cast<const uint32_t *>(dgn);  // main_end < nsteps: the next step exists
+      nb1 = *reinterpret_cast<const uint32_t *>(dgn + 16);
+      dgn += 256;
+      compute(rd_base + rd_stage, b0, b1);
+      rd_stage = rd_stage + WSTAGE_BYTES == TSTAGES * WSTAGE_BYTES ? 0 : rd_stage + WSTAGE_BYTES;
+      wr_stage = wr_stage + WSTAGE_BYTES == TSTAGES * WSTAGE_BYTES ? 0 : wr_stage + WSTAGE_BYTES;
+    }
+  }
+  for (; step < nsteps; step++) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(TSTAGES - 2) : "memory");
+    __syncwarp();
+    {
+      const int nxt = step + TSTAGES - 1;
+      if (nxt < nsteps) issue(nxt, (int)(wr_stage / WSTAGE_BYTES));
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    const uint32_t b0 = nb0, b1 = nb1;
+    if (step + 1 < nsteps) {
+      nb0 = *reinterpret_cast<const uint32_t *>(dgn);
+      nb1 = *reinterpret_cast<const uint32_t *>(dgn + 16);
+      dgn += 256;
+    }
+    compute(rd_base + rd_stage, b0, b1);
+    rd_stage = rd_stage + WSTAGE_BYTES == TSTAGES * WSTAGE_BYTES ? 0 : rd_stage + WSTAGE_BYTES;
+    wr_stage = wr_stage + WSTAGE_BYTES == TSTAGES * WSTAGE_BYTES ? 0 : wr_stage + WSTAGE_BYTES;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  // epilogue: D rows = samples (slot g / g + 8), D columns = slices 2q, 2q + 1
+#pragma unroll
+  for (int j = 0; j < 4; j++)
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+      for (int sl = 0; sl < 2; sl++) {
+        const int64_t sample = 4 * (byte0 + 4 * (8 * sl + g) + j) + c;
+        if (sample < a.n) {
+          unsigned long long *dst = reinterpret_cast<unsigned long long *>(a.part) + sample * 16 + (PLANE ? 8 : 0) + 2 * q;
+          long long v0 = acc[j][c][2 * sl], v1 = acc[j][c][2 * sl + 1];
+          v0 >>= 2 * c;
+          v1 >>= 2 * c;
+          if (v0) atomicAdd(dst, (unsigned long long)v0);
+          if (v1) atomicAdd(dst + 1, (unsigned long long)v1);
+        }
+      }
+}
+
+// digits of the quantised vector(s) in step order: dig[(t / 32) * 256 + slice * 32 + (t % 32)]
+__global__ void k_quantT(int mode, const double *__restrict__ x, const double *__restrict__ center,
+                         const double *__restrict__ scale, int len, int len_pad, const pmv::Scal *sc,
+                         uint8_t *__restrict__ dig1, uint8_t *__restrict__ dig2) {
+  const int e0 = sc->e[0], e1 = sc->e[1];
+  const bool bad = sc->nonfinite != 0;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < len_pad; t += gridDim.x * blockDim.x) {
+    long long q0 = 0, q1 = 0;
+    if (t < len && !bad) {
+      double v0, v1;
+      pmv::make_vals(mode, x, center, scale, t, v0, v1);
+      q0 = __double2ll_rn(scalbn(v0, e0));
+      if (dig2) q1 = __double2ll_rn(scalbn(v1, e1));
+    }
+    const int64_t base = (int64_t)(t >> 5) * 256 + (t & 31);
+#pragma unroll
+    for (int sl = 0; sl < 8; sl++) {
+      int d = (int)(signed char)(q0 & 0xFF);
+      q0 = (q0 - d) >> 8;
+      dig1[base + sl * 32] = (uint8_t)d;
+      if (dig2) {
+        int d2 = (int)(signed char)(q1 & 0xFF);
+        q1 = (q1 - d2) >> 8;
+        dig2[base + sl * 32] = (uint8_t)d2;
+      }
+    }
+  }
+}
+}  // namespace pmvt
+
 static int launch_cap_pub(int64_t work) { return pmv::launch_cap_pub_impl(work); }
 
 // =============================================================================================
@@ -993,6 +1232,144 @@ int bsg_view_cprodvec_dev(bsg_view *v, const double *x_dev, double *out_dev, voi
   return BSG_OK;
 }
 
+// Launcher of k_pmvT: raw plane with `dig_raw`, then (plane != 0) the flag plane (1 = missing value, 2 = high bit)
+// with `dig_plane`, both accumulating into part[n][16] (zeroed here).  Lines = the view's selected columns.
+static int run_pmvT(bsg_view *v, const uint8_t *dig_raw, int plane, const uint8_t *dig_plane, long long **part_out,
+                    cudaStream_t s) {
+  using namespace pmv;
+  using namespace pmvt;
+  bsg_bed *h = v->h;
+  const int n = h->n, nc = v->nc;
+  const int nsteps = (nc + TLINES - 1) / TLINES;
+  BSG_TRY(v->s_part.ensure((size_t)std::max(n, 1) * 16 * sizeof(long long)));
+  long long *part = v->s_part.as<long long>();
+  *part_out = part;
+  BSG_CUDA(cudaMemsetAsync(part, 0, (size_t)n * 16 * sizeof(long long), s));
+  if (nc == 0 || n == 0) return BSG_OK;
+  TArgs a;
+  a.P = h->A;
+  a.stride = h->strideA;
+  a.lines = v->d_col;
+  a.nlines = nc;
+  a.n = n;
+  a.part = part;
+  const int64_t nbytes = ((int64_t)n + 3) / 4;
+  a.nblocks = (int)((nbytes + TBYTES - 1) / TBYTES);
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
+  // items = nblocks x ksplit CTAs, 2 resident per SM: fill whole waves (4 of them) so no tail wave runs nearly empty
+  static int waves = 0;
+  if (!waves) {
+    const char *ev = getenv("BSG_PMVT_WAVES");
+    waves = ev ? std::max(1, std::min(64, atoi(ev))) : 4;
+  }
+  int ks = std::max(1, (waves * 2 * nsm) / a.nblocks);
+  ks = std::min(ks, std::max(1, nsteps / 32));                             // at least 32 steps per item
+  ks = std::max(ks, (nc + MAX_LINES_PER_ITEM - 1) / MAX_LINES_PER_ITEM);  // int32 accumulator head-room
+  a.lines_per_split = (int)round_up((nc + ks - 1) / ks, TLINES);
+  a.ksplit = (nc + a.lines_per_split - 1) / a.lines_per_split;
+  static bool attr_done = false;
+  if (!attr_done) {
+    BSG_CUDA(cudaFuncSetAttribute(k_pmvT<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TSMEM));
+    BSG_CUDA(cudaFuncSetAttribute(k_pmvT<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TSMEM));
+    BSG_CUDA(cudaFuncSetAttribute(k_pmvT<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TSMEM));
+    BSG_CUDA(cudaFuncSetAttribute(k_pmvT<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TSMEM));
+    BSG_CUDA(cudaFuncSetAttribute(k_pmvT<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TSMEM));
+    BSG_CUDA(cudaFuncSetAttribute(k_pmvT<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TSMEM));
+    attr_done = true;
+  }
+  const int grid = a.nblocks * a.ksplit, thr = TWARPS * 32;
+  const bool lines = a.lines != nullptr;
+  a.dig = dig_raw;
+  if (g_timing) cudaEventRecord(g_ev0[g_ev_n % EV_POOL], s);
+  if (lines)
+    k_pmvT<0, true><<<grid, thr, TSMEM, s>>>(a);
+  else
+    k_pmvT<0, false><<<grid, thr, TSMEM, s>>>(a);
+  if (plane) {
+    a.dig = dig_plane;
+    if (plane == 1) {
+      if (lines)
+        k_pmvT<1, true><<<grid, thr, TSMEM, s>>>(a);
+      else
+        k_pmvT<1, false><<<grid, thr, TSMEM, s>>>(a);
+    } else {
+      if (lines)
+        k_pmvT<2, true><<<grid, thr, TSMEM, s>>>(a);
+      else
+        k_pmvT<2, false><<<grid, thr, TSMEM, s>>>(a);
+    }
+  }
+  if (g_timing) {
+    cudaEventRecord(g_ev1[g_ev_n % EV_POOL], s);
+    g_ev_n++;
+  }
+  count_launch(plane ? 2 : 1);
+  BSG_CUDA(cudaGetLastError());
+  return BSG_OK;
+}
+
+// digit blocks of one or two vectors over the selected columns, in k_pmvT's step order
+static int prep_T(bsg_view *v, int mode, const double *x, const double *p1, const double *p2, bool two, cudaStream_t s) {
+  using namespace pmv;
+  using namespace pmvt;
+  Scal *sc = v->s_scal.as<Scal>();
+  const int nc = v->nc;
+  const int nsteps = (nc + TLINES - 1) / TLINES;
+  BSG_TRY(v->s_dig1.ensure((size_t)std::max(nsteps, 1) * 256));
+  if (two) BSG_TRY(v->s_dig2.ensure((size_t)std::max(nsteps, 1) * 256));
+  k_scal_reset<<<1, 1, 0, s>>>(sc);
+  k_maxabs<<<launch_cap(nc, 256, 592), 256, 0, s>>>(mode, x, p1, p2, nc, sc);
+  k_pick_exp<<<1, 1, 0, s>>>(sc, 0);
+  k_quantT<<<launch_cap((int64_t)std::max(nsteps, 1) * TLINES, 256, 1184), 256, 0, s>>>(
+      mode, x, p1, p2, nc, nsteps * TLINES, sc, v->s_dig1.as<uint8_t>(), two ? v->s_dig2.as<uint8_t>() : nullptr);
+  count_launch(4);
+  return BSG_OK;
+}
+
+// X~ x from the SNP-major copy alone (k_pmvT): lines = selected SNP columns in selection order (duplicates are
+// just repeated lines), all n samples are produced and the requested rows gathered at the end.
+static int prodvec_T(bsg_view *v, const double *x_dev, double *out_dev, cudaStream_t s) {
+  using namespace pmv;
+  bsg_bed *h = v->h;
+  Scal *sc = v->s_scal.as<Scal>();
+  const int n = h->n, nc = v->nc;
+  const int mode = v->has_scaling ? 1 : 0;
+  const bool two = v->has_scaling && h->has_na;
+  BSG_TRY(prep_T(v, mode, x_dev, v->d_center, v->d_scale, two, s));
+  if (v->has_scaling) {
+    k_sum_cz<<<SUMCZ_BLOCKS, 256, 0, s>>>(x_dev, v->d_center, v->d_scale, nc, sc->cpart);
+    count_launch();
+  }
+  long long *part = nullptr;
+  BSG_TRY(run_pmvT(v, v->s_dig1.as<uint8_t>(), h->has_na ? 1 : 0, two ? v->s_dig2.as<uint8_t>() : v->s_dig1.as<uint8_t>(),
+                   &part, s));
+  double *full = out_dev;
+  if (!v->row_identity) {
+    BSG_TRY(v->s_full.ensure((size_t)n * sizeof(double)));
+    full = v->s_full.as<double>();
+  }
+  if (n > 0) {
+    k_finish_prod<<<(n + 255) / 256, 256, 0, s>>>(part, 1, n, n, sc, v->has_scaling, h->has_na, full);
+    count_launch();
+  }
+  if (!v->row_identity && v->nr > 0) {
+    k_gather<<<(v->nr + 255) / 256, 256, 0, s>>>(full, v->d_row, v->nr, out_dev);
+    count_launch();
+  }
+  BSG_CUDA(cudaGetLastError());
+  return BSG_OK;
+}
+
+static int g_force_t = -1;  // 1: X-side products use the SNP-major kernel even when the sample-major copy is resident
+static bool use_T(const bsg_bed *h) {
+  if (g_force_t < 0) {
+    const char *ev = getenv("BSG_PMVT");
+    g_force_t = (ev && ev[0] == '1') ? 1 : 0;
+  }
+  return !h->B || g_force_t == 1;
+}
+
 // X~ x : lines = samples of copy B, contraction over SNP columns
 int bsg_view_prodvec_dev(bsg_view *v, const double *x_dev, double *out_dev, void *stream) {
   if (!v || !x_dev || !out_dev) return fail(BSG_ERR_ARG, "null argument");
@@ -1000,10 +1377,7 @@ int bsg_view_prodvec_dev(bsg_view *v, const double *x_dev, double *out_dev, void
   BSG_TRY(bind_device(h));
   cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
   if (v->nr == 0) return BSG_OK;
-  if (!h->B) {
-    // no sample-major copy resident: generic accessor kernel over copy A
-    return simple_prodvec(h, v->d_row, v->nr, v->d_col, v->nc, v->d_center, v->d_scale, x_dev, out_dev, s);
-  }
+  if (use_T(h)) return prodvec_T(v, x_dev, out_dev, s);  // transposing kernel over the SNP-major copy
   using namespace pmv;
   Scal *sc = v->s_scal.as<Scal>();
   const int m = h->m;
@@ -1072,8 +1446,7 @@ static int view_host_call(bsg_view *v, const double *x, double *out, bool cprod)
   BSG_CUDA(cudaMemcpyAsync(dx, x, (size_t)nin * sizeof(double), cudaMemcpyHostToDevice, s));
   BSG_TRY(cprod ? bsg_view_cprodvec_dev(v, dx, dout, s) : bsg_view_prodvec_dev(v, dx, dout, s));
   int bad = 0;
-  const bool fast = cprod || h->B != nullptr;
-  if (fast && nout > 0)
+  if (nout > 0)  // every product path (copy A or copy B) raises the flag on non-finite input
     BSG_CUDA(cudaMemcpyAsync(&bad, &v->s_scal.as<pmv::Scal>()->nonfinite, sizeof(int), cudaMemcpyDeviceToHost, s));
   BSG_CUDA(cudaMemcpyAsync(out, dout, (size_t)nout * sizeof(double), cudaMemcpyDeviceToHost, s));
   BSG_CUDA(cudaStreamSynchronize(s));
@@ -1164,11 +1537,35 @@ static int view_planes_dev(bsg_view *v, int dir, const double *x1, const double 
                            cudaStream_t s) {
   using namespace pmv;
   bsg_bed *h = v->h;
-  if (dir == 0 && !h->B) return fail(BSG_ERR_ARG, "planes over samples need the sample-major copy");
   if (plane == PLANE_NA && !h->has_na) plane = PLANE_NONE;
   const bool same = plane == PLANE_NA && x2 == x1;          // one digit block serves both planes
   const bool two = plane != PLANE_NONE && !same;
   Scal *sc = v->s_scal.as<Scal>();
+  if (dir == 0 && use_T(h)) {
+    // X-side sums from the SNP-major copy: raw-plane launch + flag-plane launch of k_pmvT
+    BSG_TRY(prep_T(v, two ? 2 : 0, x1, x2, nullptr, two, s));
+    long long *part = nullptr;
+    BSG_TRY(run_pmvT(v, v->s_dig1.as<uint8_t>(), plane == PLANE_NONE ? 0 : (plane == PLANE_NA ? 1 : 2),
+                     two ? v->s_dig2.as<uint8_t>() : v->s_dig1.as<uint8_t>(), &part, s));
+    const int n = h->n;
+    const bool gather = !v->row_identity;
+    double *full = o.out, *fullB = o.outB;
+    if (gather) {
+      BSG_TRY(v->s_full.ensure((size_t)n * 2 * sizeof(double)));
+      full = v->s_full.as<double>();
+      fullB = o.outB ? full + n : nullptr;
+    }
+    k_finish_planes<<<(n + 255) / 256, 256, 0, s>>>(part, n, sc, plane != PLANE_NONE, same ? 1 : 0, o.cR, o.cP, o.add0, full,
+                                                    o.cRb, o.cPb, fullB);
+    count_launch();
+    if (gather && v->nr > 0) {
+      k_gather<<<(v->nr + 255) / 256, 256, 0, s>>>(full, v->d_row, v->nr, o.out);
+      if (o.outB) k_gather<<<(v->nr + 255) / 256, 256, 0, s>>>(fullB, v->d_row, v->nr, o.outB);
+      count_launch(o.outB ? 2 : 1);
+    }
+    BSG_CUDA(cudaGetLastError());
+    return BSG_OK;
+  }
   const int L = dir == 0 ? h->m : h->n;                      // contraction length in the staged copy
   const int len = dir == 0 ? v->nc : v->nr;                  // vector length (selection order)
   const int *idx = dir == 0 ? v->d_col : v->d_row;
@@ -1348,13 +1745,11 @@ int bsg_prod_and_rowsumssq(bsg_bed *h, const int *ind_row, int nr, const int *in
   BSG_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), s));
   for (int k = 0; k < K; k++) {
     BSG_TRY(bsg_view_prodvec_dev(v, dV + (size_t)k * nc, dXV + (size_t)k * nr, s));
-    if (h->B) {
-      k_or_flag<<<1, 1, 0, s>>>(v->s_scal.as<pmv::Scal>(), d_bad);
-      count_launch();
-    }
+    k_or_flag<<<1, 1, 0, s>>>(v->s_scal.as<pmv::Scal>(), d_bad);
+    count_launch();
   }
-  bool need_simple = !h->B;
-  if (h->B) {
+  bool need_simple = false;
+  {
     double *d_a = d_cols, *d_w = d_cols + nc, *d_n = d_cols + 2 * (size_t)nc, *d_tp = d_cols + 3 * (size_t)nc;
     double *d_t1 = d_rows + nr, *d_t2 = nullptr;
     k_rss_weights<<<NP, 256, 0, s>>>(v->d_center, v->d_scale, nc, d_a, d_w, d_n, d_tp);
@@ -1444,6 +1839,14 @@ int bsg_multlinreg(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, i
   BSG_CUDA(cudaGetLastError());
   BSG_CUDA(cudaMemcpyAsync(tscores, dOut, (size_t)nc * K * sizeof(double), cudaMemcpyDeviceToHost, s));
   BSG_CUDA(cudaStreamSynchronize(s));
+  return BSG_OK;
+}
+
+// 0: automatic (sample-major kernel when that copy is resident, else the SNP-major kernel); 1: always the
+// SNP-major kernel (k_pmvT) for the X-side products.  Process-wide; for tests and measurements.
+int bsg_set_prodvec_path(int path) {
+  if (path != 0 && path != 1) return fail(BSG_ERR_ARG, "path must be 0 or 1");
+  g_force_t = path;
   return BSG_OK;
 }
 

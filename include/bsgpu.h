@@ -133,6 +133,12 @@ int bsg_clumping_chr(bsg_bed *h, const int *ind_row, int nr, const int *ind_col,
                      const double *scale, const int *ordInd, const double *pos, double size, double thr,
                      int *keep);
 
+/* Which kernel serves the X-side products (bsg_prodvec, bsg_view_prodvec*, XV and row sums of squares):
+ * 0 = automatic -- the sample-major kernel when that copy is resident, else the SNP-major kernel (k_pmvT), which
+ * needs only the copy every handle has; 1 = always the SNP-major kernel.  Process-wide; no reference twin
+ * (bed_prodVec has one code path, src/bed-prod-vec.cpp:15-54). */
+int bsg_set_prodvec_path(int path);
+
 /* ---- PCA projection / pcadapt ------------------------------------------- */
 /* _bigsnpr_prod_and_rowSumsSq: src/bed-fun.cpp:103-133 (R: part_prod, R/bed-projectPCA.R:31-58).
  * V is nc x K column-major; XV (nr x K column-major) = X~ V and rowSumsSq[nr] = sum_j X~_ij^2 with the

@@ -161,17 +161,55 @@ def test_prodvec_multiset_indices(B, gbed, gbed_na, oracle, obed, obed_na, rng):
                scale=np.max(np.abs(y_row)) * ir.size / np.min(s))
 
 
-def test_fast_and_accessor_paths_agree(B, oracle, obed_na, rng):
-    """Tensor-pipe path (both layouts resident) vs accessor kernel (SNP-major only) on the same handle data."""
-    f = os.path.join(GOLDEN, "example-missing.bed")
-    g_fast = B.Bed(f, layouts=B.LAYOUT_SNP_MAJOR | B.LAYOUT_SAMPLE_MAJOR)
-    g_slow = B.Bed(f, layouts=B.LAYOUT_SNP_MAJOR)
-    assert g_fast.layouts == 3 and g_slow.layouts == 1
-    c, s = rng.normal(size=500), rng.uniform(0.2, 1.5, size=500)
-    y = rng.normal(size=500)
-    a, b = B.bed_prodVec(g_fast, y, center=c, scale=s), B.bed_prodVec(g_slow, y, center=c, scale=s)
-    _close(a, b, scale=np.max(np.abs(y / s)) * 500)
-    _close(a, oracle.bed_prodVec(obed_na, y, center=c, scale=s), scale=np.max(np.abs(y / s)) * 500)
+def test_single_copy_kernel_matches_oracle(B, oracle, obed, obed_na, rng):
+    """X.y from the SNP-major copy alone (k_pmvT, handles opened without the sample-major copy) against the oracle
+    and against the two-copy path: subsets, multisets, scaling, missing values, non-finite input, projections."""
+    for name, o in (("example-missing.bed", obed_na), ("example.bed", obed)):
+        f = os.path.join(GOLDEN, name)
+        g2 = B.Bed(f, layouts=B.LAYOUT_SNP_MAJOR | B.LAYOUT_SAMPLE_MAJOR)
+        g1 = B.Bed(f, layouts=B.LAYOUT_SNP_MAJOR)
+        assert g2.layouts == 3 and g1.layouts == 1
+        N, M = o.nrow, o.ncol
+        cases = [(np.arange(1, N + 1), np.arange(1, M + 1)),
+                 (rng.choice(N, N // 3, replace=False) + 1, rng.choice(M, M // 2, replace=False) + 1),
+                 (rng.integers(1, N + 1, N), rng.integers(1, M + 1, min(M, 1500))),
+                 (np.array([N]), np.array([M, 1, M]))]
+        for ir, ic in cases:
+            m = ic.size
+            y = rng.normal(size=m)
+            c, s = rng.normal(size=m), rng.uniform(0.2, 1.5, size=m)
+            for cs in ((None, None), (c, s)):
+                a = B.bed_prodVec(g1, y, ir, ic, *cs)
+                b = B.bed_prodVec(g2, y, ir, ic, *cs)
+                want = oracle.bed_prodVec(o, y, ir, ic, *cs)
+                sc = np.max(np.abs(y / (s if cs[0] is not None else 1.0))) * m * 3
+                _close(a, want, scale=sc)
+                _close(a, b, scale=sc, tol=1e-13)
+        sc = oracle.bed_scaleBinom(o)
+        ir, ic = np.arange(1, N + 1), np.arange(1, M + 1)
+        V = rng.normal(size=(M, 3))
+        XV, rss = B.prod_and_rowSumsSq(g1, ir, ic, sc["center"], sc["scale"], V)
+        XVo, rsso = oracle.prod_and_rowSumsSq(o, ir, ic, sc["center"], sc["scale"], V)
+        _close(XV, XVo, tol=1e-11)
+        _close(rss, rsso, tol=1e-12)
+        y = rng.normal(size=M)
+        y[5] = np.nan
+        with np.errstate(all="ignore"):
+            a, want = B.bed_prodVec(g1, y), oracle.bed_prodVec(o, y)
+        assert np.array_equal(np.isnan(a), np.isnan(want))
+        svd1, svd2 = B.bed_randomSVD(g1, k=4), B.bed_randomSVD(g2, k=4)
+        np.testing.assert_allclose(svd1["d"], svd2["d"], rtol=1e-9)
+    # the same handle through both kernels (process-wide switch of the C ABI)
+    g = B.Bed.synthetic(3000, 7001, seed=11, na_rate=0.02)
+    y = rng.normal(size=7001)
+    sc = B.bed_scaleBinom(g)
+    a = B.bed_prodVec(g, y, center=sc["center"], scale=sc["scale"])
+    B._lib.check(B._lib.lib().bsg_set_prodvec_path(1))
+    try:
+        b = B.bed_prodVec(g, y, center=sc["center"], scale=sc["scale"])
+    finally:
+        B._lib.check(B._lib.lib().bsg_set_prodvec_path(0))
+    _close(a, b, scale=np.max(np.abs(y / sc["scale"])) * 7001, tol=1e-13)
 
 
 def test_nonfinite_inputs_follow_reference(B, gbed_na, oracle, obed_na, rng):
