@@ -163,8 +163,9 @@ def main():
     ap.add_argument("--na-rate", type=float, default=0.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-svd", action="store_true", help="skip the bed_randomSVD wall-time leg")
-    ap.add_argument("--layout", choices=("auto", "snp"), default="auto",
-                    help="snp: stage the SNP-major copy only (X.y runs on the transposing kernel k_pmvT)")
+    ap.add_argument("--layout", choices=("both", "snp"), default="both",
+                    help="both (default): SNP-major + sample-major copies, X.y on k_pmv; snp: the SNP-major copy only "
+                         "(the library's own default), X.y on the transposing kernel k_pmvT")
     ap.add_argument("--no-single-copy", action="store_true", help="skip the extra leg timing X.y on the SNP-major copy alone")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
@@ -201,7 +202,7 @@ def main():
         col0 = rank * per
         m_loc = max(0, min(wl["m"], col0 + per) - col0)
     g = B.Bed.synthetic(n, m_loc, seed=SEED, na_rate=args.na_rate, col_offset=col0, device=local,
-                        layouts=B.LAYOUT_SNP_MAJOR if args.layout == "snp" else B.LAYOUT_AUTO)
+                        layouts=B.LAYOUT_SNP_MAJOR if args.layout == "snp" else (B.LAYOUT_SNP_MAJOR | B.LAYOUT_SAMPLE_MAJOR))
     layouts = g.layouts
     sc = B.bed_scaleBinom(g)
     view = B.View(g, center=sc["center"], scale=sc["scale"])

@@ -294,33 +294,39 @@ int stage_finish(bsg_bed *h) {
   BSG_CUDA(cudaStreamSynchronize(s));
   cudaFree(d_any);
 
+  // Layout policy: the SNP-major copy serves every kernel at full speed (X.y included, k_pmvT), so AUTO stages it
+  // alone -- half the HBM footprint, no transpose at open.  The sample-major copy is built when asked for
+  // (BSG_LAYOUT_SAMPLE_MAJOR) or on first use by the GRM tiles (build_copy_B).
   int want = h->layouts;
-  size_t needB = (size_t)h->strideB * h->n + (size_t)h->n * 20;
-  if (want == BSG_LAYOUT_AUTO) {
-    size_t fr = 0, tot = 0;
-    BSG_CUDA(cudaMemGetInfo(&fr, &tot));
-    // keep 6 GB + 5% headroom for vectors, partials, correlation bands, torch, NCCL
-    size_t reserve = (size_t)6e9 + tot / 20;
-    want = BSG_LAYOUT_SNP_MAJOR | ((fr > needB + reserve) ? BSG_LAYOUT_SAMPLE_MAJOR : 0);
-  }
+  if (want == BSG_LAYOUT_AUTO) want = BSG_LAYOUT_SNP_MAJOR;
   want |= BSG_LAYOUT_SNP_MAJOR;
-  if (want & BSG_LAYOUT_SAMPLE_MAJOR) {
-    cudaError_t e = cudaMalloc(&h->B, (size_t)h->strideB * h->n);
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      return fail(BSG_ERR_ALLOC, "cannot allocate %.2f GB for the sample-major copy (%s).",
-                  (double)h->strideB * h->n / 1e9, cudaGetErrorString(e));
-    }
-    BSG_CUDA(cudaMemsetAsync(h->B, 0, (size_t)h->strideB * h->n, s));
-    dim3 grid((unsigned)((h->m + 127) / 128), (unsigned)((h->strideA + 127) / 128));
-    k_transpose<<<grid, 512, 0, s>>>(h->A, h->strideA, h->n, h->m, h->B, h->strideB);
-    count_launch();
-    BSG_CUDA(cudaMalloc(&h->cntB, (size_t)h->n * 4 * sizeof(int32_t)));
-    BSG_CUDA(cudaMalloc(&h->naB, (size_t)h->n));
-    k_line_counts<<<grid_for((int64_t)h->n * 32, 256), 256, 0, s>>>(h->B, h->strideB, h->n, h->m, h->cntB, h->naB);
-    count_launch();
+  h->layouts = BSG_LAYOUT_SNP_MAJOR;
+  if (want & BSG_LAYOUT_SAMPLE_MAJOR) BSG_TRY(build_copy_B(h));
+  BSG_CUDA(cudaStreamSynchronize(s));
+  BSG_CUDA(cudaGetLastError());
+  return BSG_OK;
+}
+
+// the 2-bit transpose (line i = sample i) with its per-line counts and missing-value flags
+int build_copy_B(bsg_bed *h) {
+  if (h->B) return BSG_OK;
+  cudaStream_t s = h->stream;
+  cudaError_t e = cudaMalloc(&h->B, (size_t)h->strideB * h->n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    h->B = nullptr;
+    return fail(BSG_ERR_ALLOC, "cannot allocate %.2f GB for the sample-major copy (%s).", (double)h->strideB * h->n / 1e9,
+                cudaGetErrorString(e));
   }
-  h->layouts = want;
+  BSG_CUDA(cudaMemsetAsync(h->B, 0, (size_t)h->strideB * h->n, s));
+  dim3 grid((unsigned)((h->m + 127) / 128), (unsigned)((h->strideA + 127) / 128));
+  k_transpose<<<grid, 512, 0, s>>>(h->A, h->strideA, h->n, h->m, h->B, h->strideB);
+  count_launch();
+  BSG_CUDA(cudaMalloc(&h->cntB, (size_t)h->n * 4 * sizeof(int32_t)));
+  BSG_CUDA(cudaMalloc(&h->naB, (size_t)h->n));
+  k_line_counts<<<grid_for((int64_t)h->n * 32, 256), 256, 0, s>>>(h->B, h->strideB, h->n, h->m, h->cntB, h->naB);
+  count_launch();
+  h->layouts |= BSG_LAYOUT_SAMPLE_MAJOR;
   BSG_CUDA(cudaStreamSynchronize(s));
   BSG_CUDA(cudaGetLastError());
   return BSG_OK;

@@ -82,7 +82,8 @@ struct bsg_bed {
 namespace bsg {
 
 // ---- bsg_core.cu -----------------------------------------------------------------------------
-int stage_finish(bsg_bed *h);  // builds copy B (if requested), counts and NA flags from copy A
+int stage_finish(bsg_bed *h);  // counts and NA flags from copy A; copy B only when requested
+int build_copy_B(bsg_bed *h);  // sample-major copy on demand (no-op when resident)
 int bind_device(const bsg_bed *h);
 
 // ---- index helpers (bsg_core.cu) -------------------------------------------------------------
@@ -100,6 +101,9 @@ int counts_rows(bsg_bed *h, const int *d_row, int nr, const int *d_col, int nc, 
 int read_dense(bsg_bed *h, const int *d_row, int nr, const int *d_col, int nc, int na_val, int *d_out, cudaStream_t s);
 int read_dense_scaled(bsg_bed *h, const int *d_row, int nr, const int *d_col, int nc, const double *d_center,
                       const double *d_scale, double *d_out, cudaStream_t s);
+
+// ---- bsg_pmv.cu: 4 x nr code counts per sample from the plane sums of the X-side kernels (device array)
+int row_counts_planes(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, int32_t *d_out4);
 
 // ---- bsg_stats.cu: 4 x nc code counts of (ind_row, ind_col) on the device (h->w_tmp0), on h->stream
 int col_counts_dev(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, int32_t **d_out);

@@ -723,6 +723,7 @@ static int tcrossprod_impl(bsg_bed *h, const int *ind_row, int nr, const int *in
     const char *es = getenv("BSG_GRM_SLICES");
     if (es) nslices = std::min(9, std::max(2, atoi(es)));
   }
+  if (!force_dsyrk && !h->B && nr > 0 && nc > 0 && build_copy_B(h) != BSG_OK) cudaGetLastError();  // no room: fp64 path
   if (force_dsyrk || !h->B || nr == 0 || nc == 0) return tcrossprod_dsyrk(h, ind_row, nr, ind_col, nc, center, scale, K, K_dev);
   using namespace wgram;
   cudaStream_t s = h->stream;

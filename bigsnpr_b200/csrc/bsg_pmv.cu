@@ -841,7 +841,7 @@ static int run_pmv(bsg_view *v, const uint8_t *P, int64_t stride, int L, const i
 // enters as 4^c x code, removed by an exact shift in the epilogue).  B = the 8 signed base-256 digits
 // of the quantised vector, 32 lines per step, laid out [step][slice][32] so a B register is one aligned word.
 // Per warp and step: 16 IMMAs over 32 lines x 64 bytes; accumulators: 4 (byte) x 4 (field) x 4 registers.
-// Missing values: a second launch with the flag plane (PLANE 1) and the matching digit block.
+// Missing values / the high-bit plane: k_pmvT2 below does the raw and the flag plane in one pass.
 // =============================================================================================
 namespace pmvt {
 using namespace pmv;
@@ -1035,6 +1035,167 @@ __global__ void __launch_bounds__(TWARPS * 32, 2) k_pmvT(const TArgs a) {
           if (v1) atomicAdd(dst + 1, (unsigned long long)v1);
         }
       }
+}
+
+// Two planes in one pass: the raw codes against `dig` and a flag plane (PL 1 = missing value, 2 = high bit)
+// against `dig2`.  Same scheme as k_pmvT with 32-byte strips per warp, so the two accumulator sets (2 x 32
+// registers) fit: rows g / g + 8 of an IMMA are bytes u and u + 2 of the lane's word column.
+constexpr int W2STAGE_BYTES = TLINES * 32;                 // 1 KB per warp and stage
+constexpr int T2BYTES = TWARPS * 32;                       // sample-bytes of a line per CTA
+constexpr int T2SMEM = TWARPS * TSTAGES * W2STAGE_BYTES;   // 48 KB
+
+template <int PL, bool LINES>
+__global__ void __launch_bounds__(TWARPS * 32, 2) k_pmvT2(const TArgs a, const uint8_t *__restrict__ dig2) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+  const int blk = blockIdx.x % a.nblocks, ks = blockIdx.x / a.nblocks;
+  const int64_t byte0 = (int64_t)blk * T2BYTES + 32 * warp;
+  const int l0 = ks * a.lines_per_split, l1 = min(a.nlines, l0 + a.lines_per_split);
+  const int nsteps = (l1 - l0 + TLINES - 1) / TLINES;
+  const uint32_t wbase = smem_u32(smem) + warp * (TSTAGES * W2STAGE_BYTES);
+  // loader role: rows 16 i + (lane >> 1), granule lane & 1; stage layout: word (row = 16 hf + 4 qq + r, column gg)
+  // at word offset (((r 2 + hf) 4 + qq) 8 + gg)
+  const int lrow = lane >> 1, lch = lane & 1;
+  const int64_t colb = (byte0 + 16 * lch < a.stride) ? byte0 + 16 * lch : 0;
+  uint32_t dst_off[2];
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    const int row = 16 * i + lrow;
+    const int hf = row >> 4, qq = (row >> 2) & 3, r = row & 3;
+    dst_off[i] = (uint32_t)(((((r * 2 + hf) * 4 + qq) * 8) + 4 * lch) * 4);
+  }
+  const int full_steps = (l1 - l0) / TLINES;
+  const int64_t stride16 = 16 * a.stride;
+  auto issue = [&](int step, int stage) {
+    const uint32_t dst = wbase + stage * W2STAGE_BYTES;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      const int t = min(l0 + step * TLINES + 16 * i + lrow, l1 - 1);
+      const int phys = LINES ? a.lines[t] : t;
+      cp_async16(dst + dst_off[i], a.P + colb + (int64_t)phys * a.stride, 16);
+    }
+  };
+  int acc[2][2][4][4];  // [plane][unit][field][fragment]
+#pragma unroll
+  for (int p = 0; p < 2; p++)
+#pragma unroll
+    for (int u = 0; u < 2; u++)
+#pragma unroll
+      for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) acc[p][u][c][k] = 0;
+#pragma unroll
+  for (int st = 0; st < TSTAGES - 1; st++) {
+    if (st < nsteps) issue(st, st);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  const int64_t doff = (int64_t)(l0 / TLINES) * 256 + g * 32 + 4 * q;
+  const uint8_t *dg = a.dig + doff, *dp = dig2 + doff;
+  uint32_t nb0 = 0, nb1 = 0, np0 = 0, np1 = 0;
+  if (nsteps > 0) {
+    nb0 = *reinterpret_cast<const uint32_t *>(dg);
+    nb1 = *reinterpret_cast<const uint32_t *>(dg + 16);
+    np0 = *reinterpret_cast<const uint32_t *>(dp);
+    np1 = *reinterpret_cast<const uint32_t *>(dp + 16);
+  }
+  const uint32_t rd_base = wbase + (uint32_t)((q * 8 + g) * 4);
+
+  auto compute = [&](uint32_t st_base, uint32_t b0, uint32_t b1, uint32_t p0, uint32_t p1) {
+    uint32_t W[2][4];  // [lines lo / hi][byte]
+#pragma unroll
+    for (int hf = 0; hf < 2; hf++) {
+      const uint32_t ad = st_base + hf * 128;
+      const uint32_t x0 = lds32(ad), x1 = lds32(ad + 256), x2 = lds32(ad + 512), x3 = lds32(ad + 768);
+      const uint32_t t0 = prmt(x0, x1, 0x5140), t1 = prmt(x2, x3, 0x5140);
+      const uint32_t t2 = prmt(x0, x1, 0x7362), t3 = prmt(x2, x3, 0x7362);
+      W[hf][0] = prmt(t0, t1, 0x5410);
+      W[hf][1] = prmt(t0, t1, 0x7632);
+      W[hf][2] = prmt(t2, t3, 0x5410);
+      W[hf][3] = prmt(t2, t3, 0x7632);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const uint32_t wa = W[0][u], wb = W[0][u + 2], wc2 = W[1][u], wd = W[1][u + 2];
+      mma_u8s8(acc[0][u][0], wa & 0x03030303u, wb & 0x03030303u, wc2 & 0x03030303u, wd & 0x03030303u, b0, b1);
+      mma_u8s8(acc[0][u][1], wa & 0x0C0C0C0Cu, wb & 0x0C0C0C0Cu, wc2 & 0x0C0C0C0Cu, wd & 0x0C0C0C0Cu, b0, b1);
+      mma_u8s8(acc[0][u][2], wa & 0x30303030u, wb & 0x30303030u, wc2 & 0x30303030u, wd & 0x30303030u, b0, b1);
+      mma_u8s8(acc[0][u][3], wa & 0xC0C0C0C0u, wb & 0xC0C0C0C0u, wc2 & 0xC0C0C0C0u, wd & 0xC0C0C0C0u, b0, b1);
+      // flag plane: one bit per field at the field's low bit
+      const uint32_t fa = PL == 1 ? (wa & (wa >> 1)) : (wa >> 1), fb = PL == 1 ? (wb & (wb >> 1)) : (wb >> 1);
+      const uint32_t fc = PL == 1 ? (wc2 & (wc2 >> 1)) : (wc2 >> 1), fd = PL == 1 ? (wd & (wd >> 1)) : (wd >> 1);
+      mma_u8s8(acc[1][u][0], fa & 0x01010101u, fb & 0x01010101u, fc & 0x01010101u, fd & 0x01010101u, p0, p1);
+      mma_u8s8(acc[1][u][1], fa & 0x04040404u, fb & 0x04040404u, fc & 0x04040404u, fd & 0x04040404u, p0, p1);
+      mma_u8s8(acc[1][u][2], fa & 0x10101010u, fb & 0x10101010u, fc & 0x10101010u, fd & 0x10101010u, p0, p1);
+      mma_u8s8(acc[1][u][3], fa & 0x40404040u, fb & 0x40404040u, fc & 0x40404040u, fd & 0x40404040u, p0, p1);
+    }
+  };
+
+  int step = 0;
+  uint32_t rd_stage = 0, wr_stage = (TSTAGES - 1) * W2STAGE_BYTES;
+  int64_t dnext = 256;
+  if (!LINES) {
+    const int main_end = min(nsteps, full_steps - (TSTAGES - 1));
+    const uint8_t *psrc = a.P + colb + (int64_t)(l0 + (TSTAGES - 1) * TLINES + lrow) * a.stride;
+    for (; step < main_end; step++) {
+      asm volatile("cp.async.wait_group %0;" ::"n"(TSTAGES - 2) : "memory");
+      __syncwarp();
+      {
+        const uint32_t dst = wbase + wr_stage;
+        cp_async16(dst + dst_off[0], psrc, 16);
+        cp_async16(dst + dst_off[1], psrc + stride16, 16);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        psrc += 2 * stride16;
+      }
+      const uint32_t b0 = nb0, b1 = nb1, p0 = np0, p1 = np1;
+      nb0 = *reinterpret_cast<const uint32_t *>(dg + dnext);
+      nb1 = *reinterpret_cast<const uint32_t *>(dg + dnext + 16);
+      np0 = *reinterpret_cast<const uint32_t *>(dp + dnext);
+      np1 = *reinterpret_cast<const uint32_t *>(dp + dnext + 16);
+      dnext += 256;
+      compute(rd_base + rd_stage, b0, b1, p0, p1);
+      rd_stage = rd_stage + W2STAGE_BYTES == TSTAGES * W2STAGE_BYTES ? 0 : rd_stage + W2STAGE_BYTES;
+      wr_stage = wr_stage + W2STAGE_BYTES == TSTAGES * W2STAGE_BYTES ? 0 : wr_stage + W2STAGE_BYTES;
+    }
+  }
+  for (; step < nsteps; step++) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(TSTAGES - 2) : "memory");
+    __syncwarp();
+    {
+      const int nxt = step + TSTAGES - 1;
+      if (nxt < nsteps) issue(nxt, (int)(wr_stage / W2STAGE_BYTES));
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    const uint32_t b0 = nb0, b1 = nb1, p0 = np0, p1 = np1;
+    if (step + 1 < nsteps) {
+      nb0 = *reinterpret_cast<const uint32_t *>(dg + dnext);
+      nb1 = *reinterpret_cast<const uint32_t *>(dg + dnext + 16);
+      np0 = *reinterpret_cast<const uint32_t *>(dp + dnext);
+      np1 = *reinterpret_cast<const uint32_t *>(dp + dnext + 16);
+      dnext += 256;
+    }
+    compute(rd_base + rd_stage, b0, b1, p0, p1);
+    rd_stage = rd_stage + W2STAGE_BYTES == TSTAGES * W2STAGE_BYTES ? 0 : rd_stage + W2STAGE_BYTES;
+    wr_stage = wr_stage + W2STAGE_BYTES == TSTAGES * W2STAGE_BYTES ? 0 : wr_stage + W2STAGE_BYTES;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+  for (int p = 0; p < 2; p++)
+#pragma unroll
+    for (int u = 0; u < 2; u++)
+#pragma unroll
+      for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int sl = 0; sl < 2; sl++) {
+          const int64_t sample = 4 * (byte0 + 4 * g + u + 2 * sl) + c;
+          if (sample < a.n) {
+            unsigned long long *dst = reinterpret_cast<unsigned long long *>(a.part) + sample * 16 + 8 * p + 2 * q;
+            long long v0 = acc[p][u][c][2 * sl], v1 = acc[p][u][c][2 * sl + 1];
+            v0 >>= 2 * c;
+            v1 >>= 2 * c;
+            if (v0) atomicAdd(dst, (unsigned long long)v0);
+            if (v1) atomicAdd(dst + 1, (unsigned long long)v1);
+          }
+        }
 }
 
 // digits of the quantised vector(s) in step order: dig[(t / 32) * 256 + slice * 32 + (t % 32)]
@@ -1271,40 +1432,49 @@ static int run_pmvT(bsg_view *v, const uint8_t *dig_raw, int plane, const uint8_
   static bool attr_done = false;
   if (!attr_done) {
     BSG_CUDA(cudaFuncSetAttribute(k_pmvT<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TSMEM));
-    BSG_CUDA(cudaFuncSetAttribute(k_pmvT<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TSMEM));
-    BSG_CUDA(cudaFuncSetAttribute(k_pmvT<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TSMEM));
     BSG_CUDA(cudaFuncSetAttribute(k_pmvT<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TSMEM));
-    BSG_CUDA(cudaFuncSetAttribute(k_pmvT<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TSMEM));
-    BSG_CUDA(cudaFuncSetAttribute(k_pmvT<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TSMEM));
+    BSG_CUDA(cudaFuncSetAttribute(k_pmvT2<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2SMEM));
+    BSG_CUDA(cudaFuncSetAttribute(k_pmvT2<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2SMEM));
+    BSG_CUDA(cudaFuncSetAttribute(k_pmvT2<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2SMEM));
+    BSG_CUDA(cudaFuncSetAttribute(k_pmvT2<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2SMEM));
     attr_done = true;
   }
-  const int grid = a.nblocks * a.ksplit, thr = TWARPS * 32;
+  const int thr = TWARPS * 32;
   const bool lines = a.lines != nullptr;
   a.dig = dig_raw;
   if (g_timing) cudaEventRecord(g_ev0[g_ev_n % EV_POOL], s);
-  if (lines)
-    k_pmvT<0, true><<<grid, thr, TSMEM, s>>>(a);
-  else
-    k_pmvT<0, false><<<grid, thr, TSMEM, s>>>(a);
-  if (plane) {
-    a.dig = dig_plane;
+  if (!plane) {
+    const int grid = a.nblocks * a.ksplit;
+    if (lines)
+      k_pmvT<0, true><<<grid, thr, TSMEM, s>>>(a);
+    else
+      k_pmvT<0, false><<<grid, thr, TSMEM, s>>>(a);
+  } else {
+    // both planes in one pass: 32-byte strips per warp, twice the sample blocks
+    a.nblocks = (int)((nbytes + T2BYTES - 1) / T2BYTES);
+    int ks2 = std::max(1, (waves * 2 * nsm) / a.nblocks);
+    ks2 = std::min(ks2, std::max(1, nsteps / 32));
+    ks2 = std::max(ks2, (nc + MAX_LINES_PER_ITEM - 1) / MAX_LINES_PER_ITEM);
+    a.lines_per_split = (int)round_up((nc + ks2 - 1) / ks2, TLINES);
+    a.ksplit = (nc + a.lines_per_split - 1) / a.lines_per_split;
+    const int grid = a.nblocks * a.ksplit;
     if (plane == 1) {
       if (lines)
-        k_pmvT<1, true><<<grid, thr, TSMEM, s>>>(a);
+        k_pmvT2<1, true><<<grid, thr, T2SMEM, s>>>(a, dig_plane);
       else
-        k_pmvT<1, false><<<grid, thr, TSMEM, s>>>(a);
+        k_pmvT2<1, false><<<grid, thr, T2SMEM, s>>>(a, dig_plane);
     } else {
       if (lines)
-        k_pmvT<2, true><<<grid, thr, TSMEM, s>>>(a);
+        k_pmvT2<2, true><<<grid, thr, T2SMEM, s>>>(a, dig_plane);
       else
-        k_pmvT<2, false><<<grid, thr, TSMEM, s>>>(a);
+        k_pmvT2<2, false><<<grid, thr, T2SMEM, s>>>(a, dig_plane);
     }
   }
   if (g_timing) {
     cudaEventRecord(g_ev1[g_ev_n % EV_POOL], s);
     g_ev_n++;
   }
-  count_launch(plane ? 2 : 1);
+  count_launch();
   BSG_CUDA(cudaGetLastError());
   return BSG_OK;
 }
@@ -1706,6 +1876,45 @@ struct ProjScratch {
     return BSG_OK;
   }
 };
+
+// bed_row_counts_cpp (src/bed-fun.cpp:72-98) from three linear functionals of the all-ones vector over the selected
+// columns: R = c1 + 2 c2 + 3 c3 (raw codes), N = c3 (missing flag), H = c2 + c3 (high bit).  Sums of exactly
+// representable integers: the counts are exact.
+__global__ void k_fill(double *x, int len, double v) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) x[i] = v;
+}
+__global__ void k_counts_from_planes(int nr, int nc, const double *__restrict__ R, const double *__restrict__ N,
+                                     const double *__restrict__ H, int32_t *__restrict__ out4) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nr) return;
+  const long long r = llrint(R[i]), c3 = llrint(N[i]), hh = llrint(H[i]);
+  const long long c2 = hh - c3, c1 = r - 2 * c2 - 3 * c3;
+  out4[4 * i + 0] = (int32_t)(nc - c1 - c2 - c3);
+  out4[4 * i + 1] = (int32_t)c1;
+  out4[4 * i + 2] = (int32_t)c2;
+  out4[4 * i + 3] = (int32_t)c3;
+}
+
+int row_counts_planes(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, int32_t *d_out4) {
+  bsg_view *v = nullptr;
+  BSG_TRY(cached_view(h, ind_row, nr, ind_col, nc, nullptr, nullptr, &v));
+  cudaStream_t s = h->stream;
+  ProjScratch mem{h};
+  double *ones = nullptr, *rows = nullptr;
+  BSG_TRY(mem.alloc(&ones, (size_t)v->nc));
+  BSG_TRY(mem.alloc(&rows, 3 * (size_t)v->nr));
+  double *R = rows, *N = rows + v->nr, *H = rows + 2 * (size_t)v->nr;
+  k_fill<<<launch_cap_pub(v->nc), 256, 0, s>>>(ones, v->nc, 1.0);
+  count_launch();
+  PlaneOut o1{1.0, 0.0, 0.0, R, 0.0, 1.0, N};
+  BSG_TRY(view_planes_dev(v, 0, ones, ones, PLANE_NA, o1, s));
+  PlaneOut o2{0.0, 1.0, 0.0, H, 0, 0, nullptr};
+  BSG_TRY(view_planes_dev(v, 0, ones, ones, PLANE_HI, o2, s));
+  k_counts_from_planes<<<(v->nr + 255) / 256, 256, 0, s>>>(v->nr, v->nc, R, N, H, d_out4);
+  count_launch();
+  BSG_CUDA(cudaGetLastError());
+  return BSG_OK;
+}
 }  // namespace bsg
 
 extern "C" {

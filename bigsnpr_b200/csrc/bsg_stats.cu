@@ -114,6 +114,9 @@ int bsg_row_counts(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, i
       k_gather_counts<<<(nr + 255) / 256, 256, 0, s>>>(h->cntB, d_row, nr, d);
       count_launch();
     }
+  } else if (nr > 0 && nc > 0) {
+    // per-sample counts from the plane sums of the X-side kernel (any column multiset, single-copy handles included)
+    BSG_TRY(row_counts_planes(h, ind_row, nr, ind_col, nc, d));
   } else {
     BSG_TRY(upload_index(h, ind_col, nc, h->m, h->w_idx_col, &d_col));
     BSG_TRY(counts_rows(h, d_row, nr, d_col, nc, d, s));
