@@ -15,6 +15,7 @@ and error behaviour, so the parity tests read like the reference's testthat file
     bed_randomSVD            R/autoSVD.R:205-219
     prod_and_rowSumsSq / bed_projectSelfPCA   src/bed-fun.cpp:103-133, R/bed-projectPCA.R:31-58,196-227
     multLinReg / bed_pcadapt / snp_pcadapt    src/multLinReg.cpp:8-95, R/pcadapt.R:3-27,61-81
+    readbina2 / snp_readBed2, writebina / snp_writeBed   src/read-plink.cpp:61-80, src/write-plink.cpp:13-52
 
 Everything computes on the GPU through libbsgpu; there is no CPU path here.
 """
@@ -519,6 +520,57 @@ def bed_randomSVD(obj_bed, fun_scaling=bed_scaleBinom, ind_row=..., ind_col=...,
     return {"d": d, "u": u.T, "v": v.T, "niter": niter.value, "nops": nops.value, "center": c_out, "scale": s_out}
 
 
+def clumping_chr(G, rowInd, colInd, ordInd, rankInd, pos, sumX, denoX, size, thr, ncores=1):
+    """src/clumping.cpp:10-91 (FBM.code256 handle) -> keep (int32 0/1 per column of colInd)."""
+    rowInd, colInd, ordInd = _i32(rowInd), _i32(colInd), _i32(ordInd)
+    pos, sumX, denoX = _f64(pos), _f64(sumX), _f64(denoX)
+    for v in (pos, sumX, denoX, ordInd):
+        if v.size != colInd.size:
+            raise ValueError(ERROR_DIM)
+    keep = np.full(colInd.size, -1, dtype=np.int32)
+    check(lib().bsg_clumping_chr_fbm(G._h, _pi(rowInd), rowInd.size, _pi(colInd), colInd.size, _pd(sumX), _pd(denoX),
+                                     _pi(ordInd), _pd(pos), float(size), float(thr), _pi(keep)))
+    return keep
+
+
+def snp_clumping(G, infos_chr, ind_row=..., S=None, thr_r2=0.2, size=None, infos_pos=None, exclude=None, ncores=1):
+    """LD clumping on an FBM.code256 handle (R/clumping.R:62-137): sorted 1-based indices of the variants kept."""
+    _assert_bed(G)
+    infos_chr = np.asarray(infos_chr)
+    _assert_lengths(infos_chr, G.cols_along())
+    if infos_pos is not None:
+        _assert_lengths(infos_pos, infos_chr)
+    if S is not None:
+        _assert_lengths(S, infos_chr)
+    ind_row = G.rows_along() if ind_row is ... else _i32(ind_row)
+    if size is None:
+        size = 100 / thr_r2
+    m = G.ncol
+    noexcl = np.setdiff1d(np.arange(1, m + 1), np.asarray([] if exclude is None else exclude, dtype=np.int64))
+    kept = []
+    for chrom in sorted(set(infos_chr[noexcl - 1].tolist())):
+        ind_chr = noexcl[infos_chr[noexcl - 1] == chrom].astype(np.int32)
+        st = snp_colstats(G, ind_row, ind_chr, ncores)
+        n = ind_row.size
+        if S is None:
+            af = st["sumX"] / (2 * n)
+            S_chr = np.minimum(af, 1 - af)
+        else:
+            S_chr = np.asarray(S)[ind_chr - 1]
+        ordv = (np.argsort(-np.asarray(S_chr, dtype=np.float64), kind="stable") + 1).astype(np.int32)
+        if infos_pos is None:
+            pos_chr, sz = np.arange(1, ind_chr.size + 1, dtype=np.float64), float(size)
+        else:
+            pos_chr, sz = _f64(np.asarray(infos_pos)[ind_chr - 1]), size * 1000.0
+            if np.any(np.diff(pos_chr) < 0):
+                raise ValueError("'pos.chr' is not sorted.")
+        keep = clumping_chr(G, ind_row, ind_chr, ordv, None, pos_chr, st["sumX"], st["denoX"], sz, thr_r2, ncores)
+        if not np.all((keep == 0) | (keep == 1)):
+            raise RuntimeError("clumping left undecided variants")
+        kept.append(ind_chr[keep == 1])
+    return np.sort(np.concatenate(kept)) if kept else np.zeros(0, dtype=np.int32)
+
+
 def prod_and_rowSumsSq(obj_bed, ind_row, ind_col, center, scale, V):
     """src/bed-fun.cpp:103-133 -> (XV (nr, K), rowSumsSq (nr)); V has one row per selected column (:116)."""
     ind_row, ind_col = _i32(ind_row), _i32(ind_col)
@@ -582,6 +634,52 @@ def bed_pcadapt(obj_bed, U_row, ind_row=..., ind_col=..., ncores=1):
 
 
 snp_pcadapt = bed_pcadapt  # R/pcadapt.R:61-68 (FBM.code256 handles share the packed kernels)
+
+
+def readbina2(obj_bed, ind_row, ind_col, ncores=1):
+    """src/read-plink.cpp:61-80 -> the FBM.code256 bytes (nr, nc) uint8 with codes 0 / 1 / 2 / 3 (NA)."""
+    ind_row, ind_col = _i32(ind_row), _i32(ind_col)
+    out = np.empty((ind_row.size, ind_col.size), dtype=np.uint8, order="F")
+    check(lib().bsg_readbina2(obj_bed._h, _pi(ind_row), ind_row.size, _pi(ind_col), ind_col.size,
+                              out.ctypes.data_as(C.POINTER(C.c_uint8))))
+    return out
+
+
+def snp_readBed2(bedfile, backingfile=None, ind_row=..., ind_col=..., ncores=1):
+    """R/read-plink.R:72-111: fill an FBM.code256 (code CODE_012) from a .bed.  Returns dict(genotypes = (nr, nc) uint8
+    codes, map = the selected .bim rows, backingfile); with `backingfile` the bytes are also written to
+    `<backingfile>.bk` (column-major, the FBM layout), refusing to overwrite like assert_noexist."""
+    obj = bed(bedfile)
+    try:
+        ind_row, ind_col = _ind(obj, *_dflt(obj, ind_row, ind_col))
+        G = readbina2(obj, ind_row, ind_col, ncores)
+        bim = {k: np.asarray(v)[ind_col - 1] for k, v in obj.map.items()}
+    finally:
+        obj.close()
+    bk = None
+    if backingfile is not None:
+        bk = os.path.expanduser(backingfile) + ".bk"
+        if os.path.exists(bk):
+            raise FileExistsError("File '%s' already exists." % bk)
+        G.T.tofile(bk)  # column-major on disk
+    return {"genotypes": G, "map": bim, "backingfile": bk}
+
+
+def writebina(filename, obj, ind_row, ind_col):
+    """src/write-plink.cpp:13-52: X[ind_row, ind_col] of a staged handle as a .bed file (the reference's bytes)."""
+    ind_row, ind_col = _i32(ind_row), _i32(ind_col)
+    check(lib().bsg_writebina(obj._h, os.fsencode(filename), _pi(ind_row), ind_row.size, _pi(ind_col), ind_col.size))
+
+
+def snp_writeBed(G, bedfile, ind_row=..., ind_col=...):
+    """R/write-plink.R:15-45 for the genotype part: write `bedfile` from a handle (bed- or FBM.code256-staged).
+    The .bim / .fam tables are plain-text host data of the caller's bigSNP and are not produced here."""
+    if os.path.exists(bedfile):
+        raise FileExistsError("File '%s' already exists." % bedfile)
+    os.makedirs(os.path.dirname(os.path.abspath(bedfile)), exist_ok=True)
+    ind_row, ind_col = _ind(G, *_dflt(G, ind_row, ind_col))
+    writebina(os.path.expanduser(bedfile), G, ind_row, ind_col)
+    return bedfile
 
 
 def bed_clumping_chr(obj_bed, ind_row, ind_col, center, scale, ordInd, rankInd, pos, size, thr, ncores=1):

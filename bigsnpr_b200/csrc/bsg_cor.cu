@@ -364,6 +364,15 @@ __global__ void k_cor_from_sums(const int *__restrict__ sums, const Tile *__rest
       xySum = (double)aa;
     }
     (void)nona_d;
+    if (KIND == 3) {
+      // clumping_chr on an FBM.code256 (src/clumping.cpp:66-73): no missing-value handling in the reference -- a
+      // missing genotype makes xySum NA and `r2 > thr` false; `center` / `scale` carry the caller's sumX / denoX
+      const bool has_na = cnt[4 * (int64_t)j0 + 3] != 0 || cnt[4 * (int64_t)j + 3] != 0;
+      const double num = xySum - center[j] * center[j0] / nrow;
+      const double r2 = num * num / (scale[j] * scale[j0]);
+      keep[o] = (!has_na && r2 > thr_r2) ? 1 : 0;
+      continue;
+    }
     if (KIND == 2) {
       const double cx = center[j0], cy = center[j];
       const double r = (xySum - cy * xSum - cx * ySum + cx * cy * (double)nona) / (scale[j0] * scale[j]);
@@ -486,8 +495,9 @@ struct CorScratch {
 };
 
 struct ClumpParams {
-  const double *center = nullptr, *scale = nullptr;  // host, per selected column
+  const double *center = nullptr, *scale = nullptr;  // host, per selected column (fbm: sumX / denoX)
   double thr = 0;
+  bool fbm = false;  // src/clumping.cpp's statistic instead of src/clumping-bed.cpp's
 };
 
 static int cor_common(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, double size,
@@ -656,7 +666,10 @@ static int cor_common(bsg_bed *h, const int *ind_row, int nr, const int *ind_col
       }
       const long long npairs = w.boff[j0_end] - w.boff[j0_begin];
       const int eg = (int)std::min<long long>((npairs + 255) / 256, 148 * 16);
-      if (clump)
+      if (clump && clump->fbm)
+        k_cor_from_sums<3><<<eg, 256, 0, s>>>(d_sums, d_tiles, d_rbs, ib_start, j0_begin, j0_end, sc.wlen, sc.boff, d_cnt, nr,
+                                              npad, nullptr, nullptr, sc.keep, TNv, d_cc, d_cs, clump->thr);
+      else if (clump)
         k_cor_from_sums<2><<<eg, 256, 0, s>>>(d_sums, d_tiles, d_rbs, ib_start, j0_begin, j0_end, sc.wlen, sc.boff, d_cnt, nr,
                                               npad, nullptr, nullptr, sc.keep, TNv, d_cc, d_cs, clump->thr);
       else if (ld)
@@ -784,18 +797,20 @@ extern "C" {
 // bed_clumping_chr: src/clumping-bed.cpp:11-91 (+ which_to_check, src/clumping-utils.h:12-43).
 // ordInd: 1-based column positions by decreasing priority (R: order(S, decreasing = TRUE)); keep[nc] receives 0 / 1.
 // All pair statistics inside the window come from the Gram tiles; the greedy pass in rank order runs on the host.
-int bsg_clumping_chr(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, const double *center,
-                     const double *scale, const int *ordInd, const double *pos, double size, double thr, int *keep) {
-  if (!h || !center || !scale || !ordInd || !pos || !keep) return fail(BSG_ERR_ARG, "null argument");
+static int clumping_common(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, const double *a1,
+                           const double *a2, const int *ordInd, const double *pos, double size, double thr, int *keep,
+                           bool fbm) {
+  if (!h || !a1 || !a2 || !ordInd || !pos || !keep) return fail(BSG_ERR_ARG, "null argument");
   BSG_TRY(bind_device(h));
   if (!ind_row) nr = h->n;
   if (!ind_col) nc = h->m;
   Window w;
   CorScratch sc;
   ClumpParams cp;
-  cp.center = center;
-  cp.scale = scale;
+  cp.center = a1;
+  cp.scale = a2;
   cp.thr = thr;
+  cp.fbm = fbm;
   BSG_TRY(cor_common(h, ind_row, nr, ind_col, nc, size, pos, nullptr, false, w, sc, &cp));
   std::vector<uint8_t> conflict((size_t)w.total);
   if (w.total)
@@ -824,6 +839,17 @@ int bsg_clumping_chr(bsg_bed *h, const int *ind_row, int nr, const int *ind_col,
     keep[j0] = keep_j0;
   }
   return BSG_OK;
+}
+
+int bsg_clumping_chr(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, const double *center,
+                     const double *scale, const int *ordInd, const double *pos, double size, double thr, int *keep) {
+  return clumping_common(h, ind_row, nr, ind_col, nc, center, scale, ordInd, pos, size, thr, keep, false);
+}
+
+int bsg_clumping_chr_fbm(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, const double *sumX,
+                         const double *denoX, const int *ordInd, const double *pos, double size, double thr,
+                         int *keep) {
+  return clumping_common(h, ind_row, nr, ind_col, nc, sumX, denoX, ordInd, pos, size, thr, keep, true);
 }
 
 }  // extern "C"

@@ -166,6 +166,37 @@ __global__ void k_read_dense_scaled(const uint8_t *__restrict__ A, int64_t strid
   }
 }
 
+// FBM.code256 bytes of the sub-matrix (readbina2, src/read-plink.cpp:61-80): out[i + nr j] = code 0 / 1 / 2 / 3 (NA)
+__global__ void k_read_bytes(const uint8_t *__restrict__ A, int64_t strideA, const int *__restrict__ rows, int nr,
+                             const int *__restrict__ cols, int nc, uint8_t *__restrict__ out) {
+  int64_t total = (int64_t)nr * nc;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    int j = (int)(t / nr), i = (int)(t - (int64_t)j * nr);
+    out[t] = (uint8_t)code_at(A, strideA, rows ? rows[i] : i, cols ? cols[j] : j);
+  }
+}
+
+// .bed bytes of the sub-matrix as writebina lays them out (src/write-plink.cpp:29-47 with tab = getInverseCode(),
+// R/utils.R:35-45): genotype 0 -> 11, 1 -> 10, 2 -> 00, NA -> 01; the unused slots of the last byte of a column hold
+// genotype 0 (code 11), like the reference's `ind` built from zeros.  One thread per output byte.
+__global__ void k_pack_bed(const uint8_t *__restrict__ A, int64_t strideA, const int *__restrict__ rows, int nr,
+                           const int *__restrict__ cols, int nc, int nbytes, uint8_t *__restrict__ out) {
+  int64_t total = (int64_t)nbytes * nc;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    int j = (int)(t / nbytes), k = (int)(t - (int64_t)j * nbytes);
+    const int col = cols ? cols[j] : j;
+    uint32_t byte = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const int i = 4 * k + c;
+      const int g = i < nr ? code_at(A, strideA, rows ? rows[i] : i, col) : 0;
+      const uint32_t bed2 = g == 0 ? 3u : (g == 1 ? 2u : (g == 2 ? 0u : 1u));
+      byte |= bed2 << (2 * c);
+    }
+    out[t] = (uint8_t)byte;
+  }
+}
+
 static int grid1(int64_t work, int block, int cap = 148 * 16) {
   int64_t g = (work + block - 1) / block;
   if (g < 1) g = 1;
@@ -234,6 +265,23 @@ int counts_rows(bsg_bed *h, const int *d_row, int nr, const int *d_col, int nc, 
 int read_dense(bsg_bed *h, const int *d_row, int nr, const int *d_col, int nc, int na_val, int *d_out, cudaStream_t s) {
   if ((int64_t)nr * nc == 0) return BSG_OK;
   k_read_dense<<<grid1((int64_t)nr * nc, 256), 256, 0, s>>>(h->A, h->strideA, d_row, nr, d_col, nc, na_val, d_out);
+  count_launch();
+  BSG_CUDA(cudaGetLastError());
+  return BSG_OK;
+}
+
+int read_bytes(bsg_bed *h, const int *d_row, int nr, const int *d_col, int nc, uint8_t *d_out, cudaStream_t s) {
+  if ((int64_t)nr * nc == 0) return BSG_OK;
+  k_read_bytes<<<grid1((int64_t)nr * nc, 256), 256, 0, s>>>(h->A, h->strideA, d_row, nr, d_col, nc, d_out);
+  count_launch();
+  BSG_CUDA(cudaGetLastError());
+  return BSG_OK;
+}
+
+int pack_bed(bsg_bed *h, const int *d_row, int nr, const int *d_col, int nc, uint8_t *d_out, cudaStream_t s) {
+  const int nbytes = (nr + 3) / 4;
+  if ((int64_t)nbytes * nc == 0) return BSG_OK;
+  k_pack_bed<<<grid1((int64_t)nbytes * nc, 256), 256, 0, s>>>(h->A, h->strideA, d_row, nr, d_col, nc, nbytes, d_out);
   count_launch();
   BSG_CUDA(cudaGetLastError());
   return BSG_OK;

@@ -3,8 +3,12 @@
 //   bed_col_counts_cpp  src/bed-fun.cpp:51-69     bed_row_counts_cpp  src/bed-fun.cpp:72-98
 //   read_bed            src/bed-mat-acc.cpp:8-26  read_bed_scaled     src/bed-mat-acc.cpp:30-49
 //   snp_colstats        src/colstats.cpp:8-35
+//   readbina2           src/read-plink.cpp:61-80  writebina           src/write-plink.cpp:13-52
 // All sums here are sums of small integers, so they are exact and order independent: results are
 // bit-identical to the reference's scalar loops.
+#include <stdio.h>
+
+#include <algorithm>
 #include <vector>
 
 #include "bsg_internal.cuh"
@@ -184,6 +188,77 @@ int bsg_read_bed(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int
   BSG_TRY(read_dense(h, d_row, nr, d_col, nc, na_val, h->w_out.as<int>(), s));
   BSG_CUDA(cudaMemcpyAsync(out, h->w_out.p, tot * sizeof(int), cudaMemcpyDeviceToHost, s));
   BSG_CUDA(cudaStreamSynchronize(s));
+  return BSG_OK;
+}
+
+// readbina2 (src/read-plink.cpp:61-80): the FBM.code256 bytes of X[ind_row, ind_col] (codes 0 / 1 / 2 / 3 = NA),
+// nr x nc column-major, i.e. the contents of the .bk file snp_readBed2 fills.
+int bsg_readbina2(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, unsigned char *out) {
+  FIX_DIMS();
+  if (!out) return fail(BSG_ERR_ARG, "null argument");
+  cudaStream_t s = h->stream;
+  const int *d_row = nullptr, *d_col = nullptr;
+  BSG_TRY(upload_index(h, ind_row, nr, h->n, h->w_idx_row, &d_row));
+  BSG_TRY(upload_index(h, ind_col, nc, h->m, h->w_idx_col, &d_col));
+  // column blocks of <= 1 GB through one device buffer
+  const int blk = (int)std::max<int64_t>(1, std::min<int64_t>(nc > 0 ? nc : 1, ((int64_t)1 << 30) / std::max(nr, 1)));
+  BSG_TRY(h->w_out.ensure((size_t)std::max(nr, 1) * blk));
+  for (int j0 = 0; j0 < nc; j0 += blk) {
+    const int b = std::min(blk, nc - j0);
+    std::vector<int> iota;
+    const int *dc = d_col ? d_col + j0 : nullptr;
+    if (!d_col && j0 > 0) {  // identity columns beyond the first block: explicit list
+      iota.resize(b);
+      for (int j = 0; j < b; j++) iota[j] = j0 + j + 1;
+      BSG_TRY(upload_index(h, iota.data(), b, h->m, h->w_idx_col, &dc));
+    }
+    BSG_TRY(read_bytes(h, d_row, nr, dc, b, h->w_out.as<uint8_t>(), s));
+    BSG_CUDA(cudaMemcpyAsync(out + (size_t)j0 * nr, h->w_out.p, (size_t)nr * b, cudaMemcpyDeviceToHost, s));
+    BSG_CUDA(cudaStreamSynchronize(s));
+  }
+  return BSG_OK;
+}
+
+// writebina (src/write-plink.cpp:13-52): write X[ind_row, ind_col] of a handle (bed- or FBM-staged) as a .bed file:
+// magic 6C 1B 01, then ceil(nr / 4) bytes per selected column, byte for byte what the reference writes.
+int bsg_writebina(bsg_bed *h, const char *path, const int *ind_row, int nr, const int *ind_col, int nc) {
+  FIX_DIMS();
+  if (!path) return fail(BSG_ERR_ARG, "null argument");
+  cudaStream_t s = h->stream;
+  const int *d_row = nullptr, *d_col = nullptr;
+  BSG_TRY(upload_index(h, ind_row, nr, h->n, h->w_idx_row, &d_row));
+  BSG_TRY(upload_index(h, ind_col, nc, h->m, h->w_idx_col, &d_col));
+  const int nbytes = (nr + 3) / 4;
+  FILE *f = fopen(path, "wb");
+  if (!f) return fail(BSG_ERR_IO, "cannot open '%s' for writing.", path);
+  const unsigned char magic[3] = {108, 27, 1};
+  bool ok = fwrite(magic, 1, 3, f) == 3;
+  const int blk = (int)std::max<int64_t>(1, std::min<int64_t>(nc > 0 ? nc : 1, ((int64_t)1 << 28) / std::max(nbytes, 1)));
+  std::vector<uint8_t> host((size_t)std::max(nbytes, 1) * blk);
+  int rc = h->w_out.ensure(host.size());
+  for (int j0 = 0; j0 < nc && ok && !rc; j0 += blk) {
+    const int b = std::min(blk, nc - j0);
+    std::vector<int> iota;
+    const int *dc = d_col ? d_col + j0 : nullptr;
+    if (!d_col && j0 > 0) {
+      iota.resize(b);
+      for (int j = 0; j < b; j++) iota[j] = j0 + j + 1;
+      rc = upload_index(h, iota.data(), b, h->m, h->w_idx_col, &dc);
+      if (rc) break;
+    }
+    rc = pack_bed(h, d_row, nr, dc, b, h->w_out.as<uint8_t>(), s);
+    if (rc) break;
+    cudaError_t e = cudaMemcpyAsync(host.data(), h->w_out.p, (size_t)nbytes * b, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+      rc = cuda_fail(e, "writebina download");
+      break;
+    }
+    ok = fwrite(host.data(), 1, (size_t)nbytes * b, f) == (size_t)nbytes * b;
+  }
+  if (fclose(f) != 0) ok = false;
+  if (rc) return rc;
+  if (!ok) return fail(BSG_ERR_IO, "short write to '%s'.", path);
   return BSG_OK;
 }
 

@@ -133,6 +133,15 @@ int bsg_clumping_chr(bsg_bed *h, const int *ind_row, int nr, const int *ind_col,
                      const double *scale, const int *ordInd, const double *pos, double size, double thr,
                      int *keep);
 
+/* ---- FBM.code256 <-> .bed conversion ----------------------------------- */
+/* _bigsnpr_readbina2: src/read-plink.cpp:61-80 (snp_readBed2, R/readBed.R).  out = nr x nc bytes column-major, the
+ * FBM.code256 codes 0 / 1 / 2 / 3 (NA) of X[ind_row, ind_col] -- what the reference writes into the .bk file. */
+int bsg_readbina2(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, unsigned char *out);
+/* _bigsnpr_writebina: src/write-plink.cpp:13-52 (snp_writeBed, R/writeBed.R).  Writes X[ind_row, ind_col] of a
+ * bed- or FBM-staged handle as a PLINK .bed: magic bytes, then ceil(nr/4) bytes per column, byte for byte the
+ * reference's output (unused slots of a column's last byte hold genotype 0). */
+int bsg_writebina(bsg_bed *h, const char *path, const int *ind_row, int nr, const int *ind_col, int nc);
+
 /* Which kernel serves the X-side products (bsg_prodvec, bsg_view_prodvec*, XV and row sums of squares):
  * 0 = automatic -- the sample-major kernel when that copy is resident, else the SNP-major kernel (k_pmvT), which
  * needs only the copy every handle has; 1 = always the SNP-major kernel.  Process-wide; no reference twin
@@ -152,6 +161,13 @@ int bsg_prod_and_rowsumssq(bsg_bed *h, const int *ind_row, int nr, const int *in
  * Works on .bed handles and on FBM.code256 handles alike (the reference dispatches on the class, :72-92). */
 int bsg_multlinreg(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, const double *U, int K,
                    double *tscores);
+
+/* _bigsnpr_clumping_chr: src/clumping.cpp:10-91 (snp_clumping on an FBM.code256, R/clumping.R:93-137).  Same
+ * greedy sweep; the statistic is r2 = (xySum - sumX_j sumX_j0 / n)^2 / (denoX_j denoX_j0) with the caller's
+ * snp_colstats vectors and no missing-value handling (a missing genotype never prunes, like the reference's NA). */
+int bsg_clumping_chr_fbm(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, const double *sumX,
+                         const double *denoX, const int *ordInd, const double *pos, double size, double thr,
+                         int *keep);
 
 /* ---- Gram product --------------------------------------------------------------------------------- */
 /* bed_tcrossprodSelf's block loop collapsed into one call: R/bed-tcrossprodSelf.R:38-49 +

@@ -669,6 +669,49 @@ int orc_bed_clumping_chr(const uint8_t *bed, int n_tot, int m_tot, const int *in
   return ORC_OK;
 }
 
+/* src/clumping.cpp:10-91  clumping_chr : the FBM.code256 twin.  Statistic (:66-73):
+ *   xySum = sum_i macc(i, j) * macc(i, j0);  num = xySum - sumX[j] * sumX[j0] / n;
+ *   r2 = num * num / (denoX[j] * denoX[j0])
+ * with the accessor's code256 values (NA_real for a missing code, so r2 is NA and never > thr).  One thread, same
+ * remark as above.  keep must come in filled with -1. */
+int orc_clumping_chr(int kind, const uint8_t *mat, int n_tot, int m_tot, const double *code256, const int *ind_row,
+                     int nr, const int *ind_col, int nc, const int *ordInd, const int *rankInd, const double *pos,
+                     const double *sumX, const double *denoX, double size, double thr, int *keep) {
+  acc_t a;
+  int rc = acc_init(&a, kind, mat, n_tot, m_tot, code256, ind_row, nr, ind_col, nc);
+  if (rc) { acc_free(&a); return rc; }
+  int *chk = (int *)malloc((size_t)(nc ? nc : 1) * sizeof(int));
+  if (!chk) { acc_free(&a); return ORC_ERR_ALLOC; }
+  size_t n = nr, m = nc;
+  for (size_t k = 0; k < m; k++) {
+    size_t j0 = (size_t)ordInd[k] - 1;
+    int nb_check = which_to_check((int)j0, keep, rankInd, pos, (int)m, size, chk);
+    int keep_j0 = 1;
+    for (int k2 = 0; k2 < nb_check; k2++) {
+      int jk = chk[k2];
+      if (keep[jk] == 0) continue;
+      size_t j = (size_t)jk;
+      double xySum = 0;
+      for (size_t i = 0; i < n; i++) {
+        double xa = acc_get3(&a, i, j), xb = acc_get3(&a, i, j0);
+        if (xa == 3) xa = NAN; /* SubBMCode256Acc returns the code itself: NA_real for a missing genotype */
+        if (xb == 3) xb = NAN;
+        xySum += xa * xb;
+      }
+      double num = xySum - sumX[j] * sumX[j0] / n;
+      double r2 = num * num / (denoX[j] * denoX[j0]);
+      if (r2 > thr) {
+        keep_j0 = 0;
+        break;
+      }
+    }
+    keep[j0] = keep_j0;
+  }
+  free(chk);
+  acc_free(&a);
+  return ORC_OK;
+}
+
 /* Synthetic .bed generator, the CPU twin of the device generator
  * (bigsnpr_b200/csrc/bsg_core.cu: k_synth): per-SNP maf ~ U(0.02, 0.5), g ~ Binomial(2, maf), missing with
  * probability na_rate; written in the .bed bit layout of src/write-plink.cpp:29-47 (pads = 00). */

@@ -553,6 +553,57 @@ def bed_clumping(obj, ind_row=None, S=None, thr_r2=0.2, size=None, exclude=None,
     return np.sort(np.concatenate(kept)) if kept else np.zeros(0, dtype=np.int32)
 
 
+def clumping_chr(G, rowInd, colInd, ordInd, rankInd, pos, sumX, denoX, size, thr):
+    """src/clumping.cpp:10-91 -> keep (int32 0/1 per column of colInd); G is an OracleFBM (or OracleBed)."""
+    rowInd, colInd = _i32(rowInd), _i32(colInd)
+    keep = np.full(colInd.size, -1, dtype=np.int32)
+    pos, sumX, denoX = _f64(pos), _f64(sumX), _f64(denoX)
+    ordInd, rankInd = _i32(ordInd), _i32(rankInd)
+    kind, mat, n, m, code = _kind_args(G)
+    with np.errstate(all="ignore"):
+        _chk(lib().orc_clumping_chr(kind, mat, n, m, code, _p(rowInd, C.c_int), rowInd.size, _p(colInd, C.c_int),
+                                    colInd.size, _p(ordInd, C.c_int), _p(rankInd, C.c_int), _p(pos, C.c_double),
+                                    _p(sumX, C.c_double), _p(denoX, C.c_double), C.c_double(size), C.c_double(thr),
+                                    _p(keep, C.c_int)))
+    return keep
+
+
+def snp_clumping(G, infos_chr, ind_row=None, S=None, thr_r2=0.2, size=None, infos_pos=None, exclude=None,
+                 clump_chr=clumping_chr):
+    """R/clumping.R:62-137 (snp_clumping + clumpingChr) -> sorted 1-based indices of the kept variants."""
+    if size is None:
+        size = 100 / thr_r2
+    infos_chr = np.asarray(infos_chr)
+    m = G.ncol
+    if infos_chr.size != m:
+        raise OracleError(ERR_MSG[1])
+    ind_row = np.arange(1, G.nrow + 1, dtype=np.int32) if ind_row is None else _i32(ind_row)
+    noexcl = np.setdiff1d(np.arange(1, m + 1), np.asarray([] if exclude is None else exclude, dtype=np.int64))
+    kept = []
+    for chrom in sorted(set(infos_chr[noexcl - 1].tolist())):
+        ind_chr = noexcl[infos_chr[noexcl - 1] == chrom].astype(np.int32)
+        st = snp_colstats(G, ind_row, ind_chr)
+        n = ind_row.size
+        if S is None:
+            af = st["sumX"] / (2 * n)
+            S_chr = np.minimum(af, 1 - af)
+        else:
+            S_chr = np.asarray(S)[ind_chr - 1]
+        ordv = np.argsort(-np.asarray(S_chr, dtype=np.float64), kind="stable") + 1
+        rank = np.empty_like(ordv)
+        rank[ordv - 1] = np.arange(1, ordv.size + 1)
+        if infos_pos is None:
+            pos_chr, sz = np.arange(1, ind_chr.size + 1, dtype=np.float64), float(size)
+        else:
+            pos_chr, sz = _f64(np.asarray(infos_pos)[ind_chr - 1]), size * 1000.0
+            if np.any(np.diff(pos_chr) < 0):
+                raise OracleError("'pos.chr' is not sorted.")
+        keep = clump_chr(G, ind_row, ind_chr, ordv, rank, pos_chr, st["sumX"], st["denoX"], sz, thr_r2)
+        assert np.all((keep == 0) | (keep == 1))
+        kept.append(ind_chr[keep == 1])
+    return np.sort(np.concatenate(kept)) if kept else np.zeros(0, dtype=np.int32)
+
+
 def synth_bed(n, m, seed=20250924, na_rate=0.0, col_offset=0) -> "OracleBed":
     """CPU twin of the device synthetic generator (same counter-based RNG), as an OracleBed."""
     nb = (n + 3) // 4

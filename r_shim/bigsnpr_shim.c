@@ -227,6 +227,31 @@ SEXP _bigsnpr_bed_clumping_chr(SEXP obj_bed, SEXP BM2, SEXP ind_row, SEXP ind_co
   return R_NilValue;
 }
 
+/* _bigsnpr_clumping_chr: src/clumping.cpp:10-91 (12 arguments; BM is the FBM.code256 environment) */
+SEXP _bigsnpr_clumping_chr(SEXP BM, SEXP BM2, SEXP rowInd, SEXP colInd, SEXP ordInd, SEXP rankInd, SEXP pos, SEXP sumX,
+                           SEXP denoX, SEXP size, SEXP thr, SEXP ncores) {
+  bsg_bed *h = handle_of(BM);
+  int nr = LENGTH(rowInd), nc = LENGTH(colInd);
+  chk(bsg_clumping_chr_fbm(h, INTEGER(rowInd), nr, INTEGER(colInd), nc, REAL(sumX), REAL(denoX), INTEGER(ordInd), REAL(pos),
+                           Rf_asReal(size), Rf_asReal(thr), fbm_int_ptr(BM2)));
+  return R_NilValue;
+}
+
+/* _bigsnpr_readbina2: src/read-plink.cpp:61-80 (5 arguments; BM is the destination FBM.code256, filled in place) */
+extern unsigned char *fbm_raw_ptr(SEXP BM); /* package glue: pointer to the mmap'ed raw matrix of an FBM */
+SEXP _bigsnpr_readbina2(SEXP BM, SEXP obj_bed, SEXP ind_row, SEXP ind_col, SEXP ncores) {
+  bsg_bed *h = handle_of(obj_bed);
+  chk(bsg_readbina2(h, INTEGER(ind_row), LENGTH(ind_row), INTEGER(ind_col), LENGTH(ind_col), fbm_raw_ptr(BM)));
+  return R_NilValue;
+}
+
+/* _bigsnpr_writebina: src/write-plink.cpp:13-52 (5 arguments; `tab` = getInverseCode() is implied by the library) */
+SEXP _bigsnpr_writebina(SEXP filename, SEXP BM, SEXP tab, SEXP rowInd, SEXP colInd) {
+  bsg_bed *h = handle_of(BM);
+  chk(bsg_writebina(h, CHAR(STRING_ELT(filename, 0)), INTEGER(rowInd), LENGTH(rowInd), INTEGER(colInd), LENGTH(colInd)));
+  return R_NilValue;
+}
+
 /* _bigsnpr_prod_and_rowSumsSq: src/bed-fun.cpp:103-133 (6 arguments) -> list(XV, rowSumsSq) */
 SEXP _bigsnpr_prod_and_rowSumsSq(SEXP obj_bed, SEXP ind_row, SEXP ind_col, SEXP center, SEXP scale, SEXP V) {
   bsg_bed *h = handle_of(obj_bed);
@@ -299,6 +324,9 @@ static const R_CallMethodDef CallEntries[] = {
     {"_bigsnpr_corMat", (DL_FUNC)&_bigsnpr_corMat, 8},
     {"_bigsnpr_ld_scores", (DL_FUNC)&_bigsnpr_ld_scores, 6},
     {"_bigsnpr_bed_clumping_chr", (DL_FUNC)&_bigsnpr_bed_clumping_chr, 12},
+    {"_bigsnpr_clumping_chr", (DL_FUNC)&_bigsnpr_clumping_chr, 12},
+    {"_bigsnpr_readbina2", (DL_FUNC)&_bigsnpr_readbina2, 5},
+    {"_bigsnpr_writebina", (DL_FUNC)&_bigsnpr_writebina, 5},
     {"_bigsnpr_prod_and_rowSumsSq", (DL_FUNC)&_bigsnpr_prod_and_rowSumsSq, 6},
     {"_bigsnpr_multLinReg", (DL_FUNC)&_bigsnpr_multLinReg, 5},
     {"_bigsnpr_bed_tcrossprod_gpu", (DL_FUNC)&_bigsnpr_bed_tcrossprod_gpu, 5},

@@ -465,3 +465,68 @@ def test_multLinReg_pcadapt(B, gbed, gbed_na, oracle, obed, obed_na, rng):
     assert res["tscores"].shape == (obed.ncol, 1) and res["score"].shape == (obed.ncol,)
     with pytest.raises(ValueError, match="Incompatibility between dimensions."):
         B.bed_pcadapt(gbed, U_row=np.ones((10, 2)))
+
+
+def test_bed_fbm_conversions(B, gbed, gbed_na, oracle, obed, obed_na, rng, tmp_path):
+    # tests/testthat/test-1-readBed.R:91-115 (snp_readBed2 == the accessor), test-1-writeBed.R (write -> read round
+    # trip); bytes against the oracle's restatement of src/write-plink.cpp:29-47
+    for g, o in ((gbed_na, obed_na), (gbed, obed)):
+        n, m = o.nrow, o.ncol
+        for ir, ic in ((np.arange(1, n + 1), np.arange(1, m + 1)),
+                       (rng.choice(n, n // 2 + 1, replace=False) + 1, rng.choice(m, m // 3, replace=False) + 1),
+                       (rng.integers(1, n + 1, size=203), rng.integers(1, m + 1, size=77))):
+            G = B.readbina2(g, ir, ic)
+            want = oracle.read_bed(o, ir, ic, na_val=3).astype(np.uint8)
+            assert G.dtype == np.uint8 and np.array_equal(G, want)
+            path = str(tmp_path / ("sub_%d_%d.bed" % (ir.size, ic.size)))
+            if os.path.exists(path):
+                os.remove(path)
+            B.snp_writeBed(g, path, ir, ic)
+            raw = np.fromfile(path, dtype=np.uint8)
+            assert raw[:3].tolist() == [108, 27, 1]
+            assert np.array_equal(raw[3:].reshape(ic.size, -1), oracle.write_bed_bytes(want))
+            with pytest.raises(FileExistsError):
+                B.snp_writeBed(g, path, ir, ic)
+            g2 = B.Bed(path, nrow=ir.size, ncol=ic.size)  # read back what was written
+            assert np.array_equal(B.readbina2(g2, np.arange(1, ir.size + 1), np.arange(1, ic.size + 1)), want)
+            g2.close()
+    # FBM.code256-staged handle -> .bed (snp_writeBed's direction) and snp_readBed2 with a backing file
+    Gf = rng.integers(0, 4, size=(37, 11)).astype(np.uint8)
+    gf = B.Bed.from_fbm(Gf)
+    p2 = str(tmp_path / "from_fbm.bed")
+    B.snp_writeBed(gf, p2)
+    assert np.array_equal(np.fromfile(p2, dtype=np.uint8)[3:].reshape(11, -1), oracle.write_bed_bytes(Gf))
+    with open(p2[:-4] + ".bim", "w") as f:
+        for j in range(11):
+            f.write("1\ts%d\t0\t%d\tA\tC\n" % (j, 1000 * (j + 1)))
+    with open(p2[:-4] + ".fam", "w") as f:
+        for i in range(37):
+            f.write("f%d i%d 0 0 0 -9\n" % (i, i))
+    res = B.snp_readBed2(p2, backingfile=str(tmp_path / "bk1"), ind_col=np.arange(2, 9))
+    assert np.array_equal(res["genotypes"], Gf[:, 1:8]) and res["map"]["physical.pos"][0] == 2000.0
+    assert np.array_equal(np.fromfile(res["backingfile"], dtype=np.uint8).reshape(7, 37).T, Gf[:, 1:8])
+    with pytest.raises(FileExistsError):
+        B.snp_readBed2(p2, backingfile=str(tmp_path / "bk1"))
+
+
+def test_snp_clumping_identical_to_oracle(B, gbed, oracle, obed, rng):
+    # tests/testthat/test-2-bed-clumping-SVD.R:34-36,47-48 and R/clumping.R:62-137: FBM.code256 clumping, indices
+    # identical to the oracle; equal to bed_clumping on a file without missing values; missing genotypes never prune
+    chrom, pos = oracle.read_bim(obed.bedfile)
+    G = oracle.read_bed(obed, obed.rows_along(), obed.cols_along(), na_val=3).astype(np.uint8)
+    gf, of = B.Bed.from_fbm(G), oracle.OracleFBM(G)
+    k = B.snp_clumping(gf, chrom, infos_pos=pos)
+    assert np.array_equal(k, oracle.snp_clumping(of, chrom, infos_pos=pos))
+    assert np.array_equal(k, B.bed_clumping(gbed))
+    ir = rng.choice(obed.nrow, 300, replace=False) + 1
+    S = rng.uniform(size=obed.ncol)
+    for kw in (dict(thr_r2=0.1, size=50), dict(thr_r2=0.5, infos_pos=pos, size=200, S=S),
+               dict(ind_row=ir, exclude=np.arange(1, 500), thr_r2=0.2)):
+        assert np.array_equal(B.snp_clumping(gf, chrom, **kw), oracle.snp_clumping(of, chrom, **kw))
+    G2 = G[:, :600].copy()
+    G2[rng.uniform(size=G2.shape) < 0.01] = 3
+    g2, o2 = B.Bed.from_fbm(G2), oracle.OracleFBM(G2)
+    ch2 = chrom[:600]
+    assert np.array_equal(B.snp_clumping(g2, ch2, thr_r2=0.2), oracle.snp_clumping(o2, ch2, thr_r2=0.2))
+    with pytest.raises(ValueError, match=B.ERROR_DIM):
+        B.snp_clumping(gf, chrom[:-1])

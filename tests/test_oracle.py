@@ -209,3 +209,24 @@ def test_clumping_relational(oracle, obed, obed_na):
     near = np.abs(pos_n[kn - 1][:, None] - pos_n[kn - 1][None, :]) <= (100 / 0.3) * 1000
     off = ~np.eye(len(kn), dtype=bool)
     assert np.all(R2[same & near & off] <= 0.3)
+
+
+def test_snp_clumping_fbm_twin(oracle, obed):
+    # tests/testthat/test-2-bed-clumping-SVD.R:34-36,47-48: on a file without missing values snp_clumping (FBM.code256,
+    # src/clumping.cpp) and bed_clumping (src/clumping-bed.cpp) keep the same variants; kept pairs are below thr
+    chrom, pos = oracle.read_bim(obed.bedfile)
+    G = oracle.read_bed(obed, obed.rows_along(), obed.cols_along(), na_val=3).astype(np.uint8)
+    fbm = oracle.OracleFBM(G)
+    k_bed = oracle.bed_clumping(obed)
+    k_fbm = oracle.snp_clumping(fbm, chrom, infos_pos=pos)
+    assert np.array_equal(k_fbm, k_bed)
+    ir = np.arange(1, obed.nrow + 1, 2).astype(np.int32)
+    k2 = oracle.snp_clumping(fbm, chrom, ind_row=ir, thr_r2=0.1, size=50)  # index-based window
+    assert 0 < len(k2) < obed.ncol
+    Gs = G[ir - 1][:, k2 - 1].astype(float)
+    with np.errstate(all="ignore"):
+        R2 = np.corrcoef(Gs.T) ** 2
+    idx = np.arange(len(k2))
+    near = (np.abs((k2[:, None] - k2[None, :])) <= 50) & (chrom[k2 - 1][:, None] == chrom[k2 - 1][None, :])
+    off = idx[:, None] != idx[None, :]
+    assert np.nanmax(R2[near & off]) <= 0.1 + 1e-12
