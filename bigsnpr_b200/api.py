@@ -13,6 +13,7 @@ and error behaviour, so the parity tests read like the reference's testthat file
     bed_ld_scores / snp_ld_scores  R/ld-scores.R:3-72
     bed_tcrossprodSelf       R/bed-tcrossprodSelf.R:21-52
     bed_randomSVD            R/autoSVD.R:205-219
+    bed_autoSVD              R/autoSVD.R:226-339 (control flow; outlier statistic pluggable, see the docstring)
     prod_and_rowSumsSq / bed_projectSelfPCA   src/bed-fun.cpp:103-133, R/bed-projectPCA.R:31-58,196-227
     multLinReg / bed_pcadapt / snp_pcadapt    src/multLinReg.cpp:8-95, R/pcadapt.R:3-27,61-81
     readbina2 / snp_readBed2, writebina / snp_writeBed   src/read-plink.cpp:61-80, src/write-plink.cpp:13-52
@@ -518,6 +519,76 @@ def bed_randomSVD(obj_bed, fun_scaling=bed_scaleBinom, ind_row=..., ind_col=...,
     check(lib().bsg_randomsvd(obj_bed._h, _pi(ind_row), n, _pi(ind_col), m, _pd(center), _pd(scale), int(k), float(tol),
                               int(maxit), _pd(d), _pd(u), _pd(v), _pd(c_out), _pd(s_out), C.byref(niter), C.byref(nops)))
     return {"d": d, "u": u.T, "v": v.T, "niter": niter.value, "nops": nops.value, "center": c_out, "scale": s_out}
+
+
+def _get_intervals(x, n=2):
+    """R/autoSVD.R:4-12: regroup consecutive integers (runs of at least n) into [start, stop] rows."""
+    x = np.asarray(x, dtype=np.int64)
+    out, i = [], 0
+    while i < x.size:
+        j = i
+        while j + 1 < x.size and x[j + 1] - x[j] == 1:
+            j += 1
+        if j - i + 1 >= n:
+            out.append((int(x[i]), int(x[j])))
+        i = j + 1
+    return out
+
+
+def bed_autoSVD(obj_bed, ind_row=..., ind_col=..., fun_scaling=bed_scaleBinom, thr_r2=0.2, size=None, k=10,
+                int_min_size=20, min_mac=10, min_maf=0.02, max_iter=5, ncores=1, verbose=False, outlier_fun=None):
+    """Truncated SVD while limiting LD (R/autoSVD.R:226-339): MAC / MAF filter (bed_MAF) -> clumping on MAC
+    (bed_clumping) -> bed_randomSVD, then up to `max_iter` rounds of outlier-variant removal.
+
+    The engine steps (counts, clumping, SVD) run on the GPU.  The outlier statistic of the reference is host-side R
+    code from bigutilsr (dist_ogk + rollmean + tukey_mc_up, un-vendored): pass it as
+    ``outlier_fun(v, infos_chr_keep) -> 0-based indices into the kept variants``; with ``outlier_fun=None`` the loop
+    stops after the first SVD (the reference's behaviour when no outlier is detected).  Returns the SVD dict plus
+    ``subset`` (1-based kept columns) and ``lrldr`` (list of (chr, start, stop, iter))."""
+    _assert_bed(obj_bed)
+    ind_row, ind_col = _ind(obj_bed, *_dflt(obj_bed, ind_row, ind_col))
+    if size is None and thr_r2 is not None and not np.isnan(thr_r2):
+        size = 100 / thr_r2
+    infos_chr, infos_pos = obj_bed.map["chromosome"], obj_bed.map["physical.pos"]
+    say = print if verbose else (lambda *a, **k: None)
+    if not (min_mac > 0 and min_maf > 0):
+        raise ValueError("You cannot use variants with no variation; set min.mac > 0 and min.maf > 0.")
+    info = bed_MAF(obj_bed, ind_row, ind_col, ncores)
+    nok = (info["mac"] < min_mac) | (info["maf"] < min_maf)
+    say("Discarding %d variant%s with MAC < %s or MAF < %s." % (nok.sum(), "s" if nok.sum() > 1 else "", min_mac, min_maf))
+    ind_keep = ind_col[~nok]
+    if thr_r2 is None or np.isnan(thr_r2):
+        say("Skipping clumping.")
+    else:
+        ind_keep = bed_clumping(obj_bed, ind_row=ind_row, exclude=np.setdiff1d(obj_bed.cols_along(), ind_keep),
+                                thr_r2=thr_r2, size=size, ncores=ncores)
+        say("Phase of clumping (on MAC) at r^2 > %s.. keep %d variants." % (thr_r2, ind_keep.size))
+    it, lrldr = 0, []
+    while True:
+        it += 1
+        svd = bed_randomSVD(obj_bed, fun_scaling=fun_scaling, ind_row=ind_row, ind_col=ind_keep, k=k, ncores=ncores)
+        if it > max_iter:
+            say("Maximum number of iterations reached.")
+            break
+        excl = np.zeros(0, dtype=np.int64) if outlier_fun is None else np.asarray(
+            outlier_fun(svd["v"], infos_chr[ind_keep - 1]), dtype=np.int64)
+        say("%d outlier variant%s detected.." % (excl.size, "s" if excl.size > 1 else ""))
+        if excl.size == 0:
+            say("Converged!")
+            break
+        for a, b in _get_intervals(np.sort(excl) + 1, n=int_min_size):
+            seq = np.arange(a, b + 1) - 1
+            chrs = infos_chr[ind_keep[seq] - 1]
+            vals, cnts = np.unique(chrs, return_counts=True)
+            ch = vals[np.argmax(cnts)]
+            in_chr = chrs == ch
+            rng_pos = infos_pos[ind_keep[seq[in_chr]] - 1]
+            lrldr.append((ch, float(rng_pos.min()), float(rng_pos.max()), it))
+        ind_keep = np.delete(ind_keep, excl)
+    svd = dict(svd)
+    svd["subset"] = ind_keep
+    svd["lrldr"] = sorted(lrldr)
+    return svd
 
 
 def clumping_chr(G, rowInd, colInd, ordInd, rankInd, pos, sumX, denoX, size, thr, ncores=1):

@@ -530,3 +530,31 @@ def test_snp_clumping_identical_to_oracle(B, gbed, oracle, obed, rng):
     assert np.array_equal(B.snp_clumping(g2, ch2, thr_r2=0.2), oracle.snp_clumping(o2, ch2, thr_r2=0.2))
     with pytest.raises(ValueError, match=B.ERROR_DIM):
         B.snp_clumping(gf, chrom[:-1])
+
+
+def test_bed_autoSVD_flow(B, gbed, oracle, obed, capsys):
+    # tests/testthat/test-2-autoSVD.R:68-100 (structure: errors, messages, subset / lrldr attributes); the outlier
+    # statistic is bigutilsr's (host R code), so a synthetic outlier function drives the pruning loop here
+    with pytest.raises(ValueError, match="no variation; set min.mac > 0"):
+        B.bed_autoSVD(gbed, min_mac=0)
+    svd = B.bed_autoSVD(gbed, k=5)
+    keep = svd["subset"]
+    info = B.bed_MAF(gbed)
+    ok = np.where(~((info["mac"] < 10) | (info["maf"] < 0.02)))[0] + 1
+    want_keep = oracle.bed_clumping(obed, exclude=np.setdiff1d(np.arange(1, obed.ncol + 1), ok))
+    assert np.array_equal(keep, want_keep) and svd["lrldr"] == []
+    ref = oracle.bed_randomSVD(obed, ind_col=keep, k=5)
+    np.testing.assert_allclose(svd["d"], ref["d"], rtol=1e-7)
+    B.bed_autoSVD(gbed, thr_r2=np.nan, k=3, verbose=True)
+    assert "Skipping clumping." in capsys.readouterr().out
+    calls = []
+
+    def fake_outliers(v, chr_keep):  # first round: a run of 30 consecutive variants + 2 isolated ones; then none
+        calls.append(v.shape)
+        return np.r_[100:130, 500, 900] if len(calls) == 1 else np.zeros(0, dtype=int)
+
+    svd2 = B.bed_autoSVD(gbed, k=5, outlier_fun=fake_outliers)
+    assert len(calls) == 2 and svd2["subset"].size == keep.size - 32
+    assert len(svd2["lrldr"]) == 1 and svd2["lrldr"][0][3] == 1 and svd2["lrldr"][0][1] <= svd2["lrldr"][0][2]
+    svd3 = B.bed_autoSVD(gbed, k=3, max_iter=1, outlier_fun=lambda v, c: np.array([0]), verbose=True)
+    assert "Maximum number of iterations reached." in capsys.readouterr().out and svd3["subset"].size == keep.size - 1
