@@ -275,7 +275,8 @@ def main():
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                "kernel": "bsg::pmv::k_pmv" if (layouts & 2) else "bsg::pmvt::k_pmvT",
+                "kernel": ("bsg::pmvt::k_pmvT2" if g.has_na else
+                           ("bsg::pmv::k_pmv" if (layouts & 2) else "bsg::pmvt::k_pmvT")),
                 "kernel_ms": kern_ms, "launches_timed": cnt.value, "algorithmic_bytes_per_launch": alg_bytes,
                 "peak_source": peak_src, "kernel_share_of_step": (kern_ms * args.steps / ms) if ms > 0 else None}
 
