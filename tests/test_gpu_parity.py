@@ -558,3 +558,38 @@ def test_bed_autoSVD_flow(B, gbed, oracle, obed, capsys):
     assert len(svd2["lrldr"]) == 1 and svd2["lrldr"][0][3] == 1 and svd2["lrldr"][0][1] <= svd2["lrldr"][0][2]
     svd3 = B.bed_autoSVD(gbed, k=3, max_iter=1, outlier_fun=lambda v, c: np.array([0]), verbose=True)
     assert "Maximum number of iterations reached." in capsys.readouterr().out and svd3["subset"].size == keep.size - 1
+
+
+def test_edge_shapes_and_empty_selections(B, oracle, rng, tmp_path):
+    """Ragged and degenerate inputs through every product path: empty ind.row / ind.col, 1 x 1, n not a multiple of 4,
+    fewer columns than one IMMA step, out-of-bounds subscripts (src/bed-acc.h:64-65)."""
+    for n, m in ((1, 1), (3, 2), (5, 33), (130, 31), (257, 1030)):
+        G = rng.integers(0, 4, size=(n, m)).astype(np.uint8)
+        if n * m > 4:
+            G[0, 0], G[-1, -1] = 3, 2
+        path = oracle.write_bed(str(tmp_path / ("e_%d_%d.bed" % (n, m))), G)
+        o = oracle.OracleBed(path)
+        for layouts in (B.LAYOUT_SNP_MAJOR, B.LAYOUT_SNP_MAJOR | B.LAYOUT_SAMPLE_MAJOR):
+            g = B.Bed(path, layouts=layouts)
+            y_col, y_row = rng.normal(size=m), rng.normal(size=n)
+            c, s = rng.normal(size=m), rng.uniform(0.5, 1.5, size=m)
+            _close(B.bed_prodVec(g, y_col, center=c, scale=s), oracle.bed_prodVec(o, y_col, center=c, scale=s),
+                   scale=np.max(np.abs(y_col / s)) * m * 3 + 1e-300)
+            _close(B.bed_cprodVec(g, y_row, center=c, scale=s), oracle.bed_cprodVec(o, y_row, center=c, scale=s),
+                   scale=np.max(np.abs(y_row)) * n * 3 / np.min(s) + 1e-300)
+            assert np.array_equal(B.bed_counts(g), oracle.bed_counts(o))
+            assert np.array_equal(B.bed_counts(g, byrow=True), oracle.bed_counts(o, byrow=True))
+            e = np.zeros(0, dtype=np.int32)
+            allr, allc = np.arange(1, n + 1), np.arange(1, m + 1)
+            assert B.bed_prodVec(g, np.zeros(m), e, allc).shape == (0,)
+            assert np.array_equal(B.bed_prodVec(g, np.zeros(0), allr, e), np.zeros(n))
+            assert np.array_equal(B.bed_cprodVec(g, np.zeros(0), e, allc), np.zeros(m))
+            assert B.bed_cprodVec(g, np.zeros(n), allr, e).shape == (0,)
+            assert B.bed_counts(g, allr, e).shape == (4, 0) and B.readbina2(g, e, allc).shape == (0, m)
+            XV, rss = B.prod_and_rowSumsSq(g, allr, allc, c, s, rng.normal(size=(m, 2)))
+            assert XV.shape == (n, 2) and rss.shape == (n,)
+            with pytest.raises(B.BsgError, match="out of bounds"):
+                B.bed_prodVec(g, np.zeros(1), allr, np.array([m + 1]))
+            with pytest.raises(B.BsgError, match="out of bounds"):
+                B.bed_cprodVec(g, np.zeros(1), np.array([0]), allc)
+            g.close()
