@@ -106,6 +106,26 @@ def physical_gpu_index(local_rank):
     return local_rank
 
 
+def host_thread_candidates():
+    """Thread counts worth trying for the CPU port: every CPU this process may run on and one per physical core.
+    Taken from the OS, not from OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1 to its workers); the oracle's
+    loops take the count as their `ncores` argument, like the reference's."""
+    try:
+        logical = len(os.sched_getaffinity(0))
+    except Exception:
+        logical = os.cpu_count() or 1
+    cands = {max(1, logical)}
+    try:
+        import psutil
+
+        phys = psutil.cpu_count(logical=False)
+        if phys:
+            cands.add(max(1, min(logical, phys)))
+    except Exception:
+        pass
+    return sorted(cands)
+
+
 def cpu_port_rate(n, m_cols, seed, steps=1, warmup=0, threads=None):
     """genotypes/s of the oracle's bed_pMatVec4 port on a column sample of the synthetic matrix."""
     from oracle import ref
@@ -128,21 +148,17 @@ def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use the host's cores, and libgomp
+    # reads the variable once, when the oracle library is loaded below
+    os.environ["OMP_NUM_THREADS"] = str(max(host_thread_candidates()))
     from oracle import ref
 
     n = wl["n"]
     # calibrate warm on 20,000 columns (the first OpenMP regions of a process are slow) with every logical CPU and
     # with one thread per physical core, keep the faster (SMT oversubscription halves this loop's rate on some
     # hosts); then size a step to ~min(4 s, 150 s / (K + W)), at most the whole per-GPU matrix
-    cands = {ref.max_threads()}
-    try:
-        import psutil
-
-        cands.add(max(1, min(ref.max_threads(), psutil.cpu_count(logical=False) or ref.max_threads())))
-    except Exception:
-        pass
-    rate0, threads = 0.0, ref.max_threads()
-    for t in sorted(cands):
+    rate0, threads = 0.0, 1
+    for t in host_thread_candidates():
         r, _, _ = cpu_port_rate(n, 20000, SEED, steps=2, warmup=2, threads=t)
         if r > rate0:
             rate0, threads = r, t
@@ -378,8 +394,11 @@ def main():
         try:
             from oracle import ref
 
-            threads = ref.max_threads()
-            r0, _, _ = cpu_port_rate(n, 20000, SEED, steps=2, warmup=2, threads=threads)
+            r0, threads = 0.0, 1
+            for t in host_thread_candidates():
+                rr, _, _ = cpu_port_rate(n, 20000, SEED, steps=2, warmup=2, threads=t)
+                if rr > r0:
+                    r0, threads = rr, t
             m_s = int(max(20000, min(m_loc, r0 * 12.0 / n)))  # ~12 s of CPU work (capped at the whole matrix)
             r1, sec, _ = cpu_port_rate(n, m_s, SEED, steps=1, warmup=1, threads=threads)
             cpu_baseline = {"value": r1, "unit": "genotypes/s", "cores": threads, "kind": "port",
