@@ -529,7 +529,7 @@ def _get_intervals(x, n=2):
         j = i
         while j + 1 < x.size and x[j + 1] - x[j] == 1:
             j += 1
-        if j - i + 1 >= n:
+        if j - i + 1 >= max(n, 2):  # rle(diff(x)): a run needs at least one unit step, singletons never count
             out.append((int(x[i]), int(x[j])))
         i = j + 1
     return out

@@ -92,3 +92,16 @@ def test_synth_reference_shapes():
     assert g.shape == (50, 20) and set(np.unique(g)) <= {0, 1, 2, 3} and (g == 3).any()
     g2 = synth_matrix(50, 10, seed=7, na_rate=0.1, col_offset=10)
     assert np.array_equal(g[:, 10:], g2)
+
+
+def test_host_helpers_without_gpu():
+    """Pure host logic of the Python mirror: getIntervals (R/autoSVD.R:4-12) and the correlation thresholds
+    (R/corr.R:17-23) -- no CUDA call."""
+    from bigsnpr_b200.api import _get_intervals, cor_thresholds
+
+    assert _get_intervals([1, 2, 3, 7, 8, 10, 11, 12, 13], n=3) == [(1, 3), (10, 13)]
+    assert _get_intervals([5], n=2) == [] and _get_intervals([], n=2) == []
+    assert _get_intervals([4, 5], n=2) == [(4, 5)] and _get_intervals([4, 5], n=0) == [(4, 5)]
+    assert _get_intervals([1, 2, 5], n=0) == [(1, 2)]
+    thr = cor_thresholds(10, alpha=1.0, thr_r2=0.04)
+    assert thr.shape == (10,) and np.allclose(thr[2:], 0.2) and np.isnan(thr[0])
