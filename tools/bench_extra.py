@@ -31,6 +31,8 @@ def main():
     ap.add_argument("--cor-n", type=int, default=100000)
     ap.add_argument("--cor-m", type=int, default=20000)
     ap.add_argument("--size", type=int, default=500)
+    ap.add_argument("--clump-n", type=int, default=50000)
+    ap.add_argument("--clump-m", type=int, default=100000)
     ap.add_argument("--grm-n", type=int, default=10000)
     ap.add_argument("--grm-m", type=int, default=50000)
     a = ap.parse_args()
@@ -46,6 +48,27 @@ def main():
     t, _ = timeit(lambda: B.bed_counts(g))
     print(json.dumps({"op": "bed_counts(all)", "seconds": t}), flush=True)
     g.close()
+    # --- bed_clumping (thr.r2 = 0.2, size = 500 kb on a 1 kb grid: 500 SNPs either side)
+    gc = B.Bed.synthetic(a.clump_n, a.clump_m, seed=20250929)
+    chrom, pos = np.ones(a.clump_m, dtype=int), 1000.0 * np.arange(1, a.clump_m + 1)
+    t, keep = timeit(lambda: B.bed_clumping(gc, infos_chr=chrom, infos_pos=pos))
+    rec = {"op": "bed_clumping", "n": a.clump_n, "m": a.clump_m, "thr_r2": 0.2, "size_kb": 500, "seconds": t,
+           "kept": int(keep.size), "window_pairs": int(a.clump_m) * 500 - 500 * 501 // 2}
+    try:
+        from oracle import ref
+
+        mo = min(a.clump_m, 1500)
+        o = ref.synth_bed(a.clump_n, mo, seed=20250929)
+        t0 = time.perf_counter()
+        ko = ref.bed_clumping(o, infos_chr=chrom[:mo], infos_pos=pos[:mo])
+        tc = time.perf_counter() - t0
+        rec.update({"cpu_oracle_cols": mo, "cpu_oracle_seconds": tc, "cpu_oracle_threads": 1,
+                    "same_kept_on_sample": bool(np.array_equal(ko, B.bed_clumping(gc, infos_chr=chrom, infos_pos=pos,
+                                                                                   exclude=np.arange(mo + 1, a.clump_m + 1))))})
+    except Exception as e:  # pragma: no cover
+        rec["cpu_oracle_error"] = repr(e)
+    print(json.dumps(rec), flush=True)
+    gc.close()
     # --- bed_tcrossprodSelf (configs[3] is 10,000 x 1,000,000)
     for na_rate in (0.0, 0.01):
         g = B.Bed.synthetic(a.grm_n, a.grm_m, seed=20250928, na_rate=na_rate)
