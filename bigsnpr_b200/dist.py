@@ -273,3 +273,46 @@ def ld_scores_sharded(ld_fn, pos, size_bp, m_total, group=None):
     lo, hi = halo_bounds(pos, size_bp, b, e, right=True)
     ld = np.asarray(ld_fn(lo, hi), dtype=np.float64)
     return gather_columns(ld[b - lo:e - lo], m_total, group)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Arbitrary `ind.col` over column shards ("staging" row): the caller's global 1-based column
+# multiset is bucketed by owning rank once per call; every rank then works on its own local indices.
+# ---------------------------------------------------------------------------------------------------------
+def bucket_columns(ind_col, m_total, world):
+    """For every entry of the global 1-based `ind_col` (any order, duplicates allowed): the owning rank and the
+    1-based index inside that rank's shard (shard_bounds).  Returns (owner, local) int arrays of ind_col's length."""
+    ind_col = np.asarray(ind_col, dtype=np.int64)
+    if ind_col.size and (ind_col.min() < 1 or ind_col.max() > m_total):
+        raise IndexError("Tested subscript out of bounds (column not in 1..%d)." % m_total)
+    begins = np.array([shard_bounds(m_total, world, r)[0] for r in range(world)], dtype=np.int64)
+    owner = np.searchsorted(begins, ind_col - 1, side="right") - 1
+    return owner.astype(np.int32), (ind_col - begins[owner]).astype(np.int32)
+
+
+def prodvec_selected(local_prodvec, ind_col, x, m_total, group=None):
+    """X~[, ind_col] x over column shards.  `local_prodvec(local_ind_col, x_part)` returns this rank's partial
+    n-vector (a torch tensor on the collective's device) for its own columns of the multiset; the partials are
+    summed by one all-reduce.  Ranks that own none of the columns contribute zeros."""
+    import torch.distributed as dist
+
+    world, rank = _world(group)
+    owner, local = bucket_columns(ind_col, m_total, world)
+    mine = owner == rank
+    out = local_prodvec(local[mine], np.asarray(x, dtype=np.float64)[mine])
+    if world > 1:
+        dist.all_reduce(out, group=group)
+    return out
+
+
+def cprodvec_selected(local_cprodvec, ind_col, y, m_total, group=None):
+    """t(X~[, ind_col]) y over column shards, in the caller's order.  `local_cprodvec(local_ind_col, y)` returns the
+    values of this rank's columns of the multiset (numpy); every rank fills its positions of a zero vector and one
+    all-reduce (a sum of disjoint supports, i.e. a gather) assembles the result."""
+    world, rank = _world(group)
+    owner, local = bucket_columns(ind_col, m_total, world)
+    mine = owner == rank
+    full = np.zeros(len(owner), dtype=np.float64)
+    if mine.any():
+        full[mine] = np.asarray(local_cprodvec(local[mine], y), dtype=np.float64)
+    return sum_over_ranks(full, group)

@@ -130,9 +130,47 @@ def _worker_rows(rank, world, port, q):
         errs["ld"] = float(np.nanmax(np.abs(ld - ldw)))
         lo, hi = D.halo_bounds(pos, size_kb * 1000.0, b, e, right=True)
         errs["halo"] = (b - lo, hi - e)
+
+        # arbitrary global ind.col (unsorted, with duplicates) bucketed by owner
+        rng = np.random.default_rng(11)
+        gcols = rng.integers(1, m + 1, size=333)
+        xs, ys = rng.normal(size=gcols.size), rng.normal(size=o.nrow)
+        sc = ref.bed_scaleBinom(o)
+
+        def lp(loc, xpart):
+            gl = (loc + b).astype(np.int32)  # local 1-based -> global 1-based
+            if gl.size == 0:
+                return torch.zeros(o.nrow, dtype=torch.float64)
+            return torch.from_numpy(ref.bed_prodVec(o, xpart, ind_col=gl, center=sc["center"][gl - 1], scale=sc["scale"][gl - 1]))
+
+        def lc(loc, yv):
+            gl = (loc + b).astype(np.int32)
+            return ref.bed_cprodVec(o, yv, ind_col=gl, center=sc["center"][gl - 1], scale=sc["scale"][gl - 1])
+
+        got = D.prodvec_selected(lp, gcols, xs, m).numpy()
+        want = ref.bed_prodVec(o, xs, ind_col=gcols.astype(np.int32), center=sc["center"][gcols - 1], scale=sc["scale"][gcols - 1])
+        errs["sel_prod"] = float(np.max(np.abs(got - want)) / np.max(np.abs(want)))
+        gotc = D.cprodvec_selected(lc, gcols, ys, m)
+        wantc = ref.bed_cprodVec(o, ys, ind_col=gcols.astype(np.int32), center=sc["center"][gcols - 1], scale=sc["scale"][gcols - 1])
+        errs["sel_cprod"] = float(np.max(np.abs(gotc - wantc)))
         q.put((rank, errs))
     finally:
         dist.destroy_process_group()
+
+
+def test_bucket_columns_by_owner():
+    from bigsnpr_b200.dist import bucket_columns, shard_bounds
+
+    m, world = 1001, 4
+    cols = np.array([1, 1001, 251, 250, 252, 500, 501, 751, 1, 1000])
+    owner, local = bucket_columns(cols, m, world)
+    for c, r, l in zip(cols, owner, local):
+        b, e = shard_bounds(m, world, r)
+        assert b < c <= e and l == c - b
+    with pytest.raises(IndexError):
+        bucket_columns([0], m, world)
+    with pytest.raises(IndexError):
+        bucket_columns([m + 1], m, world)
 
 
 def test_halo_bounds_cover_the_reference_window():
@@ -170,4 +208,5 @@ def test_sharded_rows_gloo_world3():
         assert e["grm"] < 1e-12, (rank, e)
         assert e["cor_identical"] and e["cor_nnz"] > 500, (rank, e)
         assert e["ld"] < 1e-10, (rank, e)
+        assert e["sel_prod"] < 1e-12 and e["sel_cprod"] == 0.0, (rank, e)
     assert any(e["halo"][0] > 0 for _, e in res) and any(e["halo"][1] > 0 for _, e in res)
