@@ -1429,15 +1429,15 @@ static int run_pmvT(bsg_view *v, const uint8_t *dig_raw, int plane, const uint8_
   ks = std::max(ks, (nc + MAX_LINES_PER_ITEM - 1) / MAX_LINES_PER_ITEM);  // int32 accumulator head-room
   a.lines_per_split = (int)round_up((nc + ks - 1) / ks, TLINES);
   a.ksplit = (nc + a.lines_per_split - 1) / a.lines_per_split;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned attr_done = 0;  // one bit per device: function attributes are per device
+  if (!(attr_done >> (h->device & 31) & 1u)) {
     BSG_CUDA(cudaFuncSetAttribute(k_pmvT<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TSMEM));
     BSG_CUDA(cudaFuncSetAttribute(k_pmvT<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TSMEM));
     BSG_CUDA(cudaFuncSetAttribute(k_pmvT2<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2SMEM));
     BSG_CUDA(cudaFuncSetAttribute(k_pmvT2<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2SMEM));
     BSG_CUDA(cudaFuncSetAttribute(k_pmvT2<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2SMEM));
     BSG_CUDA(cudaFuncSetAttribute(k_pmvT2<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2SMEM));
-    attr_done = true;
+    attr_done |= 1u << (h->device & 31);
   }
   const int thr = TWARPS * 32;
   const bool lines = a.lines != nullptr;
