@@ -311,24 +311,32 @@ int stage_finish(bsg_bed *h) {
 int build_copy_B(bsg_bed *h) {
   if (h->B) return BSG_OK;
   cudaStream_t s = h->stream;
-  cudaError_t e = cudaMalloc(&h->B, (size_t)h->strideB * h->n);
-  if (e != cudaSuccess) {
+  uint8_t *B = nullptr, *naB = nullptr;
+  int32_t *cntB = nullptr;
+  cudaError_t e = cudaMalloc(&B, (size_t)h->strideB * h->n);
+  if (e == cudaSuccess) e = cudaMalloc(&cntB, (size_t)h->n * 4 * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&naB, (size_t)h->n);
+  if (e == cudaSuccess) e = cudaMemsetAsync(B, 0, (size_t)h->strideB * h->n, s);
+  if (e == cudaSuccess) {
+    dim3 grid((unsigned)((h->m + 127) / 128), (unsigned)((h->strideA + 127) / 128));
+    k_transpose<<<grid, 512, 0, s>>>(h->A, h->strideA, h->n, h->m, B, h->strideB);
+    k_line_counts<<<grid_for((int64_t)h->n * 32, 256), 256, 0, s>>>(B, h->strideB, h->n, h->m, cntB, naB);
+    count_launch(2);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) {  // all or nothing: a half-built copy must never be visible to the kernels
     cudaGetLastError();
-    h->B = nullptr;
-    return fail(BSG_ERR_ALLOC, "cannot allocate %.2f GB for the sample-major copy (%s).", (double)h->strideB * h->n / 1e9,
+    cudaFree(B);
+    cudaFree(cntB);
+    cudaFree(naB);
+    return fail(BSG_ERR_ALLOC, "cannot build the sample-major copy (%.2f GB): %s.", (double)h->strideB * h->n / 1e9,
                 cudaGetErrorString(e));
   }
-  BSG_CUDA(cudaMemsetAsync(h->B, 0, (size_t)h->strideB * h->n, s));
-  dim3 grid((unsigned)((h->m + 127) / 128), (unsigned)((h->strideA + 127) / 128));
-  k_transpose<<<grid, 512, 0, s>>>(h->A, h->strideA, h->n, h->m, h->B, h->strideB);
-  count_launch();
-  BSG_CUDA(cudaMalloc(&h->cntB, (size_t)h->n * 4 * sizeof(int32_t)));
-  BSG_CUDA(cudaMalloc(&h->naB, (size_t)h->n));
-  k_line_counts<<<grid_for((int64_t)h->n * 32, 256), 256, 0, s>>>(h->B, h->strideB, h->n, h->m, h->cntB, h->naB);
-  count_launch();
+  h->B = B;
+  h->cntB = cntB;
+  h->naB = naB;
   h->layouts |= BSG_LAYOUT_SAMPLE_MAJOR;
-  BSG_CUDA(cudaStreamSynchronize(s));
-  BSG_CUDA(cudaGetLastError());
   return BSG_OK;
 }
 
