@@ -572,7 +572,7 @@ void bsg_close(bsg_bed *h) {
     bsg_view_destroy(h->cv);
     h->cv = nullptr;
   }
-  void *ptrs[] = {h->A, h->B, h->cntA, h->cntB, h->naA, h->naB};
+  void *ptrs[] = {h->A, h->B, h->cntA, h->cntB, h->naA, h->naB, h->naColOff, h->naRowOff, h->naColIdx, h->naRowIdx};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   DevBuf *bufs[] = {&h->w_idx_row, &h->w_idx_col, &h->w_center, &h->w_scale, &h->w_x, &h->w_out, &h->w_tmp0,

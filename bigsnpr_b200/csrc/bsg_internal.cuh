@@ -66,6 +66,11 @@ struct bsg_bed {
   int32_t *cntB = nullptr;   // [n][4] counts per sample over all m SNPs (only with copy B)
   uint8_t *naA = nullptr;    // [m] 1 if the SNP line has a missing value
   uint8_t *naB = nullptr;    // [n]
+  // sparse missing-value lists, built on first use when the missing rate is low (bsg_pmv.cu: ensure_na_lists)
+  int64_t *naColOff = nullptr, *naRowOff = nullptr;  // [m + 1] / [n + 1]
+  int32_t *naColIdx = nullptr, *naRowIdx = nullptr;  // sample indices per SNP line / SNP indices per sample
+  int64_t na_nnz = 0;
+  int na_lists = 0;          // 0 not tried yet, 1 resident, -1 not used (rate too high, no memory, disabled)
   double code256[256];       // FBM handles: value of each raw byte code (bigstatsr code256)
   int fbm_generic = 0;       // FBM whose codes are not {0,1,2,NA}: only 0/1/2/NA repack is supported
   cudaStream_t stream = nullptr;

@@ -593,3 +593,38 @@ def test_edge_shapes_and_empty_selections(B, oracle, rng, tmp_path):
             with pytest.raises(B.BsgError, match="out of bounds"):
                 B.bed_cprodVec(g, np.zeros(1), np.array([0]), allc)
             g.close()
+
+
+def test_sparse_missing_lists_equal_plane_path(B, oracle, obed_na, rng, monkeypatch):
+    """Missing values handled by the per-line lists (default for rates <= 0.5 %) and by the flag plane give the same
+    numbers: both sum the same integers.  The rate limit is lifted so the 2.8 %-missing fixture takes the list path."""
+    f = os.path.join(GOLDEN, "example-missing.bed")
+    N, M = obed_na.nrow, obed_na.ncol
+    monkeypatch.setenv("BSG_NA_LIST_MAX_RATE", "1.0")
+    g_list = B.Bed(f)
+    monkeypatch.setenv("BSG_NA_LISTS", "0")
+    g_plane = B.Bed(f)
+    sc = oracle.bed_scaleBinom(obed_na)
+    cases = [(np.arange(1, N + 1), np.arange(1, M + 1)),
+             (rng.choice(N, N // 2, replace=False) + 1, rng.choice(M, M // 2, replace=False) + 1),
+             (rng.integers(1, N + 1, N + 7), rng.integers(1, M + 1, M + 9))]
+    for ir, ic in cases:
+        y_col, y_row = rng.normal(size=ic.size), rng.normal(size=ir.size)
+        for cs in ((None, None), (sc["center"][ic - 1], sc["scale"][ic - 1])):
+            monkeypatch.setenv("BSG_NA_LISTS", "1")
+            a1, b1 = B.bed_prodVec(g_list, y_col, ir, ic, *cs), B.bed_cprodVec(g_list, y_row, ir, ic, *cs)
+            monkeypatch.setenv("BSG_NA_LISTS", "0")
+            a0, b0 = B.bed_prodVec(g_plane, y_col, ir, ic, *cs), B.bed_cprodVec(g_plane, y_row, ir, ic, *cs)
+            if np.unique(ic).size == ic.size:  # no duplicate column: the very same integers, slice by slice
+                assert np.array_equal(a1, a0) and np.array_equal(b1, b0)
+            else:  # duplicates are summed before (lists) or after (plane) the digit split: same total, last-bit rounding
+                _close(a1, a0, scale=np.max(np.abs(a0)), tol=1e-14)
+                assert np.array_equal(b1, b0)
+            s = cs[1] if cs[1] is not None else 1.0
+            _close(a1, oracle.bed_prodVec(obed_na, y_col, ir, ic, *cs), scale=np.max(np.abs(y_col / s)) * ic.size * 3)
+            _close(b1, oracle.bed_cprodVec(obed_na, y_row, ir, ic, *cs),
+                   scale=np.max(np.abs(y_row)) * ir.size * 3 / (np.min(cs[1]) if cs[1] is not None else 1.0))
+    monkeypatch.setenv("BSG_NA_LISTS", "1")
+    svd1 = B.bed_randomSVD(g_list, k=5)
+    svd0 = B.bed_randomSVD(g_plane, k=5)
+    np.testing.assert_allclose(svd1["d"], svd0["d"], rtol=1e-12)
