@@ -73,7 +73,8 @@ def main():
         V = rng.normal(size=(ic.size, 2))
         XV, rss = B.prod_and_rowSumsSq(g, ir, ic, cs[0], cs[1], V)
         XVo, rsso = ref.prod_and_rowSumsSq(o, ir, ic, cs[0], cs[1], V)
-        checks["XV"] = close(XV, XVo, np.max(np.abs(XVo)) + 1e-300)
+        vscale = np.max(np.abs(V)) * ic.size * 3 / np.min(cs[1]) * (1.0 + np.max(np.abs(cs[0])))
+        checks["XV"] = close(XV, XVo, max(np.max(np.abs(XVo)), 1e-3 * vscale))
         checks["rowSumsSq"] = close(rss, rsso, np.max(np.abs(rsso)) + 1e-300, tol=1e-12)
         if ir.size >= 3:
             U = np.linalg.qr(rng.normal(size=(ir.size, 2)))[0]
