@@ -535,6 +535,19 @@ def _get_intervals(x, n=2):
     return out
 
 
+def snp_autoSVD(G, infos_chr, infos_pos=None, ind_row=..., ind_col=..., fun_scaling=None, thr_r2=0.2, size=None, k=10,
+                int_min_size=20, min_mac=10, min_maf=0.02, max_iter=5, ncores=1, verbose=False, outlier_fun=None):
+    """R/autoSVD.R:67-186: the FBM.code256 twin of bed_autoSVD (snp_MAF -> snp_clumping -> randomSVD loop); `G` is a
+    handle staged from an FBM (Bed.from_fbm).  Same remark on the outlier statistic as bed_autoSVD."""
+    infos_chr = np.asarray(infos_chr)
+    _assert_lengths(infos_chr, G.cols_along())
+    if infos_pos is not None:
+        _assert_lengths(infos_pos, infos_chr)
+    return _auto_svd(G, infos_chr, None if infos_pos is None else _f64(infos_pos), ind_row, ind_col,
+                     fun_scaling or snp_scaleBinom(), thr_r2, size, k, int_min_size, min_mac, min_maf, max_iter, ncores,
+                     verbose, outlier_fun, fbm=True)
+
+
 def bed_autoSVD(obj_bed, ind_row=..., ind_col=..., fun_scaling=bed_scaleBinom, thr_r2=0.2, size=None, k=10,
                 int_min_size=20, min_mac=10, min_maf=0.02, max_iter=5, ncores=1, verbose=False, outlier_fun=None):
     """Truncated SVD while limiting LD (R/autoSVD.R:226-339): MAC / MAF filter (bed_MAF) -> clumping on MAC
@@ -546,10 +559,15 @@ def bed_autoSVD(obj_bed, ind_row=..., ind_col=..., fun_scaling=bed_scaleBinom, t
     stops after the first SVD (the reference's behaviour when no outlier is detected).  Returns the SVD dict plus
     ``subset`` (1-based kept columns) and ``lrldr`` (list of (chr, start, stop, iter))."""
     _assert_bed(obj_bed)
+    return _auto_svd(obj_bed, obj_bed.map["chromosome"], obj_bed.map["physical.pos"], ind_row, ind_col, fun_scaling, thr_r2,
+                     size, k, int_min_size, min_mac, min_maf, max_iter, ncores, verbose, outlier_fun, fbm=False)
+
+
+def _auto_svd(obj_bed, infos_chr, infos_pos, ind_row, ind_col, fun_scaling, thr_r2, size, k, int_min_size, min_mac, min_maf,
+              max_iter, ncores, verbose, outlier_fun, fbm):
     ind_row, ind_col = _ind(obj_bed, *_dflt(obj_bed, ind_row, ind_col))
     if size is None and thr_r2 is not None and not np.isnan(thr_r2):
         size = 100 / thr_r2
-    infos_chr, infos_pos = obj_bed.map["chromosome"], obj_bed.map["physical.pos"]
     say = print if verbose else (lambda *a, **k: None)
     if not (min_mac > 0 and min_maf > 0):
         raise ValueError("You cannot use variants with no variation; set min.mac > 0 and min.maf > 0.")
@@ -560,8 +578,13 @@ def bed_autoSVD(obj_bed, ind_row=..., ind_col=..., fun_scaling=bed_scaleBinom, t
     if thr_r2 is None or np.isnan(thr_r2):
         say("Skipping clumping.")
     else:
-        ind_keep = bed_clumping(obj_bed, ind_row=ind_row, exclude=np.setdiff1d(obj_bed.cols_along(), ind_keep),
-                                thr_r2=thr_r2, size=size, ncores=ncores)
+        excl = np.setdiff1d(obj_bed.cols_along(), ind_keep)
+        if fbm:
+            ind_keep = snp_clumping(obj_bed, infos_chr, ind_row=ind_row, exclude=excl, thr_r2=thr_r2, size=size,
+                                    infos_pos=infos_pos, ncores=ncores)
+        else:
+            ind_keep = bed_clumping(obj_bed, ind_row=ind_row, exclude=excl, thr_r2=thr_r2, size=size, ncores=ncores,
+                                    infos_chr=infos_chr, infos_pos=infos_pos)
         say("Phase of clumping (on MAC) at r^2 > %s.. keep %d variants." % (thr_r2, ind_keep.size))
     it, lrldr = 0, []
     while True:
@@ -582,8 +605,9 @@ def bed_autoSVD(obj_bed, ind_row=..., ind_col=..., fun_scaling=bed_scaleBinom, t
             vals, cnts = np.unique(chrs, return_counts=True)
             ch = vals[np.argmax(cnts)]
             in_chr = chrs == ch
-            rng_pos = infos_pos[ind_keep[seq[in_chr]] - 1]
-            lrldr.append((ch, float(rng_pos.min()), float(rng_pos.max()), it))
+            if infos_pos is not None:
+                rng_pos = infos_pos[ind_keep[seq[in_chr]] - 1]
+                lrldr.append((ch, float(rng_pos.min()), float(rng_pos.max()), it))
         ind_keep = np.delete(ind_keep, excl)
     svd = dict(svd)
     svd["subset"] = ind_keep

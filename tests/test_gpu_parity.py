@@ -558,6 +558,15 @@ def test_bed_autoSVD_flow(B, gbed, oracle, obed, capsys):
     assert len(svd2["lrldr"]) == 1 and svd2["lrldr"][0][3] == 1 and svd2["lrldr"][0][1] <= svd2["lrldr"][0][2]
     svd3 = B.bed_autoSVD(gbed, k=3, max_iter=1, outlier_fun=lambda v, c: np.array([0]), verbose=True)
     assert "Maximum number of iterations reached." in capsys.readouterr().out and svd3["subset"].size == keep.size - 1
+    # snp_autoSVD on the FBM.code256 twin of the same (missing-free) data: same subset, same singular values
+    chrom, pos = oracle.read_bim(obed.bedfile)
+    Gf = oracle.read_bed(obed, obed.rows_along(), obed.cols_along(), na_val=3).astype(np.uint8)
+    gf = B.Bed.from_fbm(Gf)
+    svd4 = B.snp_autoSVD(gf, chrom, pos, k=5)
+    assert np.array_equal(svd4["subset"], keep)
+    np.testing.assert_allclose(svd4["d"], svd["d"], rtol=1e-9)
+    with pytest.raises(ValueError, match=B.ERROR_DIM):
+        B.snp_autoSVD(gf, chrom[:-1], pos)
 
 
 def test_edge_shapes_and_empty_selections(B, oracle, rng, tmp_path):
