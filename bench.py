@@ -210,6 +210,10 @@ def main():
             raise SystemExit("launch with torchrun for --gpus > 1")
     torch.cuda.set_device(local)
     if world > 1:
+        # rank 0 prints exactly one line on stdout: keep NCCL's own "NCCL version ..." banner (NCCL_DEBUG=VERSION,
+        # which some launch environments export) out of it; INFO / TRACE requests are respected
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     import bigsnpr_b200 as B
