@@ -212,8 +212,9 @@ def main():
     if world > 1:
         # rank 0 prints exactly one line on stdout: keep NCCL's own "NCCL version ..." banner (NCCL_DEBUG=VERSION,
         # which some launch environments export) out of it; INFO / TRACE requests are respected
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+            os.environ["NCCL_DEBUG"] = "NONE"  # WARN still prints the banner (VERSION < WARN in NCCL's levels)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # whatever NCCL does print stays off stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     import bigsnpr_b200 as B
