@@ -14,8 +14,8 @@ and error behaviour, so the parity tests read like the reference's testthat file
     bed_tcrossprodSelf       R/bed-tcrossprodSelf.R:21-52
     bed_randomSVD            R/autoSVD.R:205-219
     bed_autoSVD              R/autoSVD.R:226-339 (control flow; outlier statistic pluggable, see the docstring)
-    prod_and_rowSumsSq / bed_projectSelfPCA   src/bed-fun.cpp:103-133, R/bed-projectPCA.R:31-58,196-227
-    multLinReg / bed_pcadapt / snp_pcadapt    src/multLinReg.cpp:8-95, R/pcadapt.R:3-27,61-81
+    prod_and_rowSumsSq / bed_projectSelfPCA   src/bed-fun.cpp:103-133, R/bed-projectPCA.R:45-58,196-227
+    multLinReg / bed_pcadapt / snp_pcadapt    src/multLinReg.cpp:8-88, R/pcadapt.R:3-27,61-81
     readbina2 / snp_readBed2, writebina / snp_writeBed   src/read-plink.cpp:61-80, src/write-plink.cpp:13-52
 
 Everything computes on the GPU through libbsgpu; there is no CPU path here.
@@ -700,7 +700,7 @@ def bed_projectSelfPCA(obj_svd, obj_bed, ind_row, ind_col=None, ncores=1):
 
 
 def multLinReg(obj, ind_row, ind_col, U, ncores=1):
-    """src/multLinReg.cpp:64-95 -> t-scores (nc, K), NaN where the reference gives NA."""
+    """src/multLinReg.cpp:64-88 -> t-scores (nc, K), NaN where the reference gives NA."""
     ind_row, ind_col = _i32(ind_row), _i32(ind_col)
     U = np.asarray(U, dtype=np.float64)
     U = np.asfortranarray(U.reshape(U.shape[0], -1))

@@ -2214,7 +2214,7 @@ int bsg_prod_and_rowsumssq(bsg_bed *h, const int *ind_row, int nr, const int *in
   return BSG_OK;
 }
 
-// multLinReg (src/multLinReg.cpp:8-95): t-scores of genotype ~ U[, k] per SNP over the samples where the
+// multLinReg (src/multLinReg.cpp:8-88): t-scores of genotype ~ U[, k] per SNP over the samples where the
 // genotype is present.  U is nr x K column-major, tscores nc x K column-major, NA_REAL is written as NaN.
 int bsg_multlinreg(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, const double *U, int K,
                    double *tscores) {

@@ -134,10 +134,10 @@ int bsg_clumping_chr(bsg_bed *h, const int *ind_row, int nr, const int *ind_col,
                      int *keep);
 
 /* ---- FBM.code256 <-> .bed conversion ----------------------------------- */
-/* _bigsnpr_readbina2: src/read-plink.cpp:61-80 (snp_readBed2, R/readBed.R).  out = nr x nc bytes column-major, the
+/* _bigsnpr_readbina2: src/read-plink.cpp:61-80 (snp_readBed2, R/read-plink.R:72-111).  out = nr x nc bytes column-major, the
  * FBM.code256 codes 0 / 1 / 2 / 3 (NA) of X[ind_row, ind_col] -- what the reference writes into the .bk file. */
 int bsg_readbina2(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, unsigned char *out);
-/* _bigsnpr_writebina: src/write-plink.cpp:13-52 (snp_writeBed, R/writeBed.R).  Writes X[ind_row, ind_col] of a
+/* _bigsnpr_writebina: src/write-plink.cpp:13-52 (snp_writeBed, R/write-plink.R:15-45).  Writes X[ind_row, ind_col] of a
  * bed- or FBM-staged handle as a PLINK .bed: magic bytes, then ceil(nr/4) bytes per column, byte for byte the
  * reference's output (unused slots of a column's last byte hold genotype 0). */
 int bsg_writebina(bsg_bed *h, const char *path, const int *ind_row, int nr, const int *ind_col, int nc);
@@ -149,14 +149,14 @@ int bsg_writebina(bsg_bed *h, const char *path, const int *ind_row, int nr, cons
 int bsg_set_prodvec_path(int path);
 
 /* ---- PCA projection / pcadapt ------------------------------------------- */
-/* _bigsnpr_prod_and_rowSumsSq: src/bed-fun.cpp:103-133 (R: part_prod, R/bed-projectPCA.R:31-58).
+/* _bigsnpr_prod_and_rowSumsSq: src/bed-fun.cpp:103-133 (R: part_prod, R/bed-projectPCA.R:45-58).
  * V is nc x K column-major; XV (nr x K column-major) = X~ V and rowSumsSq[nr] = sum_j X~_ij^2 with the
  * bedAccScaled semantics (missing value -> 0).  center / scale length nc, else
  * "Incompatibility between dimensions." */
 int bsg_prod_and_rowsumssq(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc,
                            const double *center, const double *scale, const double *V, int K,
                            double *XV, double *rowSumsSq);
-/* _bigsnpr_multLinReg: src/multLinReg.cpp:8-95 (R: pcadapt0, R/pcadapt.R:3-27).  U is nr x K column-major;
+/* _bigsnpr_multLinReg: src/multLinReg.cpp:8-88 (R: pcadapt0, R/pcadapt.R:3-27).  U is nr x K column-major;
  * tscores is nc x K column-major (the reference returns transpose(res)); NA_REAL is written as NaN.
  * Works on .bed handles and on FBM.code256 handles alike (the reference dispatches on the class, :72-92). */
 int bsg_multlinreg(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, const double *U, int K,

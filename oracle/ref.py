@@ -292,7 +292,7 @@ def corMat(obj, rowInd, colInd, size, thr, pos, fill_diag=True, ncores=1):
 
 
 def multLinReg(obj, ind_row, ind_col, U, ncores=1):
-    """src/multLinReg.cpp:8-95 -> t-scores (nc, K); NA_REAL is NaN."""
+    """src/multLinReg.cpp:8-88 -> t-scores (nc, K); NA_REAL is NaN."""
     ind_row, ind_col = _i32(ind_row), _i32(ind_col)
     U = np.asfortranarray(np.asarray(U, dtype=np.float64).reshape(len(U), -1))
     if U.shape[0] != ind_row.size:

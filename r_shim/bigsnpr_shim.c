@@ -267,7 +267,7 @@ SEXP _bigsnpr_prod_and_rowSumsSq(SEXP obj_bed, SEXP ind_row, SEXP ind_col, SEXP 
   return res;
 }
 
-/* _bigsnpr_multLinReg: src/multLinReg.cpp:64-95 (5 arguments; `obj` is a bed or an FBM.code256 environment) */
+/* _bigsnpr_multLinReg: src/multLinReg.cpp:64-88 (5 arguments; `obj` is a bed or an FBM.code256 environment) */
 SEXP _bigsnpr_multLinReg(SEXP obj, SEXP ind_row, SEXP ind_col, SEXP U, SEXP ncores) {
   bsg_bed *h = handle_of(obj);
   int nr = LENGTH(ind_row), nc = LENGTH(ind_col), K = Rf_ncols(U);

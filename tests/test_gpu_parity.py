@@ -434,7 +434,7 @@ def test_prod_and_rowSumsSq_and_projection(B, gbed, gbed_na, oracle, obed, obed_
 
 
 def test_multLinReg_pcadapt(B, gbed, gbed_na, oracle, obed, obed_na, rng):
-    # src/multLinReg.cpp:8-95 against the oracle (bed and FBM.code256 handles), R/pcadapt.R:3-27
+    # src/multLinReg.cpp:8-88 against the oracle (bed and FBM.code256 handles), R/pcadapt.R:3-27
     for g, o in ((gbed_na, obed_na), (gbed, obed)):
         n, m = o.nrow, o.ncol
         for ir, ic, K in ((np.arange(1, n + 1), np.arange(1, m + 1), 3),
