@@ -7,10 +7,13 @@
 //                   exact shifts) with full re-orthogonalisation, ncv = max(2k+1, 20), the same stopping
 //                   rule as ARPACK/Spectra (|Ritz residual| <= tol * max(eps^(2/3), |theta|)), operator =
 //                   bsg_view_{c,}prodvec_dev.  Only ncv+1 doubles cross PCIe per step.
-//   bsg_tcrossprod  bed_tcrossprodSelf (R/bed-tcrossprodSelf.R:21-52): K = sum_blocks X~_b X~_b^T.  Round-1
-//                   version: decode a column block to fp64 on the device (read_bed_scaled semantics) and
-//                   accumulate with cuBLAS DSYRK (a plain library SYRK; the int8 tensor-core Gram is the next
-//                   step).
+//   bsg_tcrossprod  bed_tcrossprodSelf (R/bed-tcrossprodSelf.R:21-52): K = sum_blocks X~_b X~_b^T as ONE weighted
+//                   integer Gram product: the per-SNP weights 1/s^2, c/s^2, c^2/s^2 are quantised to base-64 digit
+//                   slices folded into the B bytes, the 128 x 128 tiles run on tcgen05 / TMEM (bsg_gram5.cu,
+//                   k_wgram5) or on the register-IMMA kernel below (k_wgram), the centering terms come from two
+//                   matvecs.  The sample-major copy is built on demand.  Fallback (degenerate scaling, no room for
+//                   that copy): device decode of column blocks + cuBLAS DSYRK.
+//                   bsg_tcrossprod_dev leaves K in the caller's device buffer (sharded GRM: one all-reduce).
 #include <cublas_v2.h>
 #include <math.h>
 #include <string.h>

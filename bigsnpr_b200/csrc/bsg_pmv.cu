@@ -27,6 +27,12 @@
 // bytes = full sectors) through a 4-slot register ring (3 half-stages in flight per warp); only the
 // 4 KB digit block of each 512-code chunk goes through a shared-memory ring, filled by one bulk copy
 // per stage from a producer warp (mbarrier full/empty).
+//
+// Contents, in order: k_pmv (lines = contraction-contiguous: Xt.y on the SNP-major copy, X.y on the sample-major
+// copy); vector preparation and finish kernels; k_pmvT / k_pmvT2 (X.y straight from the SNP-major copy: the
+// contraction runs across lines, bytes are transposed in registers; T2 = raw + flag plane in one pass); the sparse
+// missing-value lists; views and the C-ABI entry points (bsg_prodvec / bsg_cprodvec / bsg_view_*); the planes API
+// behind bsg_prod_and_rowsumssq, bsg_multlinreg and the by-row counts.
 #include <algorithm>
 #include <math.h>
 #include <stdio.h>
