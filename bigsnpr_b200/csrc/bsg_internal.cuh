@@ -8,7 +8,8 @@
 //     hold code 0: they add nothing to any sum and are never missing.
 //   * copy A (SNP-major): line j = SNP column j, n codes, lowest bits = first sample -- the .bed
 //     orientation.  Line stride = round_up(ceil(n/4), 128) bytes.
-//   * copy B (sample-major): line i = sample i, m codes.  Line stride = round_up(ceil(m/4), 128).
+//   * copy B (sample-major), optional: line i = sample i, m codes.  Line stride = round_up(ceil(m/4), 128).
+//     Built on request or on first use by the GRM; every other kernel runs from copy A alone.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

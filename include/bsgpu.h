@@ -40,9 +40,9 @@ extern "C" {
 #define BSG_ERR_TYPE 10   /* "Unknown object type."                    src/corr.cpp:124 */
 
 /* layouts kept resident in HBM (bit mask) */
-#define BSG_LAYOUT_SNP_MAJOR 1    /* variant-major, the .bed orientation: serves Xt.y, stats, LD, decode */
-#define BSG_LAYOUT_SAMPLE_MAJOR 2 /* transposed copy: serves X.y at the same speed as Xt.y */
-#define BSG_LAYOUT_AUTO 0         /* both when they fit in free HBM, else SNP-major only */
+#define BSG_LAYOUT_SNP_MAJOR 1    /* variant-major, the .bed orientation: serves every entry point at full speed */
+#define BSG_LAYOUT_SAMPLE_MAJOR 2 /* also keep the 2-bit transpose (what the GRM tiles read; X.y 1-3 % faster on it) */
+#define BSG_LAYOUT_AUTO 0         /* SNP-major only; the transpose is built on first use by bsg_tcrossprod */
 
 typedef struct bsg_bed bsg_bed;   /* replaces class bed + XPtr<bed>: src/bed-acc.h:18-48, src/bed-acc-xptr.cpp:40-55 */
 typedef struct bsg_view bsg_view; /* replaces bedAccScaled: (ind_row, ind_col, center, scale) resident on device, src/bed-acc.h:86-115 */
