@@ -3,7 +3,7 @@
 //   S[i][j] = sum_k code(i, k) * code(j, k)      for a 128 x 128 tile of lines, exact int32
 //
 // Used for the windowed correlations when the tile holds no missing value (only xySum is pair specific then,
-// src/corr.cpp:58-75); tiles with missing values take the six-plane IMMA path of bsg_cor.cu.
+// src/corr.cpp:58-75); tiles with missing values take k_wgram5<1> below (six plane products, same pipeline).
 //
 // Pipeline per CTA (one 128 x 128 tile, whole contraction range):
 //   8 producer warps : stream the packed lines (2 x LDG.128 = 128 codes per line and stage, register prefetch),
