@@ -230,3 +230,33 @@ def test_snp_clumping_fbm_twin(oracle, obed):
     near = (np.abs((k2[:, None] - k2[None, :])) <= 50) & (chrom[k2 - 1][:, None] == chrom[k2 - 1][None, :])
     off = idx[:, None] != idx[None, :]
     assert np.nanmax(R2[near & off]) <= 0.1 + 1e-12
+
+
+def test_projection_and_pcadapt_oracle_against_numpy(oracle, obed_na):
+    # src/bed-fun.cpp:103-133 and src/multLinReg.cpp:8-60 restated in the oracle, pinned on independent NumPy / SciPy
+    # formulations: X~ V and row sums of squares of the dense scaled matrix; t-score = slope / stderr of the simple
+    # regression of the genotype on u over the samples where the genotype is present (tests/testthat/test-4-pcadapt.R
+    # compares with the pcadapt package, which computes the same statistic).
+    from scipy import stats
+
+    rng = np.random.default_rng(4)
+    n, m = obed_na.nrow, obed_na.ncol
+    ir = np.sort(rng.choice(n, 150, replace=False)) + 1
+    ic = rng.choice(m, 120, replace=False) + 1
+    sc = oracle.bed_scaleBinom(obed_na, ir, ic)
+    V = rng.normal(size=(ic.size, 3))
+    XV, rss = oracle.prod_and_rowSumsSq(obed_na, ir, ic, sc["center"], sc["scale"], V)
+    X = oracle.read_bed_scaled(obed_na, ir, ic, sc["center"], sc["scale"])
+    np.testing.assert_allclose(XV, X @ V, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(rss, (X ** 2).sum(1), rtol=1e-12)
+    U = np.linalg.qr(rng.normal(size=(ir.size, 2)))[0]
+    t = oracle.multLinReg(obed_na, ir, ic, U, ncores=2)
+    G = oracle.read_bed(obed_na, ir, ic, na_val=3).astype(float)
+    for j in rng.choice(ic.size, 12, replace=False):
+        ok = G[:, j] != 3
+        for k in range(2):
+            if np.ptp(G[ok, j]) == 0:
+                assert np.isnan(t[j, k])
+                continue
+            r = stats.linregress(U[ok, k], G[ok, j])
+            np.testing.assert_allclose(t[j, k], r.slope / r.stderr, rtol=1e-9)
