@@ -105,3 +105,38 @@ def test_host_helpers_without_gpu():
     assert _get_intervals([1, 2, 5], n=0) == [(1, 2)]
     thr = cor_thresholds(10, alpha=1.0, thr_r2=0.04)
     assert thr.shape == (10,) and np.allclose(thr[2:], 0.2) and np.isnan(thr[0])
+
+
+def test_r_shim_type_checks_against_the_c_abi():
+    """r_shim/bigsnpr_shim.c cannot be built here (no R), but it must at least parse and type-check against
+    include/bsgpu.h: gcc -fsyntax-only with declaration-only stubs of the R C API (tests/stubs/)."""
+    import subprocess
+
+    cmd = ["/usr/bin/gcc", "-fsyntax-only", "-Wall", "-Wextra", "-Wno-unused-parameter", "-Wno-cast-function-type",
+           "-Werror", "-I", os.path.join(ROOT, "tests", "stubs"), "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "r_shim", "bigsnpr_shim.c")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[:2000]
+
+
+def test_r_shim_registers_the_reference_names_and_arities():
+    """Names and arities in the shim's R_CallMethodDef table equal the reference's (src/RcppExports.cpp:597-640) for
+    every reference symbol it replaces.  The reference table is read only where the checkout is mounted."""
+    import re
+
+    shim = open(os.path.join(ROOT, "r_shim", "bigsnpr_shim.c")).read()
+    mine = {m.group(1): int(m.group(2)) for m in re.finditer(r'\{"(_bigsnpr_\w+)",\s*\(DL_FUNC\)&\w+,\s*(\d+)\}', shim)}
+    assert len(mine) >= 15
+    for name, ar in mine.items():  # the definition has as many SEXP parameters as the table says
+        m = re.search(r"SEXP %s\(([^)]*)\)" % name, shim)
+        assert m and m.group(1).count("SEXP") == ar, name
+    ref_path = "/root/reference/src/RcppExports.cpp"
+    if not os.path.exists(ref_path):
+        pytest.skip("reference checkout not mounted")
+    ref = {m.group(1): int(m.group(2)) for m in re.finditer(r'\{"(_bigsnpr_\w+)",\s*\(DL_FUNC\)\s*&\w+,\s*(\d+)\}', open(ref_path).read())}
+    new_symbols = {"_bigsnpr_bed_tcrossprod_gpu", "_bigsnpr_bed_randomSVD_gpu"}
+    for name, ar in mine.items():
+        if name in new_symbols:
+            assert name not in ref
+        else:
+            assert ref.get(name) == ar, (name, ar, ref.get(name))
