@@ -140,3 +140,18 @@ def test_r_shim_registers_the_reference_names_and_arities():
             assert name not in ref
         else:
             assert ref.get(name) == ar, (name, ar, ref.get(name))
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/bsgpu.h is the drop-in boundary: it must compile as C99 on its own (no C++ or CUDA types) and every
+    declared entry point must be addressable."""
+    import subprocess
+
+    names = re.findall(r"\b(bsg_\w+)\s*\(", open(os.path.join(ROOT, "include", "bsgpu.h")).read())
+    names = sorted(set(n for n in names if not n.endswith("_cb")))
+    src = tmp_path / "abi.c"
+    src.write_text('#include "bsgpu.h"\nconst void *table[] = {\n' + "".join("  (const void *)%s,\n" % n for n in names) + "};\n")
+    r = subprocess.run(["/usr/bin/gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-Wno-pedantic", "-c", str(src), "-I",
+                        os.path.join(ROOT, "include"), "-o", str(tmp_path / "abi.o")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[:2000]
+    assert len(names) >= 40
