@@ -25,6 +25,8 @@ SIGNATURES = {
     "bsg_open_bed": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
     "bsg_open_packed": (C.c_int, [c_u8_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
     "bsg_open_synth": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_double, C.c_int64, C.c_int, C.c_int, C.POINTER(vp)]),
+    "bsg_open_synth_ld": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_double, C.c_int64, C.c_double, C.c_int, C.c_int, C.c_int,
+                                    C.POINTER(vp)]),
     "bsg_open_fbm256": (C.c_int, [c_u8_p, C.c_int, C.c_int, c_dbl_p, C.c_int, C.c_int, C.POINTER(vp)]),
     "bsg_close": (None, [vp]),
     "bsg_nrow": (C.c_int, [vp]),
@@ -68,6 +70,7 @@ SIGNATURES = {
     "bsg_randomsvd_ex": (C.c_int, [vp, c_int_p, C.c_int, c_int_p, C.c_int, c_dbl_p, c_dbl_p, C.c_int, C.c_double,
                                    C.c_int, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, c_int_p, c_int_p, vp, vp, vp,
                                    C.c_int]),
+    "bsg_randomsvd_nconv": (C.c_int, []),
     "bsg_launch_count": (C.c_int64, []),
     "bsg_last_kernel_ms": (C.c_double, []),
     "bsg_set_kernel_timing": (C.c_int, [C.c_int]),

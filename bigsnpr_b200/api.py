@@ -104,10 +104,17 @@ class Bed:
         return cls(_handle=h, _shape=(int(n), int(m)))
 
     @classmethod
-    def synthetic(cls, n, m, seed=20250924, na_rate=0.0, col_offset=0, device=0, layouts=LAYOUT_AUTO):
+    def synthetic(cls, n, m, seed=20250924, na_rate=0.0, col_offset=0, device=0, layouts=LAYOUT_AUTO, ld_rho=0.0,
+                  ld_block=50):
+        """Synthetic matrix generated on the device.  ld_rho > 0: haplotype blocks of `ld_block`
+        SNPs whose alleles are copied from the previous SNP with probability ld_rho (correlated neighbours)."""
         h = C.c_void_p()
-        check(lib().bsg_open_synth(int(n), int(m), int(seed), float(na_rate), int(col_offset), int(device),
-                                   int(layouts), C.byref(h)))
+        if ld_rho > 0:
+            check(lib().bsg_open_synth_ld(int(n), int(m), int(seed), float(na_rate), int(col_offset), float(ld_rho),
+                                          int(ld_block), int(device), int(layouts), C.byref(h)))
+        else:
+            check(lib().bsg_open_synth(int(n), int(m), int(seed), float(na_rate), int(col_offset), int(device),
+                                       int(layouts), C.byref(h)))
         return cls(_handle=h, _shape=(int(n), int(m)))
 
     @classmethod
@@ -518,6 +525,11 @@ def bed_randomSVD(obj_bed, fun_scaling=bed_scaleBinom, ind_row=..., ind_col=...,
     niter, nops = C.c_int(0), C.c_int(0)
     check(lib().bsg_randomsvd(obj_bed._h, _pi(ind_row), n, _pi(ind_col), m, _pd(center), _pd(scale), int(k), float(tol),
                               int(maxit), _pd(d), _pd(u), _pd(v), _pd(c_out), _pd(s_out), C.byref(niter), C.byref(nops)))
+    nconv = int(lib().bsg_randomsvd_nconv())
+    if 0 <= nconv < k:  # RSpectra::svds behind big_randomSVD: "only %d singular values converged"
+        import warnings
+
+        warnings.warn("only %d singular values converged after %d restarts (maxit = %d)." % (nconv, niter.value, maxit))
     return {"d": d, "u": u.T, "v": v.T, "niter": niter.value, "nops": nops.value, "center": c_out, "scale": s_out}
 
 

@@ -446,7 +446,10 @@ struct Window {
 };
 
 // window of j0: j = j0-1 downto 0 while pos[j] >= pos[j0] - size   (src/corr.cpp:52-53), literal scan
-static void build_window(const double *pos, int nc, double size, Window &w) {
+// `both`: also admit j when pos[j0] <= pos[j] + size -- the clumping sweep tests right-hand neighbours with that expression
+// (src/clumping-utils.h:29); for non-integer positions the two roundings can differ at the window edge, so the pair
+// statistics are computed for the union and the sweep applies each side's own test.
+static void build_window(const double *pos, int nc, double size, Window &w, bool both = false) {
   w.wlen.assign(nc, 0);
   w.reach.assign(nc, 0);
   w.boff.assign(nc + 1, 0);
@@ -454,7 +457,7 @@ static void build_window(const double *pos, int nc, double size, Window &w) {
   for (int j0 = 0; j0 < nc; j0++) {
     double pos_min = pos[j0] - size;
     int j = j0 - 1, c = 0;
-    while (j >= 0 && pos[j] >= pos_min) {
+    while (j >= 0 && (pos[j] >= pos_min || (both && pos[j0] <= pos[j] + size))) {
       c++;
       j--;
     }
@@ -507,7 +510,9 @@ static int cor_common(bsg_bed *h, const int *ind_row, int nr, const int *ind_col
   const int *d_row = nullptr, *d_col = nullptr;
   BSG_TRY(upload_index(h, ind_row, nr, h->n, h->w_idx_row, &d_row));
   BSG_TRY(upload_index(h, ind_col, nc, h->m, h->w_idx_col, &d_col));
-  build_window(pos, nc, size, w);
+  for (int j = 1; j < nc; j++)  // the reference asserts this in R (assert_sorted); the C ABI checks it too
+    if (pos[j] < pos[j - 1]) return fail(BSG_ERR_ARG, "'pos' is not sorted.");
+  build_window(pos, nc, size, w, clump != nullptr);
   // identity rows and columns: the staged SNP-major copy already is the dense matrix (stride multiple of 128)
   auto ident = [](const int *ind, int len, int lim) {
     if (!ind) return true;
@@ -827,13 +832,16 @@ static int clumping_common(bsg_bed *h, const int *ind_row, int nr, const int *in
     const int j0 = ordInd[k] - 1;
     int keep_j0 = 1;
     // left neighbours: pairs (j0, j) of j0's own window; right neighbours: j0 is in the window of j
+    // which_to_check (src/clumping-utils.h:12-43): left while pos[j] >= pos[j0] - size, right while pos[j] <= pos[j0] + size
+    const double pos_min = pos[j0] - size, pos_max = pos[j0] + size;
     for (int t = 0; t < w.wlen[j0] && keep_j0; t++) {
       const int j = j0 - 1 - t;
+      if (!(pos[j] >= pos_min)) break;
       if (rank[j] < k && keep[j] == 1 && conflict[(size_t)(w.boff[j0] + t)]) keep_j0 = 0;
     }
     for (int j = j0 + 1; j < nc && keep_j0; j++) {
       const int t = j - 1 - j0;
-      if (t >= w.wlen[j]) break;  // positions are sorted: once j0 leaves the window of j it stays out
+      if (!(pos[j] <= pos_max) || t >= w.wlen[j]) break;  // the union window of j holds every pair either test admits
       if (rank[j] < k && keep[j] == 1 && conflict[(size_t)(w.boff[j] + t)]) keep_j0 = 0;
     }
     keep[j0] = keep_j0;

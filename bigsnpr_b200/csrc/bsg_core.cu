@@ -157,6 +157,53 @@ __global__ void k_synth(uint8_t *__restrict__ A, int64_t strideA, int n, int nco
   }
 }
 
+
+// LD-structured variant ("AR(1) haplotypes within blocks"): same per-(sample, SNP) hash as
+// k_synth, but the two 24-bit allele uniforms of a haplotype are COPIED from the previous SNP with probability rho
+// (a second hash decides, 16 bits per haplotype) unless the SNP starts a block of `ldblock` global columns.  Two
+// neighbouring SNPs that share the uniform carry alleles [u < maf_j] and [u < maf_j'], i.e. r close to 1 for similar
+// allele frequencies: real windows of correlated variants for the clumping / r2-threshold paths.  Integer
+// arithmetic only, so a CPU twin reproduces the matrix bit for bit; rho = 0 is exactly k_synth.
+// One thread = 16 samples x one block of columns, walking the block in order with the 32 states in registers.
+__global__ void k_synth_ld(uint8_t *__restrict__ A, int64_t strideA, int n, int ncols, uint64_t seed,
+                           int64_t col_offset, uint32_t na_thr, uint32_t rho_thr, int ldblock) {
+  const int64_t words = strideA / 4;
+  const int64_t gb0 = col_offset / ldblock;                              // first global block touched
+  const int64_t nblk = (col_offset + ncols + ldblock - 1) / ldblock - gb0;
+  const int64_t total = nblk * words;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = t / words, wq = t - b * words;
+    const int64_t g0 = (gb0 + b) * ldblock;
+    int64_t g1 = g0 + ldblock;
+    if (g1 > col_offset + ncols) g1 = col_offset + ncols;
+    uint32_t u0[16], u1[16];
+#pragma unroll
+    for (int p = 0; p < 16; p++) u0[p] = u1[p] = 0;
+    for (int64_t gj = g0; gj < g1; gj++) {
+      const uint64_t kj = mix64(seed ^ mix64((uint64_t)gj));
+      const double maf = 0.02 + 0.48 * ((double)(kj >> 11) * (1.0 / 9007199254740992.0));
+      const uint32_t thr = (uint32_t)(maf * 16777216.0);
+      const bool first = gj == g0;
+      uint32_t v = 0;
+#pragma unroll
+      for (int p = 0; p < 16; p++) {
+        const int64_t i = wq * 16 + p;
+        const uint64_t hs = mix64(kj + (uint64_t)i * 0xD1342543DE82EF95ull);
+        const uint64_t h2 = mix64(hs ^ 0xA5A5A5A5A5A5A5A5ull);
+        const bool c0 = !first && (uint32_t)(h2 & 0xFFFFu) < rho_thr;
+        const bool c1 = !first && (uint32_t)((h2 >> 16) & 0xFFFFu) < rho_thr;
+        if (!c0) u0[p] = (uint32_t)(hs & 0xFFFFFFu);
+        if (!c1) u1[p] = (uint32_t)((hs >> 24) & 0xFFFFFFu);
+        uint32_t g = (u0[p] < thr) + (u1[p] < thr);
+        if ((uint32_t)((hs >> 48) & 0xFFFFu) < na_thr) g = 3;
+        if (i < n) v |= g << (2 * p);
+      }
+      if (gj >= col_offset) reinterpret_cast<uint32_t *>(A + (gj - col_offset) * strideA)[wq] = v;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // copy A -> copy B (2-bit transpose).  Tile: 128 SNP lines x 128 B (512 samples) in, 512 sample
 // lines x 32 B (128 SNPs) out.  One thread per sample of the tile.
@@ -510,6 +557,30 @@ int bsg_open_synth(int n, int m, uint64_t seed, double na_rate, int64_t col_offs
   uint32_t na_thr = (uint32_t)(na_rate * 65536.0);
   k_synth<<<grid_for((int64_t)m * (h->strideA / 4), 256), 256, 0, h->stream>>>(h->A, h->strideA, n, m, seed, col_offset,
                                                                                na_thr);
+  count_launch();
+  int rc = stage_finish(h);
+  if (rc) {
+    bsg_close(h);
+    return rc;
+  }
+  *out = h;
+  return BSG_OK;
+}
+
+
+int bsg_open_synth_ld(int n, int m, uint64_t seed, double na_rate, int64_t col_offset, double rho, int ld_block,
+                      int device, int layouts, bsg_bed **out) {
+  if (!out) return fail(BSG_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (!(na_rate >= 0 && na_rate < 1)) return fail(BSG_ERR_ARG, "na_rate must be in [0, 1).");
+  if (!(rho >= 0 && rho < 1) || ld_block < 1 || col_offset < 0) return fail(BSG_ERR_ARG, "rho must be in [0, 1), ld_block >= 1.");
+  bsg_bed *h = nullptr;
+  BSG_TRY(alloc_handle(n, m, device, &h));
+  h->layouts = layouts;
+  const uint32_t na_thr = (uint32_t)(na_rate * 65536.0), rho_thr = (uint32_t)(rho * 65536.0);
+  const int64_t nblk = (col_offset + m + ld_block - 1) / ld_block - col_offset / ld_block;
+  k_synth_ld<<<grid_for(nblk * (h->strideA / 4), 128), 128, 0, h->stream>>>(h->A, h->strideA, n, m, seed, col_offset, na_thr,
+                                                                           rho_thr, ld_block);
   count_launch();
   int rc = stage_finish(h);
   if (rc) {

@@ -373,6 +373,8 @@ __global__ void k_grm_weights(const double *__restrict__ center, const double *_
 
 }  // namespace wgram
 
+static thread_local int g_last_nconv = -1;  // converged Ritz values of the last bsg_randomsvd* call on this thread
+
 struct SvdWork {
   double *V = nullptr, *w = nullptr, *tmp = nullptr, *h = nullptr, *S = nullptr, *Y = nullptr, *part = nullptr;
   ~SvdWork() {
@@ -608,8 +610,13 @@ int bsg_randomsvd_ex(bsg_bed *h, const int *ind_row, int nr, const int *ind_col,
   if (v) memcpy(v, Vv.data(), (size_t)nc * k * sizeof(double));
   if (niter) *niter = iters;
   if (nops) *nops = ops;
+  g_last_nconv = (full_space || ncv >= N) ? k : nconv;  // the full space is exact
   return BSG_OK;
 }
+
+// RSpectra::svds (behind big_randomSVD) warns when fewer than k values converged within maxit; the count of the last
+// call on this thread is exposed so the host wrapper can do the same
+int bsg_randomsvd_nconv(void) { return g_last_nconv; }
 
 int bsg_randomsvd(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, const double *center,
                   const double *scale, int k, double tol, int maxit, double *d, double *u, double *v,
@@ -732,7 +739,7 @@ static int tcrossprod_impl(bsg_bed *h, const int *ind_row, int nr, const int *in
   cudaStream_t s = h->stream;
   DevPtrs mem;
   // ---- weights
-  double *d_c, *d_s, *W1, *W2p, *W3, *w2, *d_stats;
+  double *d_c = nullptr, *d_s = nullptr, *W1 = nullptr, *W2p = nullptr, *W3 = nullptr, *w2 = nullptr, *d_stats = nullptr;
   BSG_TRY(mem.alloc(&d_c, nc));
   BSG_TRY(mem.alloc(&d_s, nc));
   BSG_TRY(mem.alloc(&W1, nc));

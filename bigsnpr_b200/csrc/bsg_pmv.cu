@@ -1490,7 +1490,9 @@ int bsg_view_cprodvec_dev(bsg_view *v, const double *x_dev, double *out_dev, voi
   if (!v || !x_dev || !out_dev) return fail(BSG_ERR_ARG, "null argument");
   bsg_bed *h = v->h;
   BSG_TRY(bind_device(h));
-  cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+  // NULL = the legacy default stream (what the header documents and what torch's default stream is): work is then
+  // ordered with the caller's kernels and collectives, not on the handle's private non-blocking stream
+  cudaStream_t s = stream ? (cudaStream_t)stream : cudaStreamLegacy;
   if (v->nc == 0) return BSG_OK;
   using namespace pmv;
   Scal *sc = v->s_scal.as<Scal>();
@@ -1774,7 +1776,9 @@ int bsg_view_prodvec_dev(bsg_view *v, const double *x_dev, double *out_dev, void
   if (!v || !x_dev || !out_dev) return fail(BSG_ERR_ARG, "null argument");
   bsg_bed *h = v->h;
   BSG_TRY(bind_device(h));
-  cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+  // NULL = the legacy default stream (what the header documents and what torch's default stream is): work is then
+  // ordered with the caller's kernels and collectives, not on the handle's private non-blocking stream
+  cudaStream_t s = stream ? (cudaStream_t)stream : cudaStreamLegacy;
   if (v->nr == 0) return BSG_OK;
   if (use_T(h)) return prodvec_T(v, x_dev, out_dev, s);  // transposing kernel over the SNP-major copy
   using namespace pmv;

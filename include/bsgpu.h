@@ -64,6 +64,12 @@ int bsg_open_packed(const uint8_t *packed, int n, int m, int device, int layouts
  * column = col_offset + j), so column shards of one matrix are reproducible on any rank. */
 int bsg_open_synth(int n, int m, uint64_t seed, double na_rate, int64_t col_offset, int device,
                    int layouts, bsg_bed **out);
+/* LD-structured variant of the generator (AR(1)-like haplotype blocks): within every block of
+ * `ld_block` consecutive global columns a haplotype's allele uniform is copied from the previous SNP with probability
+ * `rho`, so neighbouring SNPs are correlated (r2 well above 0) and the clumping / r2-threshold paths have something to
+ * prune.  rho = 0 reproduces bsg_open_synth bit for bit.  Same (seed, global column) keying: shards are reproducible. */
+int bsg_open_synth_ld(int n, int m, uint64_t seed, double na_rate, int64_t col_offset, double rho, int ld_block,
+                      int device, int layouts, bsg_bed **out);
 /* FBM.code256 (bigstatsr, R/bigSNP-class.R:7,13): n x m bytes column-major + 256 doubles.  Codes
  * that round to 0/1/2/NA are repacked to 2 bits at staging and share every kernel (snp_* twins:
  * src/colstats.cpp:8-35, src/corr.cpp:113-118, src/ld-scores.cpp:93-96). */
@@ -94,7 +100,8 @@ int bsg_view_create(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, 
 void bsg_view_destroy(bsg_view *v);
 int bsg_view_prodvec(bsg_view *v, const double *x, double *out);   /* host vectors */
 int bsg_view_cprodvec(bsg_view *v, const double *x, double *out);  /* host vectors */
-/* device-resident vectors, enqueued on `stream` (a cudaStream_t; NULL = default stream); no sync */
+/* device-resident vectors, enqueued on `stream` (a cudaStream_t; NULL = the legacy default stream, i.e. ordered with
+ * everything the caller enqueued on stream 0 -- torch's default stream included); no sync */
 int bsg_view_prodvec_dev(bsg_view *v, const double *x_dev, double *out_dev, void *stream);
 int bsg_view_cprodvec_dev(bsg_view *v, const double *x_dev, double *out_dev, void *stream);
 
@@ -187,6 +194,11 @@ int bsg_tcrossprod_dev(bsg_bed *h, const int *ind_row, int nr, const int *ind_co
 int bsg_randomsvd(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc,
                   const double *center, const double *scale, int k, double tol, int maxit, double *d,
                   double *u, double *v, double *center_out, double *scale_out, int *niter, int *nops);
+
+/* Ritz values that met the stopping rule in the last bsg_randomsvd / bsg_randomsvd_ex call of this thread (k when it
+ * converged; fewer when `maxit` restarts were not enough -- RSpectra::svds warns in that case and so does the host
+ * wrapper); -1 before any call. */
+int bsg_randomsvd_nconv(void);
 
 /* Same iteration for a matrix whose SNP columns are sharded over several handles (one per GPU / rank):
  * every rank calls it with its own shard and the same (ind_row, k, tol).  z_dev is a device buffer of nr

@@ -742,6 +742,46 @@ void orc_synth_packed(int n, int m, uint64_t seed, double na_rate, long long col
   }
 }
 
+/* LD-structured twin of the device generator k_synth_ld (bigsnpr_b200/csrc/bsg_core.cu): inside every block of
+ * `ld_block` global columns a haplotype's 24-bit allele uniform is copied from the previous SNP with probability rho
+ * (16 bits of a second hash per haplotype).  Integer arithmetic only -> the same bytes as the device. */
+void orc_synth_packed_ld(int n, int m, uint64_t seed, double na_rate, long long col_offset, double rho, int ld_block,
+                         uint8_t *out) {
+  static const uint8_t bedcode[4] = {3, 2, 0, 1};
+  size_t n_byte = ((size_t)n + 3) / 4;
+  uint32_t na_thr = (uint32_t)(na_rate * 65536.0), rho_thr = (uint32_t)(rho * 65536.0);
+  long long gb0 = col_offset / ld_block, nblk = (col_offset + m + ld_block - 1) / ld_block - gb0;
+#pragma omp parallel
+  {
+    uint32_t *u = (uint32_t *)malloc((size_t)2 * (n > 0 ? n : 1) * sizeof(uint32_t));
+#pragma omp for schedule(dynamic, 1)
+    for (long long b = 0; b < nblk; b++) {
+      long long g0 = (gb0 + b) * ld_block, g1 = g0 + ld_block;
+      if (g1 > col_offset + m) g1 = col_offset + m;
+      for (long long gj = g0; gj < g1; gj++) {
+        uint64_t kj = orc_mix64(seed ^ orc_mix64((uint64_t)gj));
+        double maf = 0.02 + 0.48 * ((double)(kj >> 11) * (1.0 / 9007199254740992.0));
+        uint32_t thr = (uint32_t)(maf * 16777216.0);
+        int first = gj == g0;
+        uint8_t *col = gj >= col_offset ? out + (size_t)(gj - col_offset) * n_byte : NULL;
+        if (col) memset(col, 0, n_byte);
+        for (int i = 0; i < n; i++) {
+          uint64_t hs = orc_mix64(kj + (uint64_t)i * 0xD1342543DE82EF95ull);
+          uint64_t h2 = orc_mix64(hs ^ 0xA5A5A5A5A5A5A5A5ull);
+          int c0 = !first && (uint32_t)(h2 & 0xFFFFu) < rho_thr;
+          int c1 = !first && (uint32_t)((h2 >> 16) & 0xFFFFu) < rho_thr;
+          if (!c0) u[2 * i] = (uint32_t)(hs & 0xFFFFFFu);
+          if (!c1) u[2 * i + 1] = (uint32_t)((hs >> 24) & 0xFFFFFFu);
+          uint32_t g = (u[2 * i] < thr) + (u[2 * i + 1] < thr);
+          if ((uint32_t)((hs >> 48) & 0xFFFFu) < na_thr) g = 3;
+          if (col) col[i >> 2] |= (uint8_t)(bedcode[g] << (2 * (i & 3)));
+        }
+      }
+    }
+    free(u);
+  }
+}
+
 int orc_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -604,10 +604,17 @@ def snp_clumping(G, infos_chr, ind_row=None, S=None, thr_r2=0.2, size=None, info
     return np.sort(np.concatenate(kept)) if kept else np.zeros(0, dtype=np.int32)
 
 
-def synth_bed(n, m, seed=20250924, na_rate=0.0, col_offset=0) -> "OracleBed":
-    """CPU twin of the device synthetic generator (same counter-based RNG), as an OracleBed."""
+def synth_bed(n, m, seed=20250924, na_rate=0.0, col_offset=0, ld_rho=0.0, ld_block=50) -> "OracleBed":
+    """CPU twin of the device synthetic generator (same counter-based RNG), as an OracleBed.  ld_rho > 0: the
+    LD-structured variant (haplotype blocks of ld_block SNPs, allele uniforms copied with probability ld_rho)."""
     nb = (n + 3) // 4
     out = np.zeros(nb * m, dtype=np.uint8)
+    if ld_rho > 0:
+        f = lib().orc_synth_packed_ld
+        f.restype = None
+        f.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_double, C.c_longlong, C.c_double, C.c_int, C.POINTER(C.c_uint8)]
+        f(int(n), int(m), int(seed), float(na_rate), int(col_offset), float(ld_rho), int(ld_block), _p(out, C.c_uint8))
+        return OracleBed.from_packed(out, n, m)
     f = lib().orc_synth_packed
     f.restype = None
     f.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_double, C.c_longlong, C.POINTER(C.c_uint8)]

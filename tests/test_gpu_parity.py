@@ -637,3 +637,68 @@ def test_sparse_missing_lists_equal_plane_path(B, oracle, obed_na, rng, monkeypa
     svd1 = B.bed_randomSVD(g_list, k=5)
     svd0 = B.bed_randomSVD(g_plane, k=5)
     np.testing.assert_allclose(svd1["d"], svd0["d"], rtol=1e-12)
+
+
+def test_snp_colstats_direct_with_missing(B, oracle, rng):
+    """src/colstats.cpp:8-35 on an FBM.code256 handle, compared with the oracle directly: no NA handling, so a column with
+    a missing code propagates NaN to sumX and denoX (x += NA_real in the reference); clean columns are bit-equal.  Row and
+    column multisets included (tests/testthat/test-2-bed-clumping-SVD.R:21-27 uses snp_colstats through snp_clumping)."""
+    n, m = 733, 411
+    G = rng.integers(0, 3, size=(n, m)).astype(np.uint8)
+    na_cols = rng.choice(m, 60, replace=False)
+    for j in na_cols:
+        G[rng.choice(n, rng.integers(1, 20), replace=False), j] = 3
+    gf, of = B.Bed.from_fbm(G), oracle.OracleFBM(G)
+    cases = [(gf.rows_along(), gf.cols_along()),
+             (rng.choice(n, 300, replace=False).astype(np.int32) + 1, rng.choice(m, 200, replace=False).astype(np.int32) + 1),
+             (rng.integers(1, n + 1, size=500).astype(np.int32), rng.integers(1, m + 1, size=500).astype(np.int32))]
+    for ir, ic in cases:
+        got = B.snp_colstats(gf, ir, ic)
+        want = oracle.snp_colstats(of, ir, ic)
+        for key in ("sumX", "denoX"):
+            assert np.array_equal(np.isnan(got[key]), np.isnan(want[key])), key
+            ok = ~np.isnan(want[key])
+            assert np.array_equal(got[key][ok], want[key][ok]), key
+        # a column is NaN exactly when one of its selected rows is missing
+        has_na = (G[np.ix_(ir - 1, ic - 1)] == 3).any(axis=0)
+        assert np.array_equal(np.isnan(got["sumX"]), has_na)
+    # snp_MAF / snp_scaleBinom on the same statistics (R/binom-scaling.R:62-106)
+    clean = np.setdiff1d(np.arange(m), na_cols)[:50].astype(np.int32) + 1
+    af = oracle.snp_colstats(of, of.rows_along(), clean)["sumX"] / (2 * n)
+    assert np.array_equal(B.snp_MAF(gf, ind_col=clean), np.minimum(af, 1 - af))
+    sc = B.snp_scaleBinom()(gf, ind_col=clean)
+    sco = oracle.snp_scaleBinom(of, None, clean)
+    assert np.array_equal(sc["center"], sco["center"]) and np.array_equal(sc["scale"], sco["scale"])
+    gf.close()
+
+
+def test_ld_structured_generator_matches_its_twins(B, oracle):
+    """bsg_open_synth_ld == the NumPy mirror == the oracle's C twin, bit for bit; shards by global column; rho = 0 is the
+    i.i.d. generator; neighbouring SNPs inside a block are really correlated."""
+    from tests.synth_ref import synth_matrix, synth_matrix_ld
+
+    n, m = 1003, 237
+    for na_rate, off in ((0.0, 0), (0.03, 33)):
+        g = B.Bed.synthetic(n, m, seed=9, na_rate=na_rate, col_offset=off, ld_rho=0.9, ld_block=50)
+        G = synth_matrix_ld(n, m, seed=9, na_rate=na_rate, col_offset=off, rho=0.9, ld_block=50)
+        o = oracle.OracleBed.from_packed(g.export_packed(), n, m)
+        assert np.array_equal(oracle.decode_dense(o), G)
+        o2 = oracle.synth_bed(n, m, seed=9, na_rate=na_rate, col_offset=off, ld_rho=0.9, ld_block=50)
+        assert np.array_equal(oracle.decode_dense(o2), G)
+        g.close()
+    import ctypes as C
+
+    from bigsnpr_b200 import _lib
+
+    h = C.c_void_p()
+    _lib.check(_lib.lib().bsg_open_synth_ld(n, m, 9, 0.02, 5, 0.0, 50, 0, 0, C.byref(h)))
+    g0 = B.Bed(_handle=h, _shape=(n, m))
+    assert np.array_equal(oracle.decode_dense(oracle.OracleBed.from_packed(g0.export_packed(), n, m)),
+                          synth_matrix(n, m, seed=9, na_rate=0.02, col_offset=5))
+    g0.close()
+    big = B.Bed.synthetic(20000, 200, seed=2, ld_rho=0.9, ld_block=50)
+    p, i, x = B.bed_cor(big, size=1, thr_r2=0.0)  # adjacent pairs only (1 kb = 1 SNP)
+    adj = np.array([x[p[j]] for j in range(1, 200) if p[j + 1] - p[j] == 2])
+    inside = np.array([j % 50 != 0 for j in range(1, 200) if p[j + 1] - p[j] == 2])
+    assert np.mean(adj[inside] ** 2) > 0.2 and np.mean(adj[~inside] ** 2) < 0.01
+    big.close()
