@@ -276,10 +276,19 @@ def run_workload(args, wl_key, torch, dist, B, L, rank, world, local, with_cpu, 
     stream = torch.cuda.current_stream(dev).cuda_stream
     assert stream != 0
 
+    comm = None
+    if world > 1 and not args.nccl:
+        from bigsnpr_b200.dist import Comm
+
+        comm = Comm(n, device=local)  # NVLink peer-memory communicator of the library: reduction fused into the epilogue
+
     def step():
-        view.prodvec_dev(x.data_ptr(), out.data_ptr(), stream)
-        if world > 1:
-            dist.all_reduce(out)
+        if comm is not None:
+            comm.prodvec_allreduce(view, x.data_ptr(), out.data_ptr(), stream)
+        else:
+            view.prodvec_dev(x.data_ptr(), out.data_ptr(), stream)
+            if world > 1:
+                dist.all_reduce(out)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -432,7 +441,11 @@ def run_workload(args, wl_key, torch, dist, B, L, rank, world, local, with_cpu, 
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        if world > 1:
+        if comm is not None:
+            from bigsnpr_b200.dist import randomsvd_comm
+
+            sv = randomsvd_comm(g, comm, m_total, k=k)
+        elif world > 1:
             from bigsnpr_b200.dist import randomsvd_sharded
 
             sv = randomsvd_sharded(g, m_total, k=k)
@@ -449,11 +462,19 @@ def run_workload(args, wl_key, torch, dist, B, L, rank, world, local, with_cpu, 
                     "note": "bed_randomSVD(fun.scaling = bed_scaleBinom, k = %d), Lanczos on the device; wall time includes "
                             "the scaling pass, the iteration and the k products for v" % k}
 
+    if comm is not None:
+        comm.check()
+        torch.cuda.synchronize()
+        dist.barrier()
+        comm.close()
     view.close()
     g.close()
     if rank != 0:
         return None
-    par = "1 GPU" if world == 1 else ("snp-column shards over %d GPUs, 1 all-reduce of n doubles per step" % world)
+    par = "1 GPU" if world == 1 else (
+        "snp-column shards over %d GPUs; per step the n-vector of partial products is summed %s" % (
+            world, "inside the X.y epilogue kernel over NVLink peer memory (k_ar_oneshot, no NCCL, no host hop)"
+            if comm is not None else "by one NCCL all-reduce"))
     return {
         "value": value, "ms_per_step": ms / args.steps, "scaling": wl["scaling"],
         "config": {"workload": wl["name"], "n": n, "m_total": m_total, "m_per_gpu": m_loc, "na_rate": args.na_rate,
@@ -483,6 +504,8 @@ def main():
     ap.add_argument("--layout", choices=("auto", "both", "snp"), default="auto",
                     help="snp: the SNP-major copy only (the library's default; X.y on k_pmvT); both: also the sample-major "
                          "copy (X.y on k_pmv); auto: snp for cfg5 (134 GB), both for cfg2")
+    ap.add_argument("--nccl", action="store_true", help="N > 1: reduce with torch.distributed / NCCL instead of the library's "
+                                                       "own peer-memory communicator (the baseline it is measured against)")
     ap.add_argument("--no-single-copy", action="store_true", help="skip the extra leg timing X.y on the SNP-major copy alone")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

@@ -71,6 +71,30 @@ SIGNATURES = {
                                    C.c_int, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, c_int_p, c_int_p, vp, vp, vp,
                                    C.c_int]),
     "bsg_randomsvd_nconv": (C.c_int, []),
+    "bsg_group_open_bed": (C.c_int, [C.c_char_p, C.c_int, C.c_int, c_int_p, C.c_int, C.c_int, C.POINTER(vp)]),
+    "bsg_group_open_synth": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_double, C.c_double, C.c_int, c_int_p, C.c_int, C.c_int,
+                                       C.POINTER(vp)]),
+    "bsg_group_close": (None, [vp]),
+    "bsg_group_ndev": (C.c_int, [vp]),
+    "bsg_group_nrow": (C.c_int, [vp]),
+    "bsg_group_ncol": (C.c_int, [vp]),
+    "bsg_group_shard": (vp, [vp, C.c_int]),
+    "bsg_group_shard_begin": (C.c_int, [vp, C.c_int]),
+    "bsg_group_prodvec": (C.c_int, [vp, c_int_p, C.c_int, c_int_p, C.c_int, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p]),
+    "bsg_group_cprodvec": (C.c_int, [vp, c_int_p, C.c_int, c_int_p, C.c_int, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p]),
+    "bsg_group_randomsvd": (C.c_int, [vp, c_int_p, C.c_int, c_int_p, C.c_int, c_dbl_p, c_dbl_p, C.c_int, C.c_double, C.c_int,
+                                      c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, c_int_p, c_int_p]),
+    "bsg_group_tcrossprod": (C.c_int, [vp, c_int_p, C.c_int, c_int_p, C.c_int, c_dbl_p, c_dbl_p, c_dbl_p]),
+    "bsg_comm_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.POINTER(vp), c_u8_p]),
+    "bsg_comm_connect": (C.c_int, [vp, c_u8_p]),
+    "bsg_comm_destroy": (None, [vp]),
+    "bsg_comm_rank": (C.c_int, [vp]),
+    "bsg_comm_world": (C.c_int, [vp]),
+    "bsg_comm_check": (C.c_int, [vp]),
+    "bsg_comm_allreduce_dev": (C.c_int, [vp, vp, C.c_int64, vp]),
+    "bsg_view_prodvec_allreduce_dev": (C.c_int, [vp, vp, vp, vp, vp]),
+    "bsg_randomsvd_comm": (C.c_int, [vp, vp, c_int_p, C.c_int, c_int_p, C.c_int, c_dbl_p, c_dbl_p, C.c_int, C.c_int, C.c_double,
+                                     C.c_int, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, c_int_p, c_int_p]),
     "bsg_launch_count": (C.c_int64, []),
     "bsg_last_kernel_ms": (C.c_double, []),
     "bsg_set_kernel_timing": (C.c_int, [C.c_int]),

@@ -209,6 +209,119 @@ class Bed:
         return read_bed(self, ind_row, ind_col)
 
 
+class Group:
+    """One matrix sharded by SNP columns over several GPUs driven by THIS process (bsg_group) -- the
+    multi-GPU form an R session uses.  `ind_col` is global and 1-based like everywhere else; the library buckets it by
+    owning device.  X.y ends in a sum over the devices done inside the epilogue kernel over NVLink peer memory."""
+
+    def __init__(self, _handle):
+        self._g = _handle
+        L = lib()
+        self.nrow, self.ncol, self.ndev = int(L.bsg_group_nrow(_handle)), int(L.bsg_group_ncol(_handle)), int(L.bsg_group_ndev(_handle))
+
+    @classmethod
+    def open(cls, bedfile, devices, nrow=None, ncol=None, layouts=LAYOUT_AUTO):
+        bedfile = os.path.expanduser(bedfile)
+        pre = bedfile[:-4] if bedfile.endswith(".bed") else bedfile
+        n = _count_lines(pre + ".fam") if nrow is None else int(nrow)
+        m = _count_lines(pre + ".bim") if ncol is None else int(ncol)
+        dv = _i32(devices)
+        g = C.c_void_p()
+        check(lib().bsg_group_open_bed(bedfile.encode(), n, m, _pi(dv), dv.size, int(layouts), C.byref(g)))
+        return cls(g)
+
+    @classmethod
+    def synthetic(cls, n, m, devices, seed=20250924, na_rate=0.0, ld_rho=0.0, ld_block=50, layouts=LAYOUT_AUTO):
+        dv = _i32(devices)
+        g = C.c_void_p()
+        check(lib().bsg_group_open_synth(int(n), int(m), int(seed), float(na_rate), float(ld_rho), int(ld_block), _pi(dv),
+                                         dv.size, int(layouts), C.byref(g)))
+        return cls(g)
+
+    def shard(self, i):
+        """The per-device handle as a (non-owning) Bed plus its first global column (0-based)."""
+        h = lib().bsg_group_shard(self._g, int(i))
+        b0, b1 = lib().bsg_group_shard_begin(self._g, int(i)), lib().bsg_group_shard_begin(self._g, int(i) + 1)
+        b = Bed(_handle=C.c_void_p(h), _shape=(self.nrow, b1 - b0))
+        b.close = lambda: None  # owned by the group
+        return b, b0
+
+    def rows_along(self):
+        return np.arange(1, self.nrow + 1, dtype=np.int32)
+
+    def cols_along(self):
+        return np.arange(1, self.ncol + 1, dtype=np.int32)
+
+    def _args(self, ind_row, ind_col, center, scale):
+        ir = None if ind_row is ... else _i32(ind_row)
+        ic = None if ind_col is ... else _i32(ind_col)
+        nr = self.nrow if ir is None else ir.size
+        nc = self.ncol if ic is None else ic.size
+        if (center is None) != (scale is None):
+            raise ValueError("center and scale must be given together")
+        if center is not None:
+            center, scale = _f64(center), _f64(scale)
+            if center.size != nc or scale.size != nc:
+                raise ValueError(ERROR_DIM)
+        return ir, nr, ic, nc, center, scale
+
+    def prodVec(self, y_col, ind_row=..., ind_col=..., center=None, scale=None):
+        ir, nr, ic, nc, center, scale = self._args(ind_row, ind_col, center, scale)
+        y_col = _f64(y_col)
+        if y_col.size != nc:
+            raise ValueError(ERROR_DIM)
+        out = np.empty(nr)
+        check(lib().bsg_group_prodvec(self._g, _pi(ir), nr, _pi(ic), nc, _pd(center), _pd(scale), _pd(y_col), _pd(out)))
+        return out
+
+    def cprodVec(self, y_row, ind_row=..., ind_col=..., center=None, scale=None):
+        ir, nr, ic, nc, center, scale = self._args(ind_row, ind_col, center, scale)
+        y_row = _f64(y_row)
+        if y_row.size != nr:
+            raise ValueError(ERROR_DIM)
+        out = np.empty(nc)
+        check(lib().bsg_group_cprodvec(self._g, _pi(ir), nr, _pi(ic), nc, _pd(center), _pd(scale), _pd(y_row), _pd(out)))
+        return out
+
+    def randomSVD(self, ind_row=..., ind_col=..., center=None, scale=None, k=10, tol=1e-4, maxit=1000):
+        """bed_randomSVD (binomial scaling computed per shard when center / scale are not given)."""
+        ir, nr, ic, nc, center, scale = self._args(ind_row, ind_col, center, scale)
+        d, u, v = np.empty(k), np.empty((k, nr)), np.empty((k, nc))
+        c_out, s_out = np.empty(nc), np.empty(nc)
+        niter, nops = C.c_int(0), C.c_int(0)
+        check(lib().bsg_group_randomsvd(self._g, _pi(ir), nr, _pi(ic), nc, _pd(center), _pd(scale), int(k), float(tol),
+                                        int(maxit), _pd(d), _pd(u), _pd(v), _pd(c_out), _pd(s_out), C.byref(niter),
+                                        C.byref(nops)))
+        return {"d": d, "u": u.T, "v": v.T, "niter": niter.value, "nops": nops.value, "center": c_out, "scale": s_out}
+
+    def tcrossprodSelf(self, center, scale, ind_row=..., ind_col=...):
+        ir, nr, ic, nc, center, scale = self._args(ind_row, ind_col, center, scale)
+        K = np.empty((nr, nr))
+        check(lib().bsg_group_tcrossprod(self._g, _pi(ir), nr, _pi(ic), nc, _pd(center), _pd(scale), _pd(K)))
+        return K
+
+    def scaleBinom(self, ind_row=...):
+        """bed_scaleBinom over all columns: per-shard statistics concatenated (a gather)."""
+        cs, ss = [], []
+        for i in range(self.ndev):
+            b, _ = self.shard(i)
+            sc = bed_scaleBinom(b, ind_row)
+            cs.append(sc["center"])
+            ss.append(sc["scale"])
+        return {"center": np.concatenate(cs), "scale": np.concatenate(ss)}
+
+    def close(self):
+        if self._g is not None:
+            lib().bsg_group_close(self._g)
+            self._g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def bed(bedfile, **kw):
     """Wrapper constructor (R/bed-class.R:146)."""
     return Bed(bedfile, **kw)

@@ -53,6 +53,26 @@ struct DevBuf {
 
 }  // namespace bsg
 
+#define BSG_MAX_PEERS 16
+
+// One rank's end of a group of GPUs that exchange data through each other's memory over NVLink / NVSwitch (peer access
+// inside one process, CUDA IPC between processes).  Region layout (same on every rank):
+//   [0, 1024)        push flags: flag[q] = last epoch whose data rank q has finished writing into THIS region
+//   [1024, 2048)     barrier flags, same convention
+//   [2048, 2112)     block counter of the fused kernels (+ padding)
+//   [4096, ...)      slots: 2 parities x world x slot_elems doubles; slot (p, q) receives rank q's vector of epoch parity p
+struct bsg_comm {
+  int rank = 0, world = 1, device = 0;
+  size_t slot_elems = 0;
+  uint8_t *region = nullptr;
+  size_t region_bytes = 0;
+  uint8_t *peer[BSG_MAX_PEERS] = {nullptr};  // peer[q]: rank q's region mapped into this device's address space
+  bool peer_ipc[BSG_MAX_PEERS] = {false};    // opened with cudaIpcOpenMemHandle (to be closed)
+  unsigned long long epoch = 0, bar_epoch = 0;
+  int *d_err = nullptr;                      // set by a kernel whose wait timed out
+  bool connected = false;
+};
+
 struct bsg_bed {
   int kind = BSG_KIND_BED;
   int device = 0;
@@ -134,6 +154,31 @@ int wgram5_launch(const uint8_t *P, int64_t stride, int nlines, int nslices, con
 
 // ---- bsg_pmv.cu: packed matrix x vector on the integer tensor pipe ----------------------------
 struct PmvPlan;  // opaque, owned by a view
+namespace pmv { struct Scal; }
+// X~ x enqueued on `s`; with a communicator the partial n-vectors of the column shards are summed (fused epilogue)
+int view_prodvec_comm(bsg_view *v, const double *x_dev, double *out_dev, cudaStream_t s, bsg_comm *comm);
+
+// ---- bsg_la.cu: the Lanczos driver over one or several column shards (one replica of the recurrence per shard) ----
+struct SvdShard {
+  bsg_bed *h;
+  const int *ind_col;              // local 1-based columns of this shard (null = all)
+  int nc;
+  const double *center, *scale;    // per local column, or null (bed_scaleBinom computed on the device)
+  bsg_comm *comm;                  // null: single shard
+  double *v_out;                   // host, receives this shard's rows of v (null: not wanted)
+  int64_t v_ld;                    // leading dimension of v_out
+  const int *v_pos;                // row of v_out per local column (null: 0..nc-1)
+  double *center_out, *scale_out;  // optional, indexed like the rows of v_out
+};
+int lanczos_svd(std::vector<SvdShard> &sh, const int *ind_row, int nr, int ncol_total, int k, double tol, int maxit, double *d,
+                double *u, int *niter, int *nops, double *z_dev, bsg_reduce_cb reduce_cb, void *cb_ctx);
+
+// ---- bsg_comm.cu: collectives over NVLink peer memory ------------------------------------------------
+// epilogue of X.y (integer slice sums -> fp64) fused with the all-reduce over the shards: one kernel
+int comm_finish_prod_allreduce(bsg_comm *c, const long long *part, int nlines, const pmv::Scal *sc, int has_scaling,
+                               int use_na, double *out_dev, cudaStream_t s);
+// in-place sum of `count` doubles over the ranks (one-shot: push to every peer, sum in rank order)
+int comm_allreduce_oneshot(bsg_comm *c, double *buf_dev, int64_t count, cudaStream_t s);
 }  // namespace bsg
 
 struct bsg_view {

@@ -375,166 +375,227 @@ __global__ void k_grm_weights(const double *__restrict__ center, const double *_
 
 static thread_local int g_last_nconv = -1;  // converged Ritz values of the last bsg_randomsvd* call on this thread
 
+// ---- device-side bookkeeping of the recurrence: no host round trip between two operator applications ----------------
+// column j of the projected matrix T gets the Gram-Schmidt coefficients (two passes: set, then add)
+__global__ void k_tcol(const double *__restrict__ hcoef, int cnt, double *__restrict__ tcol, int add) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cnt) tcol[i] = add ? tcol[i] + hcoef[i] : hcoef[i];
+}
+// scal[0] = |w| (the next off-diagonal entry, kept as beta of the last step), scal[1] = 1 / |w| (0 if w == 0)
+__global__ void k_norm_step(const double *__restrict__ h0, double *__restrict__ T, int ncv, int j, double *__restrict__ scal) {
+  const double nrm = sqrt(h0[0]);
+  scal[0] = nrm;
+  scal[1] = nrm > 0 ? 1.0 / nrm : 0.0;
+  if (j >= 0 && j + 1 < ncv) T[(size_t)(j + 1) * ncv + j] = nrm;
+}
+__global__ void k_scale_copy_p(const double *__restrict__ src, const double *__restrict__ alpha, int N, double *__restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) dst[i] = src[i] * alpha[0];
+}
+
 struct SvdWork {
-  double *V = nullptr, *w = nullptr, *tmp = nullptr, *h = nullptr, *S = nullptr, *Y = nullptr, *part = nullptr;
-  ~SvdWork() {
-    void *p[] = {V, w, tmp, h, S, Y, part};
+  double *V = nullptr, *w = nullptr, *tmp = nullptr, *h = nullptr, *S = nullptr, *Y = nullptr, *part = nullptr, *T = nullptr,
+         *scal = nullptr, *other = nullptr;
+  void release() {
+    void *p[] = {V, w, tmp, h, S, Y, part, T, scal, other};
     for (void *q : p)
       if (q) cudaFree(q);
+    V = w = tmp = h = S = Y = part = T = scal = other = nullptr;
   }
 };
 
-}  // namespace bsg
 
-using namespace bsg;
-
-extern "C" {
-
-// Extended form used by the multi-GPU host: `z_dev` (nr doubles, optional) is the buffer that holds the
-// n-vector of partial products; after every local A (A^T x) the library synchronises its stream and calls
-// reduce_cb(ctx), which must sum z_dev across ranks (e.g. NCCL all-reduce) and return once the sum is visible.
-int bsg_randomsvd_ex(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, const double *center,
-                     const double *scale, int k, double tol, int maxit, double *d, double *u, double *v,
-                     double *center_out, double *scale_out, int *niter, int *nops, double *z_dev,
-                     bsg_reduce_cb reduce_cb, void *ctx, int ncol_total) {
-  if (!h || !d) return fail(BSG_ERR_ARG, "null argument");
-  BSG_TRY(bind_device(h));
-  if (!ind_row) nr = h->n;
-  if (!ind_col) nc = h->m;
-  const int mtot = reduce_cb ? ncol_total : nc;  // columns of the whole (sharded) matrix
+// Thick-restart Lanczos on the Gram operator of X~ (see the header of this file), written over a LIST of column shards:
+// one replica of the recurrence per shard / device, all fed the same bits (the fused X.y + all-reduce sums in rank order), so
+// the replicas stay identical and only shard 0's projected matrix is read back -- once per restart, which is the only host
+// synchronisation of the iteration.  One shard without communicator = the single-GPU bed_randomSVD.
+int lanczos_svd(std::vector<SvdShard> &sh, const int *ind_row, int nr, int ncol_total, int k, double tol, int maxit, double *d,
+                double *u, int *niter, int *nops, double *z_dev, bsg_reduce_cb reduce_cb, void *cb_ctx) {
+  const int G = (int)sh.size();
+  if (G < 1 || !d) return fail(BSG_ERR_ARG, "null argument");
+  if (!ind_row) nr = sh[0].h->n;
+  const bool sharded = G > 1 || sh[0].comm != nullptr || reduce_cb != nullptr;
+  const int mtot = sharded ? ncol_total : sh[0].nc;
   if (k < 1 || k > std::min(nr, mtot)) return fail(BSG_ERR_ARG, "k must be in 1..min(n, m).");
   if (tol <= 0) tol = 1e-4;
   if (maxit <= 0) maxit = 1000;
-  cudaStream_t s = h->stream;
+
+  struct Rep {  // one replica
+    bsg_view *view = nullptr;
+    SvdWork W;
+    double *wv = nullptr;
+    cudaStream_t s = nullptr;
+    std::vector<double> cen, sca;
+  };
+  std::vector<Rep> rep(G);
+  struct Cleanup {
+    std::vector<Rep> &r;
+    std::vector<SvdShard> &sh;
+    ~Cleanup() {
+      for (size_t g = 0; g < r.size(); g++) {
+        cudaSetDevice(sh[g].h->device);
+        cudaStreamSynchronize(r[g].s);
+        if (r[g].view) bsg_view_destroy(r[g].view);
+        r[g].W.release();
+      }
+    }
+  } cleanup{rep, sh};
 
   // ---- scaling: default bed_scaleBinom (R/binom-scaling.R:133-142), same fp64 formulas on the same integers
-  std::vector<double> cen(nc), sca(nc);
-  if (center && scale) {
-    memcpy(cen.data(), center, (size_t)nc * sizeof(double));
-    memcpy(sca.data(), scale, (size_t)nc * sizeof(double));
-  } else {
-    std::vector<double> sumX(nc), denoX(nc);
-    std::vector<int> nona(nc);
-    int n_bad = 0;
-    BSG_TRY(bsg_colstats(h, ind_row, nr, ind_col, nc, sumX.data(), denoX.data(), nona.data(), &n_bad));
-    for (int j = 0; j < nc; j++) {
-      double af = sumX[j] / (2.0 * (double)nona[j]);
-      cen[j] = 2.0 * af;
-      sca[j] = sqrt(2.0 * af * (1.0 - af));
+  for (int g = 0; g < G; g++) {
+    bsg_bed *h = sh[g].h;
+    BSG_TRY(bind_device(h));
+    rep[g].s = h->stream;
+    const int nc = sh[g].nc;
+    rep[g].cen.resize(std::max(nc, 1));
+    rep[g].sca.resize(std::max(nc, 1));
+    if (sh[g].center && sh[g].scale) {
+      memcpy(rep[g].cen.data(), sh[g].center, (size_t)nc * sizeof(double));
+      memcpy(rep[g].sca.data(), sh[g].scale, (size_t)nc * sizeof(double));
+    } else if (nc > 0) {
+      std::vector<double> sumX(nc), denoX(nc);
+      std::vector<int> nona(nc);
+      int n_bad = 0;
+      BSG_TRY(bsg_colstats(h, ind_row, nr, sh[g].ind_col, nc, sumX.data(), denoX.data(), nona.data(), &n_bad));
+      for (int j = 0; j < nc; j++) {
+        double af = sumX[j] / (2.0 * (double)nona[j]);
+        rep[g].cen[j] = 2.0 * af;
+        rep[g].sca[j] = sqrt(2.0 * af * (1.0 - af));
+      }
     }
+    for (int j = 0; j < nc; j++) {
+      const int64_t row = sh[g].v_pos ? sh[g].v_pos[j] : j;
+      if (sh[g].center_out) sh[g].center_out[row] = rep[g].cen[j];
+      if (sh[g].scale_out) sh[g].scale_out[row] = rep[g].sca[j];
+    }
+    BSG_TRY(bsg_view_create(h, ind_row, nr, sh[g].ind_col, nc, rep[g].cen.data(), rep[g].sca.data(), &rep[g].view));
   }
-  if (center_out) memcpy(center_out, cen.data(), (size_t)nc * sizeof(double));
-  if (scale_out) memcpy(scale_out, sca.data(), (size_t)nc * sizeof(double));
-
-  bsg_view *view = nullptr;
-  BSG_TRY(bsg_view_create(h, ind_row, nr, ind_col, nc, cen.data(), sca.data(), &view));
-  struct ViewGuard {
-    bsg_view *v;
-    ~ViewGuard() { bsg_view_destroy(v); }
-  } guard{view};
 
   // operator side: the smaller Gram matrix; a sharded matrix always iterates on the sample side
-  const bool row_side = reduce_cb ? true : (nr <= nc);
-  const int N = row_side ? nr : nc, Mo = row_side ? nc : nr;
+  const bool row_side = sharded ? true : (nr <= sh[0].nc);
+  const int N = row_side ? nr : sh[0].nc;
   int ncv = std::max(2 * k + 1, 20);
   ncv = std::min(ncv, std::min(nr, mtot));
   if (ncv <= k) ncv = std::min(k + 1, std::min(nr, mtot));
   const bool full_space = ncv <= k;  // degenerate: k == min(n, m)
-
-  SvdWork W;
   const int64_t ld = N;
-  BSG_CUDA(cudaMalloc((void **)&W.V, (size_t)ld * (ncv + 1) * sizeof(double)));
-  BSG_CUDA(cudaMalloc((void **)&W.tmp, (size_t)std::max(Mo, 1) * sizeof(double)));
-  BSG_CUDA(cudaMalloc((void **)&W.h, (size_t)(ncv + 2) * sizeof(double)));
-  BSG_CUDA(cudaMalloc((void **)&W.S, (size_t)ncv * ncv * sizeof(double)));
-  BSG_CUDA(cudaMalloc((void **)&W.Y, (size_t)ld * ncv * sizeof(double)));
-  const int NSPLIT = 32;
-  BSG_CUDA(cudaMalloc((void **)&W.part, (size_t)(ncv + 2) * NSPLIT * sizeof(double)));
-  auto dots = [&](const double *Vp, int cnt, const double *wp) {  // W.h[j] = <V[:, j], w>, deterministic
-    dim3 g(NSPLIT, cnt);
-    k_dots_part<<<g, 256, 0, s>>>(Vp, ld, cnt, wp, N, NSPLIT, W.part);
-    k_dots_final<<<(cnt + 63) / 64, 64, 0, s>>>(W.part, cnt, NSPLIT, W.h);
-    count_launch(2);
-  };
-  double *wv = nullptr;  // work vector of length N; the caller's buffer when results are reduced across ranks
-  if (reduce_cb && z_dev) {
-    wv = z_dev;
-  } else {
-    BSG_CUDA(cudaMalloc((void **)&W.w, (size_t)N * sizeof(double)));
-    wv = W.w;
+  const int NSPLIT = 32, TB = 256;
+  auto gblocks = [&](int len) { return (len + TB - 1) / TB; };
+
+  for (int g = 0; g < G; g++) {
+    BSG_TRY(bind_device(sh[g].h));
+    SvdWork &W = rep[g].W;
+    const int Mo = row_side ? sh[g].nc : nr;
+    BSG_CUDA(cudaMalloc((void **)&W.V, (size_t)ld * (ncv + 1) * sizeof(double)));
+    BSG_CUDA(cudaMalloc((void **)&W.tmp, (size_t)std::max(Mo, 1) * sizeof(double)));
+    BSG_CUDA(cudaMalloc((void **)&W.other, (size_t)std::max(Mo, 1) * sizeof(double)));
+    BSG_CUDA(cudaMalloc((void **)&W.h, (size_t)(ncv + 2) * sizeof(double)));
+    BSG_CUDA(cudaMalloc((void **)&W.S, (size_t)ncv * ncv * sizeof(double)));
+    BSG_CUDA(cudaMalloc((void **)&W.Y, (size_t)ld * ncv * sizeof(double)));
+    BSG_CUDA(cudaMalloc((void **)&W.part, (size_t)(ncv + 2) * NSPLIT * sizeof(double)));
+    BSG_CUDA(cudaMalloc((void **)&W.T, (size_t)ncv * ncv * sizeof(double)));
+    BSG_CUDA(cudaMalloc((void **)&W.scal, 4 * sizeof(double)));
+    BSG_CUDA(cudaMemsetAsync(W.T, 0, (size_t)ncv * ncv * sizeof(double), rep[g].s));
+    if (reduce_cb && z_dev && g == 0) {
+      rep[g].wv = z_dev;  // the caller's buffer: results are reduced across ranks by the callback
+    } else {
+      BSG_CUDA(cudaMalloc((void **)&W.w, (size_t)N * sizeof(double)));
+      rep[g].wv = W.w;
+    }
   }
 
   int ops = 0;
-  auto apply = [&](const double *x, double *out) -> int {  // out = H x
-    if (row_side) {
-      BSG_TRY(bsg_view_cprodvec_dev(view, x, W.tmp, s));
-      BSG_TRY(bsg_view_prodvec_dev(view, W.tmp, out, s));
-    } else {
-      BSG_TRY(bsg_view_prodvec_dev(view, x, W.tmp, s));
-      BSG_TRY(bsg_view_cprodvec_dev(view, W.tmp, out, s));
-    }
-    if (reduce_cb) {
-      BSG_CUDA(cudaStreamSynchronize(s));
-      reduce_cb(ctx);
+  // every step below is enqueued on all replicas before the host moves on: the fused reductions of the replicas meet on
+  // the devices, never on the host
+  auto dots = [&](int g, const double *Vp, int cnt, const double *wp) {  // W.h[j] = <V[:, j], w>, deterministic
+    SvdWork &W = rep[g].W;
+    dim3 grd(NSPLIT, cnt);
+    k_dots_part<<<grd, 256, 0, rep[g].s>>>(Vp, ld, cnt, wp, N, NSPLIT, W.part);
+    k_dots_final<<<(cnt + 63) / 64, 64, 0, rep[g].s>>>(W.part, cnt, NSPLIT, W.h);
+    count_launch(2);
+  };
+  auto apply = [&](int col) -> int {  // wv = H V[:, col]
+    for (int g = 0; g < G; g++) {
+      BSG_TRY(bind_device(sh[g].h));
+      SvdWork &W = rep[g].W;
+      cudaStream_t s = rep[g].s;
+      const double *x = W.V + (int64_t)col * ld;
+      if (row_side) {
+        if (sh[g].nc > 0) BSG_TRY(bsg_view_cprodvec_dev(rep[g].view, x, W.tmp, s));
+        BSG_TRY(view_prodvec_comm(rep[g].view, W.tmp, rep[g].wv, s, sh[g].comm));
+      } else {
+        BSG_TRY(bsg_view_prodvec_dev(rep[g].view, x, W.tmp, s));
+        BSG_TRY(bsg_view_cprodvec_dev(rep[g].view, W.tmp, rep[g].wv, s));
+      }
+      if (reduce_cb) {
+        BSG_CUDA(cudaStreamSynchronize(s));
+        reduce_cb(cb_ctx);
+      }
     }
     ops++;
     return BSG_OK;
   };
-  std::vector<double> hh(ncv + 2);
-  const int TB = 256;
-  auto gblocks = [&](int len) { return (len + TB - 1) / TB; };
-  // orthogonalise wv against V[:, 0..cnt) (classical Gram-Schmidt, applied twice), returns coefficients and norm
-  auto orth = [&](int cnt, std::vector<double> &coef, double &nrm) -> int {
-    coef.assign(cnt, 0.0);
-    for (int pass = 0; pass < 2 && cnt > 0; pass++) {
-      dots(W.V, cnt, wv);
-      k_axpys<<<gblocks(N), TB, 0, s>>>(W.V, ld, cnt, W.h, N, wv);
+  // orthogonalise wv against V[:, 0..cnt) (classical Gram-Schmidt, applied twice); coefficients -> column j of T, norm -> scal
+  auto orth = [&](int cnt, int j) -> int {
+    for (int g = 0; g < G; g++) {
+      BSG_TRY(bind_device(sh[g].h));
+      SvdWork &W = rep[g].W;
+      cudaStream_t s = rep[g].s;
+      for (int pass = 0; pass < 2 && cnt > 0; pass++) {
+        dots(g, W.V, cnt, rep[g].wv);
+        k_axpys<<<gblocks(N), TB, 0, s>>>(W.V, ld, cnt, W.h, N, rep[g].wv);
+        if (j >= 0) k_tcol<<<(cnt + 63) / 64, 64, 0, s>>>(W.h, cnt, W.T + (size_t)j * ncv, pass);
+        count_launch(j >= 0 ? 2 : 1);
+      }
+      dots(g, rep[g].wv, 1, rep[g].wv);
+      k_norm_step<<<1, 1, 0, s>>>(W.h, W.T, ncv, j, W.scal);
       count_launch();
-      BSG_CUDA(cudaMemcpyAsync(hh.data(), W.h, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, s));
-      BSG_CUDA(cudaStreamSynchronize(s));
-      for (int j = 0; j < cnt; j++) coef[j] += hh[j];
     }
-    dots(wv, 1, wv);
-    BSG_CUDA(cudaMemcpyAsync(hh.data(), W.h, sizeof(double), cudaMemcpyDeviceToHost, s));
-    BSG_CUDA(cudaStreamSynchronize(s));
-    nrm = sqrt(hh[0]);
+    return BSG_OK;
+  };
+  auto next_vec = [&](int dst_col) -> int {
+    for (int g = 0; g < G; g++) {
+      BSG_TRY(bind_device(sh[g].h));
+      k_scale_copy_p<<<gblocks(N), TB, 0, rep[g].s>>>(rep[g].wv, rep[g].W.scal + 1, N, rep[g].W.V + (int64_t)dst_col * ld);
+      count_launch();
+    }
+    BSG_CUDA(cudaGetLastError());
     return BSG_OK;
   };
 
   // ---- start vector
-  k_init_vec<<<gblocks(N), TB, 0, s>>>(N, 0x5EEDull, wv);
-  count_launch();
-  {
-    std::vector<double> c0;
-    double nrm = 0;
-    BSG_TRY(orth(0, c0, nrm));
-    k_scale_copy<<<gblocks(N), TB, 0, s>>>(wv, 1.0 / nrm, N, W.V);
+  for (int g = 0; g < G; g++) {
+    BSG_TRY(bind_device(sh[g].h));
+    k_init_vec<<<gblocks(N), TB, 0, rep[g].s>>>(N, 0x5EEDull, rep[g].wv);
     count_launch();
   }
+  BSG_TRY(orth(0, -1));
+  BSG_TRY(next_vec(0));
 
-  std::vector<double> T((size_t)ncv * ncv, 0.0), theta, Sm;
+  std::vector<double> T((size_t)ncv * ncv, 0.0), Td((size_t)ncv * ncv), theta, Sm;
   int have = 0;      // number of basis vectors whose T column is complete
   int iters = 0, nconv = 0;
   double beta_last = 0;
   for (;;) {
-    // ---- extend the Krylov basis to ncv vectors
+    // ---- extend the Krylov basis to ncv vectors: nothing but kernel launches
     for (int j = have; j < ncv; j++) {
-      BSG_TRY(apply(W.V + (int64_t)j * ld, wv));
-      std::vector<double> coef;
-      double nrm = 0;
-      BSG_TRY(orth(j + 1, coef, nrm));
-      for (int i = 0; i <= j; i++) {
-        T[(size_t)j * ncv + i] = coef[i];
-        T[(size_t)i * ncv + j] = coef[i];
-      }
-      beta_last = nrm;
-      if (j + 1 < ncv) {
-        T[(size_t)(j + 1) * ncv + j] = T[(size_t)j * ncv + j + 1] = nrm;
-      }
-      // next basis vector (also kept as the residual vector V[:, ncv] after the last step)
-      double inv = nrm > 0 ? 1.0 / nrm : 0.0;
-      k_scale_copy<<<gblocks(N), TB, 0, s>>>(wv, inv, N, W.V + (int64_t)(j + 1) * ld);
-      count_launch();
+      BSG_TRY(apply(j));
+      BSG_TRY(orth(j + 1, j));
+      BSG_TRY(next_vec(j + 1));  // next basis vector (also kept as the residual vector V[:, ncv] after the last step)
+    }
+    // ---- the projected matrix of replica 0 (all replicas hold the same bits): the one synchronisation per restart
+    {
+      BSG_TRY(bind_device(sh[0].h));
+      double sc2[2];
+      BSG_CUDA(cudaMemcpyAsync(Td.data(), rep[0].W.T, (size_t)ncv * ncv * sizeof(double), cudaMemcpyDeviceToHost, rep[0].s));
+      BSG_CUDA(cudaMemcpyAsync(sc2, rep[0].W.scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, rep[0].s));
+      BSG_CUDA(cudaStreamSynchronize(rep[0].s));
+      beta_last = sc2[0];
+      for (int j = have; j < ncv; j++)
+        for (int i = 0; i <= j; i++) {
+          T[(size_t)j * ncv + i] = Td[(size_t)j * ncv + i];
+          T[(size_t)i * ncv + j] = Td[(size_t)j * ncv + i];
+        }
     }
     have = ncv;
     // ---- Ritz pairs of the projected matrix
@@ -551,14 +612,6 @@ int bsg_randomsvd_ex(bsg_bed *h, const int *ind_row, int nr, const int *ind_col,
     int nkeep = k + std::min(nconv, (ncv - k) / 2);
     if (nkeep == 1 && ncv > 3) nkeep = ncv / 2;
     nkeep = std::min(nkeep, ncv - 1);
-    BSG_CUDA(cudaMemcpyAsync(W.S, Sm.data(), (size_t)ncv * ncv * sizeof(double), cudaMemcpyHostToDevice, s));
-    dim3 grid(gblocks(N), nkeep);
-    k_combine<<<grid, TB, 0, s>>>(W.V, ld, ncv, W.S, ncv, nkeep, N, W.Y, ld);
-    count_launch();
-    BSG_CUDA(cudaMemcpyAsync(W.V, W.Y, (size_t)ld * nkeep * sizeof(double), cudaMemcpyDeviceToDevice, s));
-    BSG_CUDA(cudaMemcpyAsync(W.V + (int64_t)nkeep * ld, W.V + (int64_t)ncv * ld, (size_t)N * sizeof(double),
-                             cudaMemcpyDeviceToDevice, s));
-    BSG_CUDA(cudaStreamSynchronize(s));
     std::fill(T.begin(), T.end(), 0.0);
     for (int i = 0; i < nkeep; i++) {
       T[(size_t)i * ncv + i] = theta[i];
@@ -566,57 +619,114 @@ int bsg_randomsvd_ex(bsg_bed *h, const int *ind_row, int nr, const int *ind_col,
       T[(size_t)nkeep * ncv + i] = b;
       T[(size_t)i * ncv + nkeep] = b;
     }
+    for (int g = 0; g < G; g++) {
+      BSG_TRY(bind_device(sh[g].h));
+      SvdWork &W = rep[g].W;
+      cudaStream_t s = rep[g].s;
+      BSG_CUDA(cudaMemcpyAsync(W.S, Sm.data(), (size_t)ncv * ncv * sizeof(double), cudaMemcpyHostToDevice, s));
+      BSG_CUDA(cudaMemcpyAsync(W.T, T.data(), (size_t)ncv * ncv * sizeof(double), cudaMemcpyHostToDevice, s));
+      dim3 grid(gblocks(N), nkeep);
+      k_combine<<<grid, TB, 0, s>>>(W.V, ld, ncv, W.S, ncv, nkeep, N, W.Y, ld);
+      count_launch();
+      BSG_CUDA(cudaMemcpyAsync(W.V, W.Y, (size_t)ld * nkeep * sizeof(double), cudaMemcpyDeviceToDevice, s));
+      BSG_CUDA(cudaMemcpyAsync(W.V + (int64_t)nkeep * ld, W.V + (int64_t)ncv * ld, (size_t)N * sizeof(double),
+                               cudaMemcpyDeviceToDevice, s));
+    }
     have = nkeep;
   }
 
   // ---- singular triplets
-  BSG_CUDA(cudaMemcpyAsync(W.S, Sm.data(), (size_t)ncv * ncv * sizeof(double), cudaMemcpyHostToDevice, s));
-  dim3 grid(gblocks(N), k);
-  k_combine<<<grid, TB, 0, s>>>(W.V, ld, ncv, W.S, ncv, k, N, W.Y, ld);
-  count_launch();
-  std::vector<double> side((size_t)N * k), other((size_t)Mo * k);
-  BSG_CUDA(cudaMemcpyAsync(side.data(), W.Y, (size_t)N * k * sizeof(double), cudaMemcpyDeviceToHost, s));
-  double *d_other = nullptr;
-  BSG_CUDA(cudaMalloc((void **)&d_other, (size_t)std::max(Mo, 1) * sizeof(double)));
-  for (int c = 0; c < k; c++) {
-    d[c] = sqrt(std::max(theta[c], 0.0));
-    int rc = row_side ? bsg_view_cprodvec_dev(view, W.Y + (int64_t)c * ld, W.tmp, s)
-                      : bsg_view_prodvec_dev(view, W.Y + (int64_t)c * ld, W.tmp, s);
-    if (rc) {
-      cudaFree(d_other);
-      return rc;
-    }
-    k_scale_copy<<<gblocks(Mo), TB, 0, s>>>(W.tmp, d[c] > 0 ? 1.0 / d[c] : 0.0, Mo, d_other);
+  std::vector<double> side((size_t)N * k);
+  for (int c = 0; c < k; c++) d[c] = sqrt(std::max(theta[c], 0.0));
+  std::vector<std::vector<double>> other(G);
+  for (int g = 0; g < G; g++) {
+    BSG_TRY(bind_device(sh[g].h));
+    SvdWork &W = rep[g].W;
+    cudaStream_t s = rep[g].s;
+    const int Mo = row_side ? sh[g].nc : nr;
+    BSG_CUDA(cudaMemcpyAsync(W.S, Sm.data(), (size_t)ncv * ncv * sizeof(double), cudaMemcpyHostToDevice, s));
+    dim3 grid(gblocks(N), k);
+    k_combine<<<grid, TB, 0, s>>>(W.V, ld, ncv, W.S, ncv, k, N, W.Y, ld);
     count_launch();
-    cudaMemcpyAsync(other.data() + (size_t)c * Mo, d_other, (size_t)Mo * sizeof(double), cudaMemcpyDeviceToHost, s);
-    cudaStreamSynchronize(s);
+    if (g == 0) BSG_CUDA(cudaMemcpyAsync(side.data(), W.Y, (size_t)N * k * sizeof(double), cudaMemcpyDeviceToHost, s));
+    other[g].resize((size_t)std::max(Mo, 1) * k);
+    for (int c = 0; c < k && Mo > 0; c++) {
+      BSG_TRY(row_side ? bsg_view_cprodvec_dev(rep[g].view, W.Y + (int64_t)c * ld, W.tmp, s)
+                       : bsg_view_prodvec_dev(rep[g].view, W.Y + (int64_t)c * ld, W.tmp, s));
+      k_scale_copy<<<gblocks(Mo), TB, 0, s>>>(W.tmp, d[c] > 0 ? 1.0 / d[c] : 0.0, Mo, W.other);
+      count_launch();
+      BSG_CUDA(cudaMemcpyAsync(other[g].data() + (size_t)c * Mo, W.other, (size_t)Mo * sizeof(double), cudaMemcpyDeviceToHost, s));
+      BSG_CUDA(cudaStreamSynchronize(s));  // W.other is reused by the next column
+    }
   }
-  cudaFree(d_other);
-  BSG_CUDA(cudaStreamSynchronize(s));
+  for (int g = 0; g < G; g++) {
+    BSG_TRY(bind_device(sh[g].h));
+    BSG_CUDA(cudaStreamSynchronize(rep[g].s));
+  }
   // deterministic sign: the entry of largest magnitude of each left vector (row side) is positive
   for (int c = 0; c < k; c++) {
-    double *us = row_side ? side.data() + (size_t)c * N : other.data() + (size_t)c * Mo;
-    int len = row_side ? N : Mo;
+    const double *us = row_side ? side.data() + (size_t)c * N : other[0].data() + (size_t)c * nr;
+    const int len = row_side ? N : nr;
     double best = 0;
     for (int i = 0; i < len; i++)
       if (fabs(us[i]) > fabs(best)) best = us[i];
     if (best < 0) {
       for (int i = 0; i < N; i++) side[(size_t)c * N + i] = -side[(size_t)c * N + i];
-      for (int i = 0; i < Mo; i++) other[(size_t)c * Mo + i] = -other[(size_t)c * Mo + i];
+      for (int g = 0; g < G; g++) {
+        const int Mo = row_side ? sh[g].nc : nr;
+        for (int i = 0; i < Mo; i++) other[g][(size_t)c * Mo + i] = -other[g][(size_t)c * Mo + i];
+      }
     }
   }
-  const std::vector<double> &U = row_side ? side : other, &Vv = row_side ? other : side;
-  if (u) memcpy(u, U.data(), (size_t)nr * k * sizeof(double));
-  if (v) memcpy(v, Vv.data(), (size_t)nc * k * sizeof(double));
+  if (row_side) {
+    if (u) memcpy(u, side.data(), (size_t)nr * k * sizeof(double));
+    for (int g = 0; g < G; g++) {
+      if (!sh[g].v_out) continue;
+      const int Mo = sh[g].nc;
+      for (int c = 0; c < k; c++)
+        for (int j = 0; j < Mo; j++) {
+          const int64_t row = sh[g].v_pos ? sh[g].v_pos[j] : j;
+          sh[g].v_out[(size_t)c * sh[g].v_ld + row] = other[g][(size_t)c * Mo + j];
+        }
+    }
+  } else {
+    if (u) memcpy(u, other[0].data(), (size_t)nr * k * sizeof(double));
+    if (sh[0].v_out)
+      for (int c = 0; c < k; c++)
+        for (int j = 0; j < N; j++) {
+          const int64_t row = sh[0].v_pos ? sh[0].v_pos[j] : j;
+          sh[0].v_out[(size_t)c * sh[0].v_ld + row] = side[(size_t)c * N + j];
+        }
+  }
   if (niter) *niter = iters;
   if (nops) *nops = ops;
   g_last_nconv = (full_space || ncv >= N) ? k : nconv;  // the full space is exact
   return BSG_OK;
 }
 
+}  // namespace bsg
+
+using namespace bsg;
+
+extern "C" {
+
 // RSpectra::svds (behind big_randomSVD) warns when fewer than k values converged within maxit; the count of the last
 // call on this thread is exposed so the host wrapper can do the same
 int bsg_randomsvd_nconv(void) { return g_last_nconv; }
+
+// Callback form kept for hosts that bring their own collective: `z_dev` (nr doubles) holds the n-vector of partial
+// products; after every local A (A^T x) the library synchronises its stream and calls reduce_cb(ctx), which must sum z_dev
+// across ranks and return once the sum is visible.  The communicator form (bsg_randomsvd_comm) needs neither.
+int bsg_randomsvd_ex(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, const double *center,
+                     const double *scale, int k, double tol, int maxit, double *d, double *u, double *v,
+                     double *center_out, double *scale_out, int *niter, int *nops, double *z_dev,
+                     bsg_reduce_cb reduce_cb, void *ctx, int ncol_total) {
+  if (!h || !d) return fail(BSG_ERR_ARG, "null argument");
+  if (!ind_col) nc = h->m;
+  std::vector<SvdShard> sh(1);
+  sh[0] = SvdShard{h, ind_col, nc, center, scale, nullptr, v, nc, nullptr, center_out, scale_out};
+  return lanczos_svd(sh, ind_row, nr, ncol_total, k, tol, maxit, d, u, niter, nops, z_dev, reduce_cb, ctx);
+}
 
 int bsg_randomsvd(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, const double *center,
                   const double *scale, int k, double tol, int maxit, double *d, double *u, double *v,

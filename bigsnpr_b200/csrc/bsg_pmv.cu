@@ -42,6 +42,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include "bsg_internal.cuh"
+#include "bsg_pmv_shared.cuh"
 
 namespace bsg {
 namespace pmv {
@@ -367,16 +368,6 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_pmv(const Args a) {
 // ---------------------------------------------------------------------------------------------
 // vector preparation: max |v| + finiteness, quantisation, digit layout, exact sums
 // ---------------------------------------------------------------------------------------------
-struct Scal {          // device-resident scalars of one call
-  double maxabs[2];    // [0] raw-plane vector, [1] NA-plane vector
-  int nonfinite;
-  int e[2];            // Q = rint(v * 2^e); written by the scatter path, derived from maxabs on the direct path
-  int hb;              // headroom bits (log2 of the largest index multiplicity)
-  double Y;            // sum of the (scattered) vector, for Xt.y
-  double C;            // (unused, kept for layout)
-  long long sum_hi, sum_lo;
-  double cpart[128];   // per-block partials of sum_k c_k z_k (X.y), added in index order by the finish kernel
-};
 
 // mode 0: v0 = x                      (Xt.y, identity scaling handled in finish)
 // mode 1: v0 = x / s, v1 = (c - 3) * x / s   (X.y with scaling)
@@ -506,7 +497,6 @@ __device__ __forceinline__ int pick_e(double m, int hb) {
 
 // Fused preparation, direct (identity index) path -- pass 1: max |v0|, max |v1|, finiteness and, for X.y with
 // scaling, the per-block partials of C = sum_k c_k z_k.  Fixed grid of SUMCZ_BLOCKS blocks.
-constexpr int SUMCZ_BLOCKS = 128;
 __global__ void k_prep1(int mode, const double *__restrict__ x, const double *__restrict__ center,
                         const double *__restrict__ scale, int len, int hb, Scal *sc) {
   __shared__ double sh[32];
@@ -656,21 +646,6 @@ __global__ void k_sum_cz(const double *__restrict__ x, const double *__restrict_
   }
 }
 
-// (raw-plane * c0 + NA-plane * c1) per digit slice, exact in integers, then one top-down fp64 sum of the 8
-// scaled slice totals.
-__device__ __forceinline__ double combine8(const long long *__restrict__ part, int64_t line, int c0, int c1, int e) {
-  const long long *p = part + line * 16;
-  double acc = 0;
-#pragma unroll
-  for (int s = 7; s >= 0; s--) {
-    long long v = 0;
-    if (c0) v += c0 * p[s];
-    if (c1) v += c1 * p[8 + s];
-    acc += scalbn((double)v, 8 * s - e);
-  }
-  return acc;
-}
-
 // Xt.y:  out_j = ((R - 3N) - c_j (Y - N)) / s_j        (bedAccScaled semantics, src/bed-acc.h:98-111)
 __global__ void k_finish_cprod(const long long *__restrict__ part, int ksplit, int64_t nlines_pad, int nlines,
                                const Scal *sc, const double *__restrict__ center, const double *__restrict__ scale,
@@ -698,19 +673,7 @@ __global__ void k_finish_prod(const long long *__restrict__ part, int ksplit, in
                               const Scal *sc, int has_scaling, int use_na, double *__restrict__ full) {
   int l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= nlines) return;
-  if (sc->nonfinite) {
-    full[l] = nan("");
-    return;
-  }
-  if (has_scaling) {
-    double C = 0;
-    for (int b = 0; b < SUMCZ_BLOCKS; b++) C += sc->cpart[b];
-    double R = combine8(part, l, 1, 0, sc->e[0]);
-    double Nw = use_na ? combine8(part, l, 0, 1, sc->e[1]) : 0.0;
-    full[l] = (R + Nw) - C;
-  } else {
-    full[l] = combine8(part, l, 1, use_na ? -3 : 0, sc->e[0]);  // R - 3N, exact
-  }
+  full[l] = finish_prod_value(part, l, sc, has_scaling, use_na);
 }
 
 // planes API:  full_l = cR * R_l + cP * P_l + add0,  R = raw-plane sum against vector 1 (exponent e[0]),
@@ -1720,7 +1683,7 @@ static int prep_T(bsg_view *v, int mode, const double *x, const double *p1, cons
 
 // X~ x from the SNP-major copy alone (k_pmvT): lines = selected SNP columns in selection order (duplicates are
 // just repeated lines), all n samples are produced and the requested rows gathered at the end.
-static int prodvec_T(bsg_view *v, const double *x_dev, double *out_dev, cudaStream_t s) {
+static int prodvec_T(bsg_view *v, const double *x_dev, double *out_dev, cudaStream_t s, bsg_comm *comm) {
   using namespace pmv;
   bsg_bed *h = v->h;
   Scal *sc = v->s_scal.as<Scal>();
@@ -1748,6 +1711,8 @@ static int prodvec_T(bsg_view *v, const double *x_dev, double *out_dev, cudaStre
     BSG_TRY(v->s_full.ensure((size_t)n * sizeof(double)));
     full = v->s_full.as<double>();
   }
+  if (comm && v->row_identity)  // epilogue fused with the sum over the column shards (NVLink peer memory, bsg_comm.cu)
+    return comm_finish_prod_allreduce(comm, part, n, sc, v->has_scaling, h->has_na, out_dev, s);
   if (n > 0) {
     k_finish_prod<<<(n + 255) / 256, 256, 0, s>>>(part, 1, n, n, sc, v->has_scaling, h->has_na, full);
     count_launch();
@@ -1757,6 +1722,7 @@ static int prodvec_T(bsg_view *v, const double *x_dev, double *out_dev, cudaStre
     count_launch();
   }
   BSG_CUDA(cudaGetLastError());
+  if (comm) return comm_allreduce_oneshot(comm, out_dev, v->nr, s);
   return BSG_OK;
 }
 
@@ -1771,16 +1737,16 @@ static bool use_T(const bsg_bed *h) {
   return !h->B || g_force_t == 1 || h->has_na;
 }
 
-// X~ x : lines = samples of copy B, contraction over SNP columns
-int bsg_view_prodvec_dev(bsg_view *v, const double *x_dev, double *out_dev, void *stream) {
+}  // extern "C"
+
+// X~ x : lines = samples of copy B, contraction over SNP columns.  comm != null: the result is summed over the column
+// shards of the communicator (every rank receives the full n-vector).
+int bsg::view_prodvec_comm(bsg_view *v, const double *x_dev, double *out_dev, cudaStream_t s, bsg_comm *comm) {
   if (!v || !x_dev || !out_dev) return fail(BSG_ERR_ARG, "null argument");
   bsg_bed *h = v->h;
   BSG_TRY(bind_device(h));
-  // NULL = the legacy default stream (what the header documents and what torch's default stream is): work is then
-  // ordered with the caller's kernels and collectives, not on the handle's private non-blocking stream
-  cudaStream_t s = stream ? (cudaStream_t)stream : cudaStreamLegacy;
   if (v->nr == 0) return BSG_OK;
-  if (use_T(h)) return prodvec_T(v, x_dev, out_dev, s);  // transposing kernel over the SNP-major copy
+  if (use_T(h)) return prodvec_T(v, x_dev, out_dev, s, comm);  // transposing kernel over the SNP-major copy
   using namespace pmv;
   Scal *sc = v->s_scal.as<Scal>();
   const int m = h->m;
@@ -1824,6 +1790,8 @@ int bsg_view_prodvec_dev(bsg_view *v, const double *x_dev, double *out_dev, void
     BSG_TRY(v->s_full.ensure((size_t)nlines * sizeof(double)));
     full = v->s_full.as<double>();
   }
+  if (comm && v->row_identity)
+    return comm_finish_prod_allreduce(comm, a.part, nlines, sc, v->has_scaling, h->has_na, out_dev, s);
   k_finish_prod<<<(nlines + 255) / 256, 256, 0, s>>>(a.part, a.ksplit, a.nlines_pad, nlines, sc, v->has_scaling,
                                                      h->has_na, full);
   count_launch();
@@ -1832,7 +1800,16 @@ int bsg_view_prodvec_dev(bsg_view *v, const double *x_dev, double *out_dev, void
     count_launch();
   }
   BSG_CUDA(cudaGetLastError());
+  if (comm) return comm_allreduce_oneshot(comm, out_dev, v->nr, s);
   return BSG_OK;
+}
+
+extern "C" {
+
+int bsg_view_prodvec_dev(bsg_view *v, const double *x_dev, double *out_dev, void *stream) {
+  // NULL = the legacy default stream (what the header documents and what torch's default stream is): work is then
+  // ordered with the caller's kernels and collectives, not on the handle's private non-blocking stream
+  return view_prodvec_comm(v, x_dev, out_dev, stream ? (cudaStream_t)stream : cudaStreamLegacy, nullptr);
 }
 
 // host-vector front ends: H2D of x, the product, D2H of the result; non-finite input falls back to the

@@ -88,10 +88,85 @@ class LocalGpu:
         return out
 
 
+class Comm:
+    """This rank's end of the library's own communicator (bsg_comm): the ranks of one node exchange data through each
+    other's HBM over NVLink (CUDA IPC mappings).  The only thing that crosses the host is the 64-byte IPC handle, gathered
+    here once with torch.distributed; afterwards the X.y epilogue kernel itself sums the shards' partial vectors."""
+
+    def __init__(self, max_elems, device=None, group=None):
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib
+
+        self._c = None
+        L = _lib.lib()
+        world, rank = _world(group)
+        dev = torch.cuda.current_device() if device is None else int(device)
+        c = C.c_void_p()
+        mine = np.zeros(64, dtype=np.uint8)
+        _lib.check(L.bsg_comm_create(rank, world, dev, int(max_elems), C.byref(c), mine.ctypes.data_as(_lib.c_u8_p)))
+        self._c, self.rank, self.world = c, rank, world
+        if world > 1:
+            handles = [None] * world
+            dist.all_gather_object(handles, mine.tobytes(), group=group)
+            allh = np.frombuffer(b"".join(handles), dtype=np.uint8).copy()
+            _lib.check(L.bsg_comm_connect(c, allh.ctypes.data_as(_lib.c_u8_p)))
+            dist.barrier(group=group)  # every rank has mapped every region before the first collective touches one
+
+    def prodvec_allreduce(self, view, x_ptr, out_ptr, stream=0):
+        """X~ x over this rank's shard, summed over the ranks inside the epilogue kernel; out = the full n-vector."""
+        from . import _lib
+
+        _lib.check(_lib.lib().bsg_view_prodvec_allreduce_dev(view._v, self._c, int(x_ptr), int(out_ptr), int(stream) or None))
+
+    def allreduce(self, buf_ptr, count, stream=0):
+        from . import _lib
+
+        _lib.check(_lib.lib().bsg_comm_allreduce_dev(self._c, int(buf_ptr), int(count), int(stream) or None))
+
+    def check(self):
+        from . import _lib
+
+        _lib.check(_lib.lib().bsg_comm_check(self._c))
+
+    def close(self):
+        if self._c is not None:
+            from . import _lib
+
+            _lib.lib().bsg_comm_destroy(self._c)
+            self._c = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def randomsvd_comm(obj_bed, comm, m_total, k=10, tol=1e-4, maxit=1000):
+    """bed_randomSVD on a column-sharded matrix through the library's communicator: every rank passes its shard; u (n x k)
+    and d are replicated (bit-identical on all ranks), v holds this rank's rows.  No host synchronisation inside the
+    iteration except one read of the (ncv x ncv) projected matrix per restart."""
+    from . import _lib
+
+    L = _lib.lib()
+    n, m_loc = obj_bed.nrow, obj_bed.ncol
+    d = np.empty(k)
+    u = np.empty((k, n))
+    v = np.empty((k, m_loc))
+    c_out, s_out = np.empty(m_loc), np.empty(m_loc)
+    niter, nops = C.c_int(0), C.c_int(0)
+    pd = lambda a: a.ctypes.data_as(_lib.c_dbl_p)  # noqa: E731
+    _lib.check(L.bsg_randomsvd_comm(obj_bed._h, comm._c, None, n, None, m_loc, None, None, int(m_total), int(k), float(tol),
+                                    int(maxit), pd(d), pd(u), pd(v), pd(c_out), pd(s_out), C.byref(niter), C.byref(nops)))
+    return {"d": d, "u": u.T, "v": v.T, "niter": niter.value, "nops": nops.value, "center": c_out, "scale": s_out}
+
+
 def randomsvd_sharded(obj_bed, m_total, k=10, tol=1e-4, maxit=1000, group=None):
-    """bed_randomSVD on a column-sharded matrix: every rank passes its shard handle; u (n x k) and d are
-    replicated, v holds this rank's rows.  The Lanczos iteration is the library's (bsg_randomsvd_ex); the
-    reduce callback all-reduces the n-vector of partial products with torch.distributed."""
+    """Same decomposition with the caller's collective: the Lanczos iteration is the library's (bsg_randomsvd_ex); the
+    reduce callback all-reduces the n-vector of partial products with torch.distributed (NCCL, or gloo in CPU tests of
+    the host logic).  Kept as the baseline the communicator form is measured against."""
     import torch
     import torch.distributed as dist
 

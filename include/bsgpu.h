@@ -45,6 +45,9 @@ extern "C" {
 #define BSG_LAYOUT_AUTO 0         /* SNP-major only; the transpose is built on first use by bsg_tcrossprod */
 
 typedef struct bsg_bed bsg_bed;   /* replaces class bed + XPtr<bed>: src/bed-acc.h:18-48, src/bed-acc-xptr.cpp:40-55 */
+typedef struct bsg_comm bsg_comm;   /* one rank's end of a GPU group exchanging data over NVLink peer memory (no reference twin: the
+                                       reference has no multi-device path) */
+typedef struct bsg_group bsg_group; /* several GPUs driven by ONE host process: column shards of one matrix + their communicators */
 typedef struct bsg_view bsg_view; /* replaces bedAccScaled: (ind_row, ind_col, center, scale) resident on device, src/bed-acc.h:86-115 */
 
 const char *bsg_last_error(void);
@@ -211,6 +214,52 @@ int bsg_randomsvd_ex(bsg_bed *h, const int *ind_row, int nr, const int *ind_col,
                      const double *center, const double *scale, int k, double tol, int maxit, double *d,
                      double *u, double *v, double *center_out, double *scale_out, int *niter, int *nops,
                      double *z_dev, bsg_reduce_cb reduce_cb, void *ctx, int ncol_total);
+
+/* ---- several GPUs (the reference has no multi-device path) ---------------------------------------
+ * SNP columns are sharded contiguously over the GPUs (shard g = columns [g*m/G, (g+1)*m/G), first m % G shards one longer).
+ * X.y ends in a sum of partial n-vectors over the shards, done INSIDE the product's epilogue kernel over NVLink peer memory;
+ * Xt.y, column statistics and v need no exchange; Gram partials are summed by a two-shot all-reduce over peer memory.
+ *
+ * (1) one host process driving all GPUs -- what an R session is: bsg_group_*.  ind_col is a GLOBAL 1-based multiset. */
+int bsg_group_open_bed(const char *path, int n, int m, const int *devices, int ndev, int layouts, bsg_group **out);
+int bsg_group_open_synth(int n, int m, uint64_t seed, double na_rate, double ld_rho, int ld_block, const int *devices,
+                         int ndev, int layouts, bsg_group **out);
+void bsg_group_close(bsg_group *g);
+int bsg_group_ndev(const bsg_group *g);
+int bsg_group_nrow(const bsg_group *g);
+int bsg_group_ncol(const bsg_group *g);
+bsg_bed *bsg_group_shard(bsg_group *g, int i);          /* the per-device handle (statistics, counts, decode per shard) */
+int bsg_group_shard_begin(const bsg_group *g, int i);   /* first global column (0-based) of shard i; i = ndev gives m */
+/* bed_pMatVec4 / bed_cpMatVec4 (src/bed-prod-vec.cpp:15-54, :59-97) over the shards, host vectors, the 9-argument form */
+int bsg_group_prodvec(bsg_group *g, const int *ind_row, int nr, const int *ind_col, int nc, const double *center,
+                      const double *scale, const double *x, double *out);
+int bsg_group_cprodvec(bsg_group *g, const int *ind_row, int nr, const int *ind_col, int nc, const double *center,
+                       const double *scale, const double *x, double *out);
+/* bed_randomSVD (R/autoSVD.R:205-219) over the shards: u[nr x k], v[nc x k] in the caller's column order */
+int bsg_group_randomsvd(bsg_group *g, const int *ind_row, int nr, const int *ind_col, int nc, const double *center,
+                        const double *scale, int k, double tol, int maxit, double *d, double *u, double *v,
+                        double *center_out, double *scale_out, int *niter, int *nops);
+/* bed_tcrossprodSelf (R/bed-tcrossprodSelf.R:21-52) over the shards: K[nr x nr] on the host */
+int bsg_group_tcrossprod(bsg_group *g, const int *ind_row, int nr, const int *ind_col, int nc, const double *center,
+                         const double *scale, double *K);
+
+/* (2) one process per GPU (torchrun): every rank creates its end of the communicator (the 64-byte CUDA IPC handle of its
+ * region comes back in handle64), the ranks exchange the handles by any means (torch.distributed all_gather) and connect.
+ * max_elems = longest vector that will be reduced (n).  After that no host-side exchange happens on the data path. */
+int bsg_comm_create(int rank, int world, int device, int64_t max_elems, bsg_comm **out, unsigned char *handle64);
+int bsg_comm_connect(bsg_comm *c, const unsigned char *handles /* world x 64 bytes in rank order */);
+void bsg_comm_destroy(bsg_comm *c);
+int bsg_comm_rank(const bsg_comm *c);
+int bsg_comm_world(const bsg_comm *c);
+int bsg_comm_check(bsg_comm *c); /* error if a wait inside a collective timed out (a peer never arrived) */
+/* in-place sum of count doubles over the ranks, enqueued on `stream`; same bits on every rank */
+int bsg_comm_allreduce_dev(bsg_comm *c, double *buf_dev, int64_t count, void *stream);
+/* X~ x over this rank's column shard with the sum over the ranks fused into the epilogue kernel: out_dev = full n-vector */
+int bsg_view_prodvec_allreduce_dev(bsg_view *v, bsg_comm *c, const double *x_dev, double *out_dev, void *stream);
+/* bed_randomSVD on a column-sharded matrix, every rank passing its shard: u, d replicated, v = this rank's rows */
+int bsg_randomsvd_comm(bsg_bed *h, bsg_comm *c, const int *ind_row, int nr, const int *ind_col, int nc, const double *center,
+                       const double *scale, int ncol_total, int k, double tol, int maxit, double *d, double *u, double *v,
+                       double *center_out, double *scale_out, int *niter, int *nops);
 
 /* ---- instrumentation --------------------------------------------------------------------------------- */
 /* kernels launched by this library since load (the bench's gpu_launches claim) */

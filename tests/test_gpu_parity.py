@@ -702,3 +702,41 @@ def test_ld_structured_generator_matches_its_twins(B, oracle):
     inside = np.array([j % 50 != 0 for j in range(1, 200) if p[j + 1] - p[j] == 2])
     assert np.mean(adj[inside] ** 2) > 0.2 and np.mean(adj[~inside] ** 2) < 0.01
     big.close()
+
+
+def test_group_entry_points_vs_oracle(B, oracle, rng):
+    """The single-process multi-GPU entry points of the C ABI (bsg_group_*): column shards over up to
+    two of the visible devices (one on a single-GPU box: same code path, no exchange), against the oracle on the whole
+    matrix -- products with global multiset indices, bed_randomSVD vs the dense decomposition, the GRM."""
+    from bigsnpr_b200 import _lib
+
+    ndev = max(1, min(2, _lib.lib().bsg_device_count()))
+    n, m = 2003, 6011
+    grp = B.Group.synthetic(n, m, list(range(ndev)), seed=13, na_rate=0.02)
+    o = oracle.synth_bed(n, m, seed=13, na_rate=0.02)
+    sc = grp.scaleBinom()
+    sco = oracle.bed_scaleBinom(o)
+    assert np.array_equal(sc["center"], sco["center"]) and np.array_equal(sc["scale"], sco["scale"])
+    x, y = rng.normal(size=m), rng.normal(size=n)
+    _close(grp.prodVec(x, center=sc["center"], scale=sc["scale"]), oracle.bed_prodVec(o, x, center=sc["center"], scale=sc["scale"]),
+           scale=np.max(np.abs(x / sc["scale"])) * m)
+    _close(grp.cprodVec(y, center=sc["center"], scale=sc["scale"]), oracle.bed_cprodVec(o, y, center=sc["center"], scale=sc["scale"]),
+           scale=np.max(np.abs(y)) * n / np.min(sc["scale"]))
+    ir = rng.integers(1, n + 1, size=700).astype(np.int32)
+    ic = rng.integers(1, m + 1, size=900).astype(np.int32)  # unsorted, with duplicates, spanning both shards
+    xs, ys = rng.normal(size=ic.size), rng.normal(size=ir.size)
+    _close(grp.prodVec(xs, ind_row=ir, ind_col=ic), oracle.bed_prodVec(o, xs, ind_row=ir, ind_col=ic), scale=np.max(np.abs(xs)) * ic.size)
+    _close(grp.cprodVec(ys, ind_row=ir, ind_col=ic), oracle.bed_cprodVec(o, ys, ind_row=ir, ind_col=ic), scale=np.max(np.abs(ys)) * ir.size)
+    with pytest.raises(B.BsgError, match="out of bounds"):
+        grp.prodVec(np.zeros(1), ind_col=[m + 1])
+    sub = np.arange(1, m + 1, 3).astype(np.int32)
+    svd = grp.randomSVD(ind_col=sub, k=6)
+    dense = oracle.bed_randomSVD(o, ind_col=sub, k=6)
+    assert np.max(np.abs(svd["d"] - dense["d"]) / dense["d"]) < 1e-7
+    assert np.min(np.abs(np.sum(svd["u"] * dense["u"], axis=0))) > 1 - 1e-6
+    assert np.min(np.abs(np.sum(svd["v"] * dense["v"], axis=0))) > 1 - 1e-6
+    assert np.array_equal(svd["center"], sc["center"][sub - 1])
+    K = grp.tcrossprodSelf(sc["center"][sub - 1], sc["scale"][sub - 1], ind_col=sub)
+    K0, _, _ = oracle.bed_tcrossprodSelf(o, ind_col=sub)
+    assert np.max(np.abs(K - K0)) / np.max(np.abs(K0)) < 1e-9
+    grp.close()

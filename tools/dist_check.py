@@ -37,6 +37,34 @@ def main():
     t0 = time.perf_counter()
     svd = randomsvd_sharded(g, m, k=k)
     t_svd = time.perf_counter() - t0
+    # ---- the library's own communicator (NVLink peer memory, reduction fused into the X.y epilogue) on the DEFAULT stream
+    comm = D.Comm(n, device=local)
+    xd = torch.from_numpy(x[b:e].copy()).to(dev)
+    outc = torch.empty(n, dtype=torch.float64, device=dev)
+    comm.prodvec_allreduce(view, xd.data_ptr(), outc.data_ptr(), 0)
+    torch.cuda.synchronize()
+    comm_vs_nccl = float((outc - Ax).abs().max() / Ax.abs().max())
+    gath = [torch.empty_like(outc) for _ in range(world)]
+    dist.all_gather(gath, outc)
+    comm_same_bits = all(bool(torch.equal(gath[0], t)) for t in gath)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tms = {}
+    for name in ("comm", "nccl"):
+        for it in range(25):
+            if it == 5:
+                ev0.record()
+            if name == "comm":
+                comm.prodvec_allreduce(view, xd.data_ptr(), outc.data_ptr(), 0)
+            else:
+                view.prodvec_dev(xd.data_ptr(), outc.data_ptr(), 0)
+                dist.all_reduce(outc)
+        ev1.record()
+        torch.cuda.synchronize()
+        tms[name] = ev0.elapsed_time(ev1) / 20
+    t0 = time.perf_counter()
+    svdc = D.randomsvd_comm(g, comm, m, k=k)
+    t_svdc = time.perf_counter() - t0
+    comm.check()
     res = {}
     if rank == 0:
         gf = B.Bed.synthetic(n, m, seed=seed, na_rate=0.01, device=local)
@@ -50,12 +78,21 @@ def main():
                "cprodvec_max_rel": float(np.max(np.abs(Aty.cpu().numpy() - Aty1)) / np.max(np.abs(Aty1))),
                "svd_d_max_rel": float(np.max(np.abs(svd["d"] - svd1["d"]) / svd1["d"])),
                "svd_u_min_abs_corr": float(np.min(np.abs(np.sum(svd["u"] * svd1["u"], axis=0)))),
-               "svd_sharded_s": t_svd, "svd_single_s": t1, "nops": svd["nops"], "nops_single": svd1["nops"]}
+               "svd_sharded_s": t_svd, "svd_single_s": t1, "nops": svd["nops"], "nops_single": svd1["nops"],
+               "comm_prodvec_vs_nccl_max_rel": comm_vs_nccl, "comm_same_bits_on_all_ranks": comm_same_bits,
+               "prodvec_step_ms_comm": tms["comm"], "prodvec_step_ms_nccl": tms["nccl"],
+               "svd_comm_d_max_rel": float(np.max(np.abs(svdc["d"] - svd1["d"]) / svd1["d"])),
+               "svd_comm_u_min_abs_corr": float(np.min(np.abs(np.sum(svdc["u"] * svd1["u"], axis=0)))),
+               "svd_comm_s": t_svdc, "nops_comm": svdc["nops"]}
         print(json.dumps(res), flush=True)
         ok = res["prodvec_max_rel"] < 1e-12 and res["cprodvec_max_rel"] < 1e-12 and res["svd_d_max_rel"] < 1e-7 \
-            and res["svd_u_min_abs_corr"] > 1 - 1e-6
+            and res["svd_u_min_abs_corr"] > 1 - 1e-6 and res["comm_prodvec_vs_nccl_max_rel"] < 1e-13 \
+            and res["comm_same_bits_on_all_ranks"] and res["svd_comm_d_max_rel"] < 1e-7 \
+            and res["svd_comm_u_min_abs_corr"] > 1 - 1e-6
         if not ok:
             print("DIST CHECK FAILED", flush=True)
+    dist.barrier()
+    comm.close()
     rows_check(rank, world, local)
     dist.barrier()
     dist.destroy_process_group()
