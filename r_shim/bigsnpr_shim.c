@@ -15,6 +15,11 @@
 #include <Rinternals.h>
 #include <R_ext/Rdynload.h>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include "bsgpu.h"
 
 static void chk(int rc) {
@@ -131,23 +136,54 @@ SEXP _bigsnpr_read_bed_scaled(SEXP obj_bed, SEXP ind_row, SEXP ind_col, SEXP cen
   return res;
 }
 
-/* FBM.code256 objects (snp_cor / snp_ld_scores / snp_colstats): the raw n x m bytes live in the memory-mapped
- * backing file; a handle is opened once per object and cached in the environment (field ".bsg"). */
+/* bigstatsr's FBM objects (RefClass environments) expose `$backingfile` (the .bk file: nrow x ncol elements of the FBM's
+ * type, column-major, no header), `$nrow`, `$ncol` and, for FBM.code256, `$code256`.  The shim maps that file itself
+ * (the reference reaches the same bytes through bigstatsr's C++ accessor, src/corr.cpp:113-118), so it depends on no
+ * bigstatsr header or symbol.  Writable maps serve the in-place outputs of the reference: the integer FBM `keep` of the
+ * clumping routines (R/clumping.R:115, R/bed-clumping.R:51) and the FBM.code256 filled by readbina2. */
+static void *fbm_map(SEXP obj, size_t elt_size, int writable, size_t *bytes_out) {
+  SEXP bf = field(obj, "backingfile");
+  if (TYPEOF(bf) != STRSXP || LENGTH(bf) < 1) Rf_error("object has no backing file");
+  const char *path = CHAR(STRING_ELT(bf, 0));
+  size_t want = (size_t)Rf_asInteger(field(obj, "nrow")) * (size_t)Rf_asInteger(field(obj, "ncol")) * elt_size;
+  int fd = open(path, writable ? O_RDWR : O_RDONLY);
+  if (fd < 0) Rf_error("Error when mapping file:\n  %s.\n", path);
+  struct stat st;
+  if (fstat(fd, &st) != 0 || (size_t)st.st_size < want) {
+    close(fd);
+    Rf_error("Inconsistency between size of backingfile and dimensions.");
+  }
+  void *p = want ? mmap(NULL, want, writable ? (PROT_READ | PROT_WRITE) : PROT_READ, MAP_SHARED, fd, 0) : NULL;
+  close(fd);
+  if (want && p == MAP_FAILED) Rf_error("Error when mapping file:\n  %s.\n", path);
+  *bytes_out = want;
+  return p;
+}
+static void fbm_unmap(void *p, size_t bytes, int writable) {
+  if (!p || !bytes) return;
+  if (writable) msync(p, bytes, MS_SYNC); /* R reads the result through its own mapping of the same file */
+  munmap(p, bytes);
+}
+
+/* FBM.code256 objects (snp_cor / snp_ld_scores / snp_colstats / snp_clumping / snp_pcadapt / snp_writeBed): the n x m
+ * bytes are staged to HBM once per object; the handle is cached in the environment (variable ".bsg"). */
 static bsg_bed *fbm_handle_of(SEXP obj) {
   SEXP cached = Rf_findVarInFrame(obj, Rf_install(".bsg"));
   if (cached != R_UnboundValue && TYPEOF(cached) == EXTPTRSXP && R_ExternalPtrAddr(cached))
     return (bsg_bed *)R_ExternalPtrAddr(cached);
   int n = Rf_asInteger(field(obj, "nrow")), m = Rf_asInteger(field(obj, "ncol"));
   SEXP code = PROTECT(Rf_coerceVector(field(obj, "code256"), REALSXP));
-  /* G[] as raw: the shim reads the bytes through R so it does not depend on bigstatsr's C++ classes */
-  SEXP call = PROTECT(Rf_lang2(Rf_install("as.raw.FBM.bytes"), obj)); /* helper exported by the R glue, INTEGRATION.md */
-  SEXP bytes = PROTECT(Rf_eval(call, R_GlobalEnv));
+  if (LENGTH(code) != 256) Rf_error("'code256' must have 256 values.");
+  size_t bytes = 0;
+  void *raw = fbm_map(obj, 1, 0, &bytes);
   bsg_bed *h = NULL;
-  chk(bsg_open_fbm256(RAW(bytes), n, m, REAL(code), gpu_device(), BSG_LAYOUT_SNP_MAJOR, &h));
+  int rc = bsg_open_fbm256((const uint8_t *)raw, n, m, REAL(code), gpu_device(), BSG_LAYOUT_SNP_MAJOR, &h);
+  fbm_unmap(raw, bytes, 0);
+  chk(rc);
   SEXP xp = PROTECT(R_MakeExternalPtr(h, R_NilValue, R_NilValue));
   R_RegisterCFinalizerEx(xp, bed_finalizer, TRUE);
   Rf_defineVar(Rf_install(".bsg"), xp, obj);
-  UNPROTECT(4);
+  UNPROTECT(2);
   return h;
 }
 
@@ -214,40 +250,58 @@ SEXP _bigsnpr_ld_scores(SEXP obj, SEXP rowInd, SEXP colInd, SEXP size, SEXP pos,
   return out;
 }
 
-/* _bigsnpr_bed_clumping_chr: src/clumping-bed.cpp:11-91 (12 arguments, keep is the integer FBM BM2 written in place;
- * rankInd is implied by ordInd).  BM2$address_rw is bigstatsr's XPtr<FBM_RW>: the shim writes through as.integer
- * storage obtained from R -- here via the helper `fbm_int_ptr`. */
-extern int *fbm_int_ptr(SEXP BM2); /* provided by the package glue: pointer to the mmap'ed int matrix of an FBM */
+/* _bigsnpr_bed_clumping_chr: src/clumping-bed.cpp:11-91 (12 arguments).  BM2 is the 1 x nc integer FBM `keep`
+ * (R/bed-clumping.R:51), written in place through its backing file; rankInd is implied by ordInd. */
 SEXP _bigsnpr_bed_clumping_chr(SEXP obj_bed, SEXP BM2, SEXP ind_row, SEXP ind_col, SEXP center, SEXP scale, SEXP ordInd,
                                SEXP rankInd, SEXP pos, SEXP size, SEXP thr, SEXP ncores) {
   bsg_bed *h = handle_of(obj_bed);
   int nr = LENGTH(ind_row), nc = LENGTH(ind_col);
-  chk(bsg_clumping_chr(h, INTEGER(ind_row), nr, INTEGER(ind_col), nc, REAL(center), REAL(scale), INTEGER(ordInd), REAL(pos),
-                       Rf_asReal(size), Rf_asReal(thr), fbm_int_ptr(BM2)));
+  if (LENGTH(center) != nc || LENGTH(scale) != nc || LENGTH(pos) != nc || LENGTH(ordInd) != nc)
+    Rf_error("Incompatibility between dimensions.");
+  size_t bytes = 0;
+  int *keep = (int *)fbm_map(BM2, sizeof(int), 1, &bytes);
+  if (bytes < (size_t)nc * sizeof(int)) { fbm_unmap(keep, bytes, 1); Rf_error("Incompatibility between dimensions."); }
+  int rc = bsg_clumping_chr(h, INTEGER(ind_row), nr, INTEGER(ind_col), nc, REAL(center), REAL(scale), INTEGER(ordInd), REAL(pos),
+                            Rf_asReal(size), Rf_asReal(thr), keep);
+  fbm_unmap(keep, bytes, 1);
+  chk(rc);
   return R_NilValue;
 }
 
-/* _bigsnpr_clumping_chr: src/clumping.cpp:10-91 (12 arguments; BM is the FBM.code256 environment) */
+/* _bigsnpr_clumping_chr: src/clumping.cpp:10-91 (12 arguments; BM is the FBM.code256 environment, src/clumping.cpp:24-25) */
 SEXP _bigsnpr_clumping_chr(SEXP BM, SEXP BM2, SEXP rowInd, SEXP colInd, SEXP ordInd, SEXP rankInd, SEXP pos, SEXP sumX,
                            SEXP denoX, SEXP size, SEXP thr, SEXP ncores) {
-  bsg_bed *h = handle_of(BM);
+  bsg_bed *h = fbm_handle_of(BM);
   int nr = LENGTH(rowInd), nc = LENGTH(colInd);
-  chk(bsg_clumping_chr_fbm(h, INTEGER(rowInd), nr, INTEGER(colInd), nc, REAL(sumX), REAL(denoX), INTEGER(ordInd), REAL(pos),
-                           Rf_asReal(size), Rf_asReal(thr), fbm_int_ptr(BM2)));
+  if (LENGTH(sumX) != nc || LENGTH(denoX) != nc || LENGTH(pos) != nc || LENGTH(ordInd) != nc)
+    Rf_error("Incompatibility between dimensions.");
+  size_t bytes = 0;
+  int *keep = (int *)fbm_map(BM2, sizeof(int), 1, &bytes);
+  if (bytes < (size_t)nc * sizeof(int)) { fbm_unmap(keep, bytes, 1); Rf_error("Incompatibility between dimensions."); }
+  int rc = bsg_clumping_chr_fbm(h, INTEGER(rowInd), nr, INTEGER(colInd), nc, REAL(sumX), REAL(denoX), INTEGER(ordInd), REAL(pos),
+                                Rf_asReal(size), Rf_asReal(thr), keep);
+  fbm_unmap(keep, bytes, 1);
+  chk(rc);
   return R_NilValue;
 }
 
-/* _bigsnpr_readbina2: src/read-plink.cpp:61-80 (5 arguments; BM is the destination FBM.code256, filled in place) */
-extern unsigned char *fbm_raw_ptr(SEXP BM); /* package glue: pointer to the mmap'ed raw matrix of an FBM */
+/* _bigsnpr_readbina2: src/read-plink.cpp:61-80 (5 arguments; BM is the destination FBM.code256, filled in place; the R
+ * wrapper creates it with exactly length(ind_row) x length(ind_col) bytes, R/read-plink.R:93-100) */
 SEXP _bigsnpr_readbina2(SEXP BM, SEXP obj_bed, SEXP ind_row, SEXP ind_col, SEXP ncores) {
   bsg_bed *h = handle_of(obj_bed);
-  chk(bsg_readbina2(h, INTEGER(ind_row), LENGTH(ind_row), INTEGER(ind_col), LENGTH(ind_col), fbm_raw_ptr(BM)));
+  size_t bytes = 0, want = (size_t)LENGTH(ind_row) * (size_t)LENGTH(ind_col);
+  unsigned char *dst = (unsigned char *)fbm_map(BM, 1, 1, &bytes);
+  if (bytes != want) { fbm_unmap(dst, bytes, 1); Rf_error("Incompatibility between dimensions."); }
+  int rc = bsg_readbina2(h, INTEGER(ind_row), LENGTH(ind_row), INTEGER(ind_col), LENGTH(ind_col), dst);
+  fbm_unmap(dst, bytes, 1);
+  chk(rc);
   return R_NilValue;
 }
 
-/* _bigsnpr_writebina: src/write-plink.cpp:13-52 (5 arguments; `tab` = getInverseCode() is implied by the library) */
+/* _bigsnpr_writebina: src/write-plink.cpp:13-52 (5 arguments; BM is the FBM.code256 of the bigSNP, src/write-plink.cpp:19-20;
+ * `tab` = getInverseCode() is implied by the library) */
 SEXP _bigsnpr_writebina(SEXP filename, SEXP BM, SEXP tab, SEXP rowInd, SEXP colInd) {
-  bsg_bed *h = handle_of(BM);
+  bsg_bed *h = fbm_handle_of(BM);
   chk(bsg_writebina(h, CHAR(STRING_ELT(filename, 0)), INTEGER(rowInd), LENGTH(rowInd), INTEGER(colInd), LENGTH(colInd)));
   return R_NilValue;
 }
@@ -269,7 +323,7 @@ SEXP _bigsnpr_prod_and_rowSumsSq(SEXP obj_bed, SEXP ind_row, SEXP ind_col, SEXP 
 
 /* _bigsnpr_multLinReg: src/multLinReg.cpp:64-88 (5 arguments; `obj` is a bed or an FBM.code256 environment) */
 SEXP _bigsnpr_multLinReg(SEXP obj, SEXP ind_row, SEXP ind_col, SEXP U, SEXP ncores) {
-  bsg_bed *h = handle_of(obj);
+  bsg_bed *h = any_handle(obj); /* src/multLinReg.cpp:72-78: FBM.code256 or bed, else "Unknown object type." */
   int nr = LENGTH(ind_row), nc = LENGTH(ind_col), K = Rf_ncols(U);
   if (Rf_nrows(U) != nr) Rf_error("Incompatibility between dimensions.");
   SEXP t = PROTECT(Rf_allocMatrix(REALSXP, nc, K));
@@ -309,6 +363,65 @@ SEXP _bigsnpr_bed_randomSVD_gpu(SEXP obj_bed, SEXP ind_row, SEXP ind_col, SEXP c
   return res;
 }
 
+/* ---- several GPUs from the one R process: options(bigsnpr.gpu.devices = c(0, 1, ...)) --------------
+ * A group handle shards the file's SNP columns over the listed devices; the two new symbols mirror the single-GPU ones. */
+static void group_finalizer(SEXP xp) {
+  bsg_group *g = (bsg_group *)R_ExternalPtrAddr(xp);
+  if (g) bsg_group_close(g);
+  R_ClearExternalPtr(xp);
+}
+SEXP _bigsnpr_bed_group_gpu(SEXP path, SEXP n, SEXP p, SEXP devices) {
+  bsg_group *g = NULL;
+  chk(bsg_group_open_bed(CHAR(STRING_ELT(path, 0)), Rf_asInteger(n), Rf_asInteger(p), INTEGER(devices), LENGTH(devices),
+                         BSG_LAYOUT_AUTO, &g));
+  SEXP xp = PROTECT(R_MakeExternalPtr(g, R_NilValue, R_NilValue));
+  R_RegisterCFinalizerEx(xp, group_finalizer, TRUE);
+  UNPROTECT(1);
+  return xp;
+}
+static bsg_group *group_of(SEXP xp) {
+  bsg_group *g = (TYPEOF(xp) == EXTPTRSXP) ? (bsg_group *)R_ExternalPtrAddr(xp) : NULL;
+  if (!g) Rf_error("external pointer is not valid");
+  return g;
+}
+SEXP _bigsnpr_group_pMatVec4_gpu(SEXP grp, SEXP ind_row, SEXP ind_col, SEXP center, SEXP scale, SEXP x, SEXP transpose) {
+  bsg_group *g = group_of(grp);
+  int nr = LENGTH(ind_row), nc = LENGTH(ind_col), tr = Rf_asLogical(transpose);
+  if (LENGTH(center) != nc || LENGTH(scale) != nc || LENGTH(x) != (tr ? nr : nc)) Rf_error("Incompatibility between dimensions.");
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, tr ? nc : nr));
+  chk((tr ? bsg_group_cprodvec : bsg_group_prodvec)(g, INTEGER(ind_row), nr, INTEGER(ind_col), nc, REAL(center), REAL(scale),
+                                                    REAL(x), REAL(out)));
+  UNPROTECT(1);
+  return out;
+}
+SEXP _bigsnpr_group_randomSVD_gpu(SEXP grp, SEXP ind_row, SEXP ind_col, SEXP center, SEXP scale, SEXP k, SEXP tol) {
+  bsg_group *g = group_of(grp);
+  int nr = LENGTH(ind_row), nc = LENGTH(ind_col), kk = Rf_asInteger(k), niter = 0, nops = 0;
+  SEXP d = PROTECT(Rf_allocVector(REALSXP, kk)), u = PROTECT(Rf_allocMatrix(REALSXP, nr, kk));
+  SEXP v = PROTECT(Rf_allocMatrix(REALSXP, nc, kk));
+  SEXP co = PROTECT(Rf_allocVector(REALSXP, nc)), so = PROTECT(Rf_allocVector(REALSXP, nc));
+  const double *cen = (center == R_NilValue) ? NULL : REAL(center), *sca = (scale == R_NilValue) ? NULL : REAL(scale);
+  chk(bsg_group_randomsvd(g, INTEGER(ind_row), nr, INTEGER(ind_col), nc, cen, sca, kk, Rf_asReal(tol), 1000, REAL(d), REAL(u),
+                          REAL(v), REAL(co), REAL(so), &niter, &nops));
+  const char *names[] = {"d", "u", "v", "niter", "nops", "center", "scale", ""};
+  SEXP res = PROTECT(Rf_mkNamed(VECSXP, names));
+  SET_VECTOR_ELT(res, 0, d); SET_VECTOR_ELT(res, 1, u); SET_VECTOR_ELT(res, 2, v);
+  SET_VECTOR_ELT(res, 3, Rf_ScalarInteger(niter)); SET_VECTOR_ELT(res, 4, Rf_ScalarInteger(nops));
+  SET_VECTOR_ELT(res, 5, co); SET_VECTOR_ELT(res, 6, so);
+  Rf_setAttrib(res, R_ClassSymbol, Rf_mkString("big_SVD"));
+  UNPROTECT(6);
+  return res;
+}
+SEXP _bigsnpr_group_tcrossprod_gpu(SEXP grp, SEXP ind_row, SEXP ind_col, SEXP center, SEXP scale) {
+  bsg_group *g = group_of(grp);
+  int nr = LENGTH(ind_row), nc = LENGTH(ind_col);
+  if (LENGTH(center) != nc || LENGTH(scale) != nc) Rf_error("Incompatibility between dimensions.");
+  SEXP K = PROTECT(Rf_allocMatrix(REALSXP, nr, nr));
+  chk(bsg_group_tcrossprod(g, INTEGER(ind_row), nr, INTEGER(ind_col), nc, REAL(center), REAL(scale), REAL(K)));
+  UNPROTECT(1);
+  return K;
+}
+
 /* registration: same table shape as src/RcppExports.cpp:597-640 (only the hot-path rows shown; the other
  * entries of the reference stay as generated) */
 static const R_CallMethodDef CallEntries[] = {
@@ -331,6 +444,10 @@ static const R_CallMethodDef CallEntries[] = {
     {"_bigsnpr_multLinReg", (DL_FUNC)&_bigsnpr_multLinReg, 5},
     {"_bigsnpr_bed_tcrossprod_gpu", (DL_FUNC)&_bigsnpr_bed_tcrossprod_gpu, 5},
     {"_bigsnpr_bed_randomSVD_gpu", (DL_FUNC)&_bigsnpr_bed_randomSVD_gpu, 7},
+    {"_bigsnpr_bed_group_gpu", (DL_FUNC)&_bigsnpr_bed_group_gpu, 4},
+    {"_bigsnpr_group_pMatVec4_gpu", (DL_FUNC)&_bigsnpr_group_pMatVec4_gpu, 7},
+    {"_bigsnpr_group_randomSVD_gpu", (DL_FUNC)&_bigsnpr_group_randomSVD_gpu, 7},
+    {"_bigsnpr_group_tcrossprod_gpu", (DL_FUNC)&_bigsnpr_group_tcrossprod_gpu, 5},
     {NULL, NULL, 0}};
 
 void R_init_bigsnpr_hotpath(DllInfo *dll) {
