@@ -230,19 +230,18 @@ def run_reference(args, wl):
     return 0
 
 
-def traffic_for(workload, kernel):
-    """dram bytes per launch of the dominant kernel from the committed ncu capture of the same kernel and shape
-    (bench.py cannot run under ncu and report a number; the source file is named beside the value)."""
-    for fn in ("r02_pmv_traffic.json", "r01_pmv_traffic.json"):
-        tp = os.path.join(ROOT, "profiles", fn)
-        if os.path.exists(tp):
-            try:
-                d = json.load(open(tp))
-                v = d.get("%s:%s" % (workload, kernel), d.get(workload) if "k_pmv<" in str(d.get("source", "")) and kernel.endswith("k_pmv") else None)
-                if v:
-                    return float(v), "profiles/%s (%s)" % (fn, d.get("source", "ncu --set full"))
-            except Exception:
-                pass
+def traffic_for(kernel, alg_bytes):
+    """DRAM bytes per launch of the dominant kernel: the ratio (dram read + write) / algorithmic bytes measured by the
+    committed ncu --set full captures of the same kernel (bench.py cannot run under ncu and report a number), applied to
+    this launch's algorithmic bytes; the source file is named beside the value."""
+    tp = os.path.join(ROOT, "profiles", "r02_pmv_traffic.json")
+    try:
+        d = json.load(open(tp))
+        r = d["ratio_vs_algorithmic"].get(kernel)
+        if r:
+            return float(r) * alg_bytes, "profiles/r02_pmv_traffic.json: measured ratio %.4f x algorithmic bytes; %s" % (r, d["source"])
+    except Exception:
+        pass
     return None, None
 
 
@@ -333,7 +332,7 @@ def run_workload(args, wl_key, torch, dist, B, L, rank, world, local, with_cpu, 
     peak, peak_src = measured_peaks()
     achieved = alg_bytes / (kern_ms / 1e3) / 1e9 if kern_ms > 0 else None
     kernel = ("bsg::pmvt::k_pmvT2" if g.has_na else ("bsg::pmv::k_pmv" if (layouts & 2) else "bsg::pmvt::k_pmvT"))
-    traffic, traffic_src = traffic_for(wl_key, kernel)
+    traffic, traffic_src = traffic_for(kernel, alg_bytes)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
                 "kernel": kernel, "kernel_ms": kern_ms, "launches_timed": cnt.value,

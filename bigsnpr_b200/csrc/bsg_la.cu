@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgram(const WArgs a) {
 }
 
 // weight digits in fragment order: byte ((chunk*4 + q)*4 + w)*16 + c*4 + r  <->  k = chunk*256 + (4q+w)*16 + 4r + c
-__global__ void k_weight_digits(const double *__restrict__ W, int len, int nchunks, int nslices, int e,
+__global__ void k_weight_digits(const double *__restrict__ W, int len, int nchunks, int nslices, int e, int dbits,
                                 uint8_t *__restrict__ dig) {
   int64_t total = (int64_t)nchunks * 256;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -322,8 +322,8 @@ __global__ void k_weight_digits(const double *__restrict__ W, int len, int nchun
     unsigned long long v = 0;
     if (k < len) v = (unsigned long long)__double2ll_rn(scalbn(W[k], e));
     for (int sl = 0; sl < nslices; sl++) {
-      dig[(int64_t)sl * total + t] = (uint8_t)(v & 63ull);
-      v >>= 6;
+      dig[(int64_t)sl * total + t] = (uint8_t)(v & ((1ull << dbits) - 1ull));
+      v >>= dbits;
     }
   }
 }
@@ -836,7 +836,10 @@ static int tcrossprod_impl(bsg_bed *h, const int *ind_row, int nr, const int *in
   BSG_TRY(bind_device(h));
   if (!ind_row) nr = h->n;
   if (!ind_col) nc = h->m;
-  static int force_dsyrk = -1, nslices = 8;
+  // Weight digits: base 128 (7 bits; the B byte code * digit <= 2 * 127 still fits u8 and a whole sweep of up to 4.2 M
+  // columns fits the int32 accumulator: 2 * 254 * m < 2^31), 4 slices = 28 bits of each per-SNP weight -> K agrees with
+  // the fp64 reference to ~1e-9, three orders inside the 1e-6 contract.  BSG_GRM_SLICES changes the count.
+  static int force_dsyrk = -1, nslices = 4;
   if (force_dsyrk < 0) {
     const char *ev = getenv("BSG_GRM_DSYRK");
     force_dsyrk = (ev && ev[0] == '1') ? 1 : 0;
@@ -907,17 +910,18 @@ static int tcrossprod_impl(bsg_bed *h, const int *ind_row, int nr, const int *in
   a.nchunks = nchunks;
   a.nslices = nslices;
   const double *Ws[3] = {W1, W2p, W3};
+  const int dbits = nc <= 4000000 ? 7 : 6;  // longer sweeps keep the int32 head-room with 6-bit digits (2 * 126 * m < 2^31 up to 8.5 M)
   for (int wv = 0; wv < 3; wv++) {
     uint8_t *dg = nullptr;
     BSG_TRY(mem.alloc(&dg, (size_t)nslices * nchunks * 256));
     int ex = 0;
     if (stats[wv] > 0) frexp(stats[wv], &ex);
-    const int e = 6 * nslices - 1 - ex;
+    const int e = dbits * nslices - 1 - ex;
     k_weight_digits<<<(int)std::min<int64_t>(((int64_t)nchunks * 256 + 255) / 256, 148 * 16), 256, 0, s>>>(Ws[wv], nc, nchunks,
-                                                                                                        nslices, e, dg);
+                                                                                                        nslices, e, dbits, dg);
     count_launch();
     a.dig[wv] = dg;
-    for (int sl = 0; sl < nslices; sl++) a.scale[wv][sl] = ldexp(1.0, 6 * sl - e);
+    for (int sl = 0; sl < nslices; sl++) a.scale[wv][sl] = ldexp(1.0, dbits * sl - e);
   }
 
   // ---- tiles of the lower triangle

@@ -101,8 +101,8 @@ def test_shim_bed_entry_points(R, oracle, obed_na, rng):
     with pytest.raises(RuntimeError, match="n or p does not match the dimensions of the file."):
         R.call("_bigsnpr_bedXPtr", R.s(path), R.ints([n]), R.ints([m - 1]))
     bed = _bed_env(R, path, n, m)
-    ir = (rng.choice(n, 300, replace=False) + 1).astype(np.int32)
-    ic = (rng.choice(m, 900, replace=False) + 1).astype(np.int32)
+    ir = (rng.choice(n, 150, replace=False) + 1).astype(np.int32)
+    ic = (rng.choice(m, 400, replace=False) + 1).astype(np.int32)
     one = R.ints([1])
     st = R.call("_bigsnpr_bed_colstats", bed, R.ints(ir), R.ints(ic), one)
     sto = oracle.bed_colstats(o, ir, ic)
