@@ -79,9 +79,9 @@ struct ArArgs {
 // integer slice sums instead of read from `src`).  The grid is at most one wave, so every block is resident while it
 // waits for the peers.
 template <bool FUSED>
-__global__ void __launch_bounds__(256) k_ar_oneshot(const ArArgs a, int64_t len, const double *__restrict__ src,
+__global__ void __launch_bounds__(256) k_ar_oneshot(const ArArgs a, int64_t len, const double *src,
                                                     const long long *__restrict__ part, const pmv::Scal *sc, int has_scaling,
-                                                    int use_na, double *__restrict__ out) {
+                                                    int use_na, double *out) {  // src may alias out (in-place form)
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < len; l += stride) {
     const double v = FUSED ? pmv::finish_prod_value(part, l, sc, has_scaling, use_na) : src[l];

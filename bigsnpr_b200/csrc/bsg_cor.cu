@@ -659,7 +659,10 @@ static int cor_common(bsg_bed *h, const int *ind_row, int nr, const int *ind_col
       if (g5) {
         bool any0 = false, any1 = false;
         for (const Tile &tl : tiles) (tl.mode ? any1 : any0) = true;
-        int rc5 = gram5_launch(sc.M, stride, nc, stride, d_tiles, (int)tiles.size(), d_sums, any0, any1, s);
+        // TMA-fed 2-CTA tiles over operands expanded once (bsg_gramt.cu); in-kernel expansion when they do not fit
+        bool done = false;
+        int rc5 = gramt_enabled() ? gramt_cor(sc.M, stride, nc, tiles.data(), (int)tiles.size(), d_sums, s, &done) : BSG_OK;
+        if (!rc5 && !done) rc5 = gram5_launch(sc.M, stride, nc, stride, d_tiles, (int)tiles.size(), d_sums, any0, any1, s);
         if (rc5) {
           cudaFree(d_tiles);
           cudaFree(d_rbs);

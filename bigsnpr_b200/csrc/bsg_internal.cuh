@@ -152,6 +152,14 @@ int wgram5_launch(const uint8_t *P, int64_t stride, int nlines, int nslices, con
                   int64_t dig_stride, const double (*scale)[10], const int *h_tiles, int ntiles, double *K,
                   int64_t ldk, cudaStream_t s);
 
+// ---- bsg_gramt.cu: integer Gram tiles fed by TMA, 2-CTA tcgen05 MMAs (GRM and windowed correlations) ----------
+namespace gram { struct Tile; }
+bool gramt_enabled();  // BSG_GRAM_TMA=0 selects the round-1 kernels (in-kernel expansion) for cross-checks
+int gramt_grm(const uint8_t *P, int64_t stride, int nr, int nc, const double *const Ws[3], const double wmax[3],
+              const uint8_t *na, int nslices, double *K, int64_t ldk, cudaStream_t s);
+int gramt_cor(const uint8_t *M, int64_t stride, int nlines, const gram::Tile *tiles, int ntiles, int *d_sums, cudaStream_t s,
+              bool *done);
+
 // ---- bsg_pmv.cu: packed matrix x vector on the integer tensor pipe ----------------------------
 struct PmvPlan;  // opaque, owned by a view
 namespace pmv { struct Scal; }

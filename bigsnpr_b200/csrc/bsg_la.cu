@@ -902,6 +902,15 @@ static int tcrossprod_impl(bsg_bed *h, const int *ind_row, int nr, const int *in
   BSG_CUDA(cudaStreamSynchronize(s));
   const int nchunks = (int)(stride / CHUNK);
 
+  double *dK = K_dev;
+  if (!K_dev) BSG_TRY(mem.alloc(&dK, (size_t)nr * nr));
+  BSG_CUDA(cudaMemsetAsync(dK, 0, (size_t)nr * nr * sizeof(double), s));
+  if (gramt_enabled() && nslices <= 4) {
+    // TMA-fed 2-CTA tcgen05 tiles over operands expanded once to uint8 (bsg_gramt.cu): all digit slices in one pass
+    const double *Ws3[3] = {W1, W2p, W3};
+    const double wmax[3] = {stats[0], stats[1], stats[2]};
+    BSG_TRY(gramt_grm(P, stride, nr, nc, Ws3, wmax, na.data(), nslices, dK, nr, s));
+  } else {
   // ---- weight digits (base 64, nslices digits) in fragment order
   WArgs a;
   a.P = P;
@@ -934,9 +943,6 @@ static int tcrossprod_impl(bsg_bed *h, const int *ind_row, int nr, const int *in
   const int njb = (nr + TNv - 1) / TNv;
   std::vector<uint8_t> na_jb(njb, 0);
   for (int i = 0; i < nr; i++) na_jb[i / TNv] |= na[i];
-  double *dK = K_dev;
-  if (!K_dev) BSG_TRY(mem.alloc(&dK, (size_t)nr * nr));
-  BSG_CUDA(cudaMemsetAsync(dK, 0, (size_t)nr * nr * sizeof(double), s));
   if (use_t5) {
     // 128 x 128 tiles on tcgen05 / TMEM (bsg_gram5.cu); digits are laid out 16 bytes per packed word, in order
     std::vector<int> trip;
@@ -969,6 +975,8 @@ static int tcrossprod_impl(bsg_bed *h, const int *ind_row, int nr, const int *in
     count_launch();
     BSG_CUDA(cudaGetLastError());
     BSG_CUDA(cudaStreamSynchronize(s));
+  }
+
   }
 
   // ---- vector terms through the matvec engine:  r = A w2 ;  q = N w3 = (X~_{c=1,s=1} w3) - A w3 + sum(w3)

@@ -35,9 +35,12 @@ def main():
     ap.add_argument("--clump-m", type=int, default=100000)
     ap.add_argument("--grm-n", type=int, default=10000)
     ap.add_argument("--grm-m", type=int, default=50000)
+    ap.add_argument("--ld-rho", type=float, default=0.9, help="LD-structured data for the windowed rows (0 = i.i.d.)")
+    ap.add_argument("--skip", default="", help="comma list of: cor, clump, grm")
     a = ap.parse_args()
     # --- snp_cor / ld_scores (configs[2] is 100,000 x 200,000, size 500: 9.99e7 pairs)
-    g = B.Bed.synthetic(a.cor_n, a.cor_m, seed=20250927, layouts=B.LAYOUT_SNP_MAJOR)
+    skip = set(a.skip.split(","))
+    g = B.Bed.synthetic(a.cor_n, a.cor_m, seed=20250927, layouts=B.LAYOUT_SNP_MAJOR, ld_rho=a.ld_rho)
     t, (p, i, x) = timeit(lambda: B.bed_cor(g, size=a.size))
     pairs = int(p[-1]) - a.cor_m
     print(json.dumps({"op": "bed_cor", "n": a.cor_n, "m": a.cor_m, "size": a.size, "pairs": pairs, "seconds": t,
@@ -49,7 +52,7 @@ def main():
     print(json.dumps({"op": "bed_counts(all)", "seconds": t}), flush=True)
     g.close()
     # --- bed_clumping (thr.r2 = 0.2, size = 500 kb on a 1 kb grid: 500 SNPs either side)
-    gc = B.Bed.synthetic(a.clump_n, a.clump_m, seed=20250929)
+    gc = B.Bed.synthetic(a.clump_n, a.clump_m, seed=20250929, ld_rho=a.ld_rho)
     chrom, pos = np.ones(a.clump_m, dtype=int), 1000.0 * np.arange(1, a.clump_m + 1)
     t, keep = timeit(lambda: B.bed_clumping(gc, infos_chr=chrom, infos_pos=pos))
     rec = {"op": "bed_clumping", "n": a.clump_n, "m": a.clump_m, "thr_r2": 0.2, "size_kb": 500, "seconds": t,
@@ -58,7 +61,7 @@ def main():
         from oracle import ref
 
         mo = min(a.clump_m, 1500)
-        o = ref.synth_bed(a.clump_n, mo, seed=20250929)
+        o = ref.synth_bed(a.clump_n, mo, seed=20250929, ld_rho=a.ld_rho)
         t0 = time.perf_counter()
         ko = ref.bed_clumping(o, infos_chr=chrom[:mo], infos_pos=pos[:mo])
         tc = time.perf_counter() - t0
