@@ -660,10 +660,22 @@ def _get_intervals(x, n=2):
     return out
 
 
+def _outlier_callable(outlier_fun, roll_size, alpha_tukey):
+    """"default": the reference's detector (OGK distance -> rolling mean -> adjusted Tukey fence, outliers.py);
+    None: never flag a variant (the loop stops after the first SVD); a callable is used as is."""
+    if outlier_fun == "default":
+        from .outliers import autosvd_outlier_fun
+
+        return autosvd_outlier_fun(roll_size, alpha_tukey)
+    return outlier_fun
+
+
 def snp_autoSVD(G, infos_chr, infos_pos=None, ind_row=..., ind_col=..., fun_scaling=None, thr_r2=0.2, size=None, k=10,
-                int_min_size=20, min_mac=10, min_maf=0.02, max_iter=5, ncores=1, verbose=False, outlier_fun=None):
+                roll_size=50, int_min_size=20, alpha_tukey=0.05, min_mac=10, min_maf=0.02, max_iter=5, ncores=1,
+                verbose=False, outlier_fun="default"):
     """R/autoSVD.R:67-186: the FBM.code256 twin of bed_autoSVD (snp_MAF -> snp_clumping -> randomSVD loop); `G` is a
     handle staged from an FBM (Bed.from_fbm).  Same remark on the outlier statistic as bed_autoSVD."""
+    outlier_fun = _outlier_callable(outlier_fun, roll_size, alpha_tukey)
     infos_chr = np.asarray(infos_chr)
     _assert_lengths(infos_chr, G.cols_along())
     if infos_pos is not None:
@@ -674,16 +686,20 @@ def snp_autoSVD(G, infos_chr, infos_pos=None, ind_row=..., ind_col=..., fun_scal
 
 
 def bed_autoSVD(obj_bed, ind_row=..., ind_col=..., fun_scaling=bed_scaleBinom, thr_r2=0.2, size=None, k=10,
-                int_min_size=20, min_mac=10, min_maf=0.02, max_iter=5, ncores=1, verbose=False, outlier_fun=None):
+                roll_size=50, int_min_size=20, alpha_tukey=0.05, min_mac=10, min_maf=0.02, max_iter=5, ncores=1,
+                verbose=False, outlier_fun="default"):
     """Truncated SVD while limiting LD (R/autoSVD.R:226-339): MAC / MAF filter (bed_MAF) -> clumping on MAC
-    (bed_clumping) -> bed_randomSVD, then up to `max_iter` rounds of outlier-variant removal.
+    (bed_clumping) -> bed_randomSVD, then up to `max_iter` rounds of outlier-variant removal, same arguments and defaults
+    as the reference (roll.size = 50, int.min.size = 20, alpha.tukey = 0.05).
 
-    The engine steps (counts, clumping, SVD) run on the GPU.  The outlier statistic of the reference is host-side R
-    code from bigutilsr (dist_ogk + rollmean + tukey_mc_up, un-vendored): pass it as
-    ``outlier_fun(v, infos_chr_keep) -> 0-based indices into the kept variants``; with ``outlier_fun=None`` the loop
-    stops after the first SVD (the reference's behaviour when no outlier is detected).  Returns the SVD dict plus
-    ``subset`` (1-based kept columns) and ``lrldr`` (list of (chr, start, stop, iter))."""
+    The engine steps (counts, clumping, SVD) run on the GPU.  The outlier statistic (R/autoSVD.R:295-302) is host-side
+    code on the (m x k) loadings: the default restates bigutilsr's dist_ogk / rollmean / tukey_mc_up from their published
+    algorithms (bigsnpr_b200/outliers.py -- bigutilsr is un-vendored, so this step's numbers are NOT pinned against the
+    reference; every engine step is).  ``outlier_fun`` may also be a callable ``(v, infos_chr_keep) -> 0-based indices
+    into the kept variants`` or None (no pruning).  Returns the SVD dict plus ``subset`` (1-based kept columns) and
+    ``lrldr`` (list of (chr, start, stop, iter))."""
     _assert_bed(obj_bed)
+    outlier_fun = _outlier_callable(outlier_fun, roll_size, alpha_tukey)
     return _auto_svd(obj_bed, obj_bed.map["chromosome"], obj_bed.map["physical.pos"], ind_row, ind_col, fun_scaling, thr_r2,
                      size, k, int_min_size, min_mac, min_maf, max_iter, ncores, verbose, outlier_fun, fbm=False)
 

@@ -513,6 +513,35 @@ static int cor_common(bsg_bed *h, const int *ind_row, int nr, const int *ind_col
   for (int j = 1; j < nc; j++)  // the reference asserts this in R (assert_sorted); the C ABI checks it too
     if (pos[j] < pos[j - 1]) return fail(BSG_ERR_ARG, "'pos' is not sorted.");
   build_window(pos, nc, size, w, clump != nullptr);
+  if (h->fbm_generic) {
+    // dosage FBM: the pair statistics come from fp64 sums over code256[byte] (bsg_generic.cu); thresholds, CSC assembly,
+    // LD reduction and the clumping sweep downstream are the same code
+    if (clump && !clump->fbm) BSG_PACKED_ONLY(h, "bed_clumping_chr");
+    BSG_TRY(to_dev(&sc.wlen, w.wlen, s));
+    BSG_TRY(to_dev(&sc.boff, w.boff, s));
+    const size_t tot = (size_t)(w.total ? w.total : 1);
+    double *d_sx = nullptr, *d_dx = nullptr;
+    if (clump) {
+      std::vector<double> c(clump->center, clump->center + nc), sv(clump->scale, clump->scale + nc);
+      BSG_TRY(to_dev(&d_sx, c, s));
+      BSG_TRY(to_dev(&d_dx, sv, s));
+      sc.thr = d_sx;  // owned by the scratch (freed with it)
+      sc.res = d_dx;
+      BSG_CUDA(cudaMalloc((void **)&sc.keep, tot));
+    } else {
+      BSG_CUDA(cudaMalloc((void **)&sc.band, tot * sizeof(double)));
+      if (!ld) {
+        std::vector<double> t(thr, thr + nr);
+        if (t.empty()) t.push_back(0.0);
+        BSG_TRY(to_dev(&sc.thr, t, s));
+        BSG_CUDA(cudaMalloc((void **)&sc.keep, tot));
+      }
+    }
+    BSG_TRY(generic_pairs(h, d_row, nr, d_col, nc, clump ? 3 : (ld ? 1 : 0), sc.wlen, sc.boff, w.total, clump ? nullptr : sc.thr,
+                          sc.band, sc.keep, d_sx, d_dx, clump ? clump->thr : 0.0, s));
+    BSG_CUDA(cudaStreamSynchronize(s));
+    return BSG_OK;
+  }
   // identity rows and columns: the staged SNP-major copy already is the dense matrix (stride multiple of 128)
   auto ident = [](const int *ind, int len, int lim) {
     if (!ind) return true;

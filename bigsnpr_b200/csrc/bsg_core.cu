@@ -596,15 +596,17 @@ int bsg_open_fbm256(const uint8_t *bytes, int n, int m, const double *code256, i
   if (!out || !bytes || !code256) return fail(BSG_ERR_ARG, "null argument");
   *out = nullptr;
   uint8_t map[256];
+  bool generic = false;  // a code other than 0 / 1 / 2 / NA (dosages, CODE_DOSAGE): the handle keeps the bytes, fp64 kernels
   for (int k = 0; k < 256; k++) {
     double v = code256[k];
     if (v != v) map[k] = 3;
     else if (v == 0.0) map[k] = 0;
     else if (v == 1.0) map[k] = 1;
     else if (v == 2.0) map[k] = 2;
-    else
-      return fail(BSG_ERR_TYPE,
-                  "FBM.code256 with codes other than 0, 1, 2, NA (e.g. dosages) is not supported by the packed engine.");
+    else {
+      map[k] = 3;
+      generic = true;
+    }
   }
   bsg_bed *h = nullptr;
   BSG_TRY(alloc_handle(n, m, device, &h));
@@ -623,6 +625,19 @@ int bsg_open_fbm256(const uint8_t *bytes, int n, int m, const double *code256, i
     k_stage_fbm<<<grid_for((int64_t)m * (h->strideA / 4), 256), 256, 0, h->stream>>>(draw, n, m, dmap, h->A, h->strideA);
     count_launch();
     cudaStreamSynchronize(h->stream);
+  }
+  if (generic && !rc) {  // keep the code bytes and the table: bsg_generic.cu reads code256[byte] like SubBMCode256Acc does
+    h->fbm_generic = 1;
+    h->raw = draw;
+    draw = nullptr;
+    double both[512];
+    for (int k = 0; k < 256; k++) {
+      both[k] = code256[k];
+      both[256 + k] = (code256[k] != code256[k]) ? 3.0 : code256[k];  // code[is_na(code)] = 3 (src/corr.cpp:115)
+    }
+    ce = cudaMalloc((void **)&h->d_code, sizeof both);
+    if (ce == cudaSuccess) ce = cudaMemcpy(h->d_code, both, sizeof both, cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) rc = cuda_fail(ce, "upload code256");
   }
   if (draw) cudaFree(draw);
   if (dmap) cudaFree(dmap);
@@ -643,7 +658,7 @@ void bsg_close(bsg_bed *h) {
     bsg_view_destroy(h->cv);
     h->cv = nullptr;
   }
-  void *ptrs[] = {h->A, h->B, h->cntA, h->cntB, h->naA, h->naB, h->naColOff, h->naRowOff, h->naColIdx, h->naRowIdx};
+  void *ptrs[] = {h->A, h->B, h->cntA, h->cntB, h->naA, h->naB, h->naColOff, h->naRowOff, h->naColIdx, h->naRowIdx, h->raw, h->d_code};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   DevBuf *bufs[] = {&h->w_idx_row, &h->w_idx_col, &h->w_center, &h->w_scale, &h->w_x, &h->w_out, &h->w_tmp0,
@@ -664,6 +679,7 @@ int64_t bsg_packed_bytes(const bsg_bed *h) { return h ? h->n_byte * (int64_t)h->
 
 int bsg_export_packed(const bsg_bed *h, uint8_t *out) {
   if (!h || !out) return fail(BSG_ERR_ARG, "null argument");
+  BSG_PACKED_ONLY(h, "The 2-bit export");
   BSG_TRY(bind_device(h));
   uint8_t *d = nullptr;
   size_t bytes = (size_t)h->n_byte * h->m;

@@ -93,7 +93,9 @@ struct bsg_bed {
   int64_t na_nnz = 0;
   int na_lists = 0;          // 0 not tried yet, 1 resident, -1 not used (rate too high, no memory, disabled)
   double code256[256];       // FBM handles: value of each raw byte code (bigstatsr code256)
-  int fbm_generic = 0;       // FBM whose codes are not {0,1,2,NA}: only 0/1/2/NA repack is supported
+  int fbm_generic = 0;       // FBM whose codes are not {0,1,2,NA} (dosages ...): served by the fp64 kernels of bsg_generic.cu
+  uint8_t *raw = nullptr;    // generic FBM: the n x m code bytes, column-major, as in the .bk file
+  double *d_code = nullptr;  // generic FBM: code256 on the device [0,256) and the same with NA -> 3 [256,512)
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // view cached for the 9-argument drop-in matvec calls (bsg_prodvec / bsg_cprodvec)
@@ -151,6 +153,24 @@ int gram5_launch(const uint8_t *P, int64_t stride, int nlines, int64_t line_byte
 int wgram5_launch(const uint8_t *P, int64_t stride, int nlines, int nslices, const uint8_t *const dig[3],
                   int64_t dig_stride, const double (*scale)[10], const int *h_tiles, int ntiles, double *K,
                   int64_t ldk, cudaStream_t s);
+
+// ---- bsg_generic.cu: fp64 fallback for FBM.code256 handles whose codes are not 0 / 1 / 2 / NA (dosages) --------------
+#define BSG_PACKED_ONLY(h, what)                                                                                          \
+  do {                                                                                                                    \
+    if ((h)->fbm_generic)                                                                                                 \
+      return bsg::fail(BSG_ERR_TYPE, "%s needs hard calls (codes 0 / 1 / 2 / NA); this FBM.code256 holds other values "    \
+                                     "(dosages): snp_colstats, snp_cor, snp_ld_scores, snp_clumping and snp_pcadapt are served " \
+                                     "by the fp64 kernels, the packed engine is not.", what);                             \
+  } while (0)
+int generic_colstats(bsg_bed *h, const int *d_row, int nr, const int *d_col, int nc, double *d_sumX, double *d_denoX,
+                     cudaStream_t s);
+// pair statistics of the windowed correlations straight from the code bytes; kind 0: r + keep (threshold), 1: r^2,
+// 3: clumping_chr conflict flag (src/clumping.cpp:66-73) with the caller's sumX / denoX
+int generic_pairs(bsg_bed *h, const int *d_row, int nr, const int *d_col, int nc, int kind, const int *d_wlen,
+                  const long long *d_boff, long long total, const double *d_thr, double *d_band, uint8_t *d_keep,
+                  const double *d_sumX, const double *d_denoX, double thr_r2, cudaStream_t s);
+int generic_multlinreg(bsg_bed *h, const int *d_row, int nr, const int *d_col, int nc, const double *d_U, int K,
+                       double *d_out, cudaStream_t s);
 
 // ---- bsg_gramt.cu: integer Gram tiles fed by TMA, 2-CTA tcgen05 MMAs (GRM and windowed correlations) ----------
 namespace gram { struct Tile; }

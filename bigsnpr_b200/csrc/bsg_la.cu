@@ -832,6 +832,7 @@ extern "C" {
 static int tcrossprod_impl(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, const double *center,
                            const double *scale, double *K, double *K_dev) {
   if (!h || (!K && !K_dev)) return fail(BSG_ERR_ARG, "null argument");
+  BSG_PACKED_ONLY(h, "The Gram product");
   if (!center || !scale) return fail(BSG_ERR_DIM, "Incompatibility between dimensions.");
   BSG_TRY(bind_device(h));
   if (!ind_row) nr = h->n;

@@ -1360,6 +1360,7 @@ int bsg_view_create(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, 
                     const double *scale, bsg_view **out) {
   if (!h || !out) return fail(BSG_ERR_ARG, "null argument");
   *out = nullptr;
+  BSG_PACKED_ONLY(h, "The packed matrix-vector engine");
   BSG_TRY(bind_device(h));
   if (!ind_row) nr = h->n;
   if (!ind_col) nc = h->m;
@@ -2207,6 +2208,23 @@ int bsg_multlinreg(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, i
                    double *tscores) {
   if (!h || !tscores || (!U && K > 0)) return fail(BSG_ERR_ARG, "null argument");
   if (K < 0) return fail(BSG_ERR_ARG, "negative length");
+  if (h->fbm_generic) {  // dosage FBM: literal fp64 sums over code256[byte] (bsg_generic.cu)
+    BSG_TRY(bind_device(h));
+    if (!ind_row) nr = h->n;
+    if (!ind_col) nc = h->m;
+    if (nc == 0 || K == 0) return BSG_OK;
+    cudaStream_t gs = h->stream;
+    const int *d_row = nullptr, *d_col = nullptr;
+    BSG_TRY(upload_index(h, ind_row, nr, h->n, h->w_idx_row, &d_row));
+    BSG_TRY(upload_index(h, ind_col, nc, h->m, h->w_idx_col, &d_col));
+    BSG_TRY(h->w_tmp1.ensure((size_t)std::max(nr, 1) * K * sizeof(double)));
+    BSG_TRY(h->w_tmp2.ensure((size_t)nc * K * sizeof(double)));
+    BSG_CUDA(cudaMemcpyAsync(h->w_tmp1.p, U, (size_t)nr * K * sizeof(double), cudaMemcpyHostToDevice, gs));
+    BSG_TRY(generic_multlinreg(h, d_row, nr, d_col, nc, h->w_tmp1.as<double>(), K, h->w_tmp2.as<double>(), gs));
+    BSG_CUDA(cudaMemcpyAsync(tscores, h->w_tmp2.p, (size_t)nc * K * sizeof(double), cudaMemcpyDeviceToHost, gs));
+    BSG_CUDA(cudaStreamSynchronize(gs));
+    return BSG_OK;
+  }
   bsg_view *v = nullptr;
   BSG_TRY(cached_view(h, ind_row, nr, ind_col, nc, nullptr, nullptr, &v));
   nr = v->nr;

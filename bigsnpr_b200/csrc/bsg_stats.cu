@@ -90,10 +90,13 @@ using namespace bsg;
 
 #define FIX_DIMS()                         \
   if (!h) return fail(BSG_ERR_ARG, "null handle"); \
+  if (h->fbm_generic && !generic_ok) BSG_PACKED_ONLY(h, "This entry point"); \
   BSG_TRY(bind_device(h));                 \
   if (!ind_row) nr = h->n;                 \
   if (!ind_col) nc = h->m;                 \
   if (nr < 0 || nc < 0) return fail(BSG_ERR_ARG, "negative length");
+
+static const bool generic_ok = false;  // entry points that serve dosage FBMs shadow this with `true`
 
 extern "C" {
 
@@ -159,14 +162,22 @@ int bsg_colstats(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int
 }
 
 int bsg_snp_colstats(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, double *sumX, double *denoX) {
+  const bool generic_ok = true;
   FIX_DIMS();
   cudaStream_t s = h->stream;
-  int32_t *d = nullptr;
-  BSG_TRY(col_counts_dev(h, ind_row, nr, ind_col, nc, &d));
   size_t nn = (size_t)(nc > 0 ? nc : 1);
   BSG_TRY(h->w_tmp1.ensure(nn * sizeof(double)));
   BSG_TRY(h->w_tmp2.ensure(nn * sizeof(double)));
-  if (nc > 0) {
+  int32_t *d = nullptr;
+  if (h->fbm_generic) {  // dosage codes: fp64 sums of code256[byte] (bsg_generic.cu)
+    const int *d_row = nullptr, *d_col = nullptr;
+    BSG_TRY(upload_index(h, ind_row, nr, h->n, h->w_idx_row, &d_row));
+    BSG_TRY(upload_index(h, ind_col, nc, h->m, h->w_idx_col, &d_col));
+    BSG_TRY(generic_colstats(h, d_row, nr, d_col, nc, h->w_tmp1.as<double>(), h->w_tmp2.as<double>(), s));
+  } else {
+    BSG_TRY(col_counts_dev(h, ind_row, nr, ind_col, nc, &d));
+  }
+  if (nc > 0 && !h->fbm_generic) {
     k_snp_colstats_from_counts<<<(nc + 255) / 256, 256, 0, s>>>(d, nc, nr, h->w_tmp1.as<double>(),
                                                               h->w_tmp2.as<double>());
     count_launch();

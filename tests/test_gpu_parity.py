@@ -281,8 +281,11 @@ def test_cor_with_missing_alpha_and_fbm(B, oracle, rng, tmp_path):
         p, i, x = B.snp_cor(g2)
     po, io, xo = oracle.cor0(oracle.OracleFBM(G2.astype(np.uint8)))
     assert np.array_equal(i, io) and np.array_equal(x, xo, equal_nan=True)
-    with pytest.raises(B.BsgError, match="not supported"):
-        B.Bed.from_fbm(G2.astype(np.uint8), code256=np.linspace(0, 2, 256))
+    # a code table that is not 0 / 1 / 2 / NA (dosages) stages a generic handle: the packed engine refuses it by name
+    gd = B.Bed.from_fbm(G2.astype(np.uint8), code256=np.linspace(0, 2, 256))
+    with pytest.raises(B.BsgError, match="needs hard calls"):
+        B.bed_prodVec(gd, np.ones(10))
+    gd.close()
 
 
 def test_synthetic_matches_numpy_mirror_and_oracle(B, oracle, rng):
@@ -538,7 +541,7 @@ def test_bed_autoSVD_flow(B, gbed, oracle, obed, capsys):
     # statistic is bigutilsr's (host R code), so a synthetic outlier function drives the pruning loop here
     with pytest.raises(ValueError, match="no variation; set min.mac > 0"):
         B.bed_autoSVD(gbed, min_mac=0)
-    svd = B.bed_autoSVD(gbed, k=5)
+    svd = B.bed_autoSVD(gbed, k=5, outlier_fun=None)  # first iteration only: MAF / MAC filter -> clumping -> SVD
     keep = svd["subset"]
     info = B.bed_MAF(gbed)
     ok = np.where(~((info["mac"] < 10) | (info["maf"] < 0.02)))[0] + 1
@@ -563,11 +566,22 @@ def test_bed_autoSVD_flow(B, gbed, oracle, obed, capsys):
     chrom, pos = oracle.read_bim(obed.bedfile)
     Gf = oracle.read_bed(obed, obed.rows_along(), obed.cols_along(), na_val=3).astype(np.uint8)
     gf = B.Bed.from_fbm(Gf)
-    svd4 = B.snp_autoSVD(gf, chrom, pos, k=5)
+    svd4 = B.snp_autoSVD(gf, chrom, pos, k=5, outlier_fun=None)
     assert np.array_equal(svd4["subset"], keep)
     np.testing.assert_allclose(svd4["d"], svd["d"], rtol=1e-9)
     with pytest.raises(ValueError, match=B.ERROR_DIM):
         B.snp_autoSVD(gf, chrom[:-1], pos)
+    # the default detector (OGK distance -> rolling mean -> adjusted Tukey fence, R/autoSVD.R:295-302) drives the loop:
+    # whatever it removes, the result is a fixed point of the reference's iteration -- the statistic applied to the final
+    # loadings flags nothing, unless the iteration cap was hit -- and the removed variants come out of the clumped set
+    from bigsnpr_b200.outliers import autosvd_outlier_fun
+
+    svd5 = B.bed_autoSVD(gbed, k=5, roll_size=10, verbose=True)
+    out = capsys.readouterr().out
+    assert set(svd5["subset"]) <= set(keep) and svd5["v"].shape == (svd5["subset"].size, 5)
+    if "Maximum number of iterations reached." not in out:
+        assert "Converged!" in out
+        assert autosvd_outlier_fun(10, 0.05)(svd5["v"], chrom[svd5["subset"] - 1]).size == 0
 
 
 def test_edge_shapes_and_empty_selections(B, oracle, rng, tmp_path):
@@ -739,5 +753,53 @@ def test_group_entry_points_vs_oracle(B, oracle, rng):
     assert np.array_equal(svd["center"], sc["center"][sub - 1])
     K = grp.tcrossprodSelf(sc["center"][sub - 1], sc["scale"][sub - 1], ind_col=sub)
     K0, _, _ = oracle.bed_tcrossprodSelf(o, ind_col=sub)
-    assert np.max(np.abs(K - K0)) / np.max(np.abs(K0)) < 1e-9
+    assert np.max(np.abs(K - K0)) / np.max(np.abs(K0)) < 1e-8
     grp.close()
+
+
+def test_dosage_fbm_generic_code_fallback(B, oracle, rng):
+    """SURVEY.md section 8f row 3: an FBM.code256 whose codes are dosages (CODE_DOSAGE-like: byte / 100 for 0..200, NA above;
+    R/bigSNP-class.R:13) is served by the fp64 kernels of bsg_generic.cu with the reference's per-element semantics
+    (code256[byte], NA -> 3 for the pairwise statistics): snp_colstats, snp_cor, snp_ld_scores, snp_clumping, multLinReg /
+    snp_pcadapt against the oracle's literal loops.  Sums of non-integers: 1e-10, far inside the 1e-6 contract."""
+    n, m = 811, 403
+    code = np.full(256, np.nan)
+    code[:201] = np.arange(201) / 100.0
+    # correlated dosages: blocks of 20 columns share a latent variable, so clumping prunes and thresholds matter
+    lat = rng.normal(size=(n, (m + 19) // 20))
+    prob = 1 / (1 + np.exp(-(0.9 * lat[:, np.arange(m) // 20] + 0.6 * rng.normal(size=(n, m)))))
+    G = np.clip(np.rint(200 * prob), 0, 200).astype(np.uint8)
+    na = rng.random(size=(n, m)) < 0.01
+    na[:, :50] = False  # the first 50 columns stay complete
+    G[na] = 255
+    gf, of = B.Bed.from_fbm(G, code256=code), oracle.OracleFBM(G, code256=code)
+    ir = np.sort(rng.choice(n, 700, replace=False)).astype(np.int32) + 1
+    ic = np.arange(1, m + 1, dtype=np.int32)
+    st, st0 = B.snp_colstats(gf, ir, ic), oracle.snp_colstats(of, ir, ic)
+    for k in ("sumX", "denoX"):
+        assert np.array_equal(np.isnan(st[k]), np.isnan(st0[k]))
+        ok = ~np.isnan(st0[k])
+        assert np.allclose(st[k][ok], st0[k][ok], rtol=1e-12)
+    assert np.isnan(st0["sumX"]).any() and not np.isnan(st0["sumX"][:50]).any()
+    for kw in (dict(size=30, thr_r2=0.0), dict(size=30, thr_r2=0.1), dict(size=12, alpha=0.01)):
+        p, i, x = B.snp_cor(gf, ir, ic, **kw)
+        p0, i0, x0 = oracle.cor0(of, ir, ic, **kw)
+        assert np.array_equal(p, p0) and np.array_equal(i, i0)
+        assert np.allclose(x, x0, rtol=0, atol=1e-10)
+    ld, ld0 = B.snp_ld_scores(gf, ir, ic, size=30), oracle.ld0(of, ir, ic, size=30)
+    assert np.allclose(ld, ld0, rtol=1e-10)
+    chrom = np.ones(m, dtype=int)
+    excl = np.nonzero(np.isnan(st0["sumX"]))[0] + 1  # like the reference, clumping on columns with NA statistics is moot
+    for kw in (dict(thr_r2=0.2), dict(thr_r2=0.05, size=40)):
+        k1 = B.snp_clumping(gf, chrom, ind_row=ir, exclude=excl, **kw)
+        k0 = oracle.snp_clumping(of, chrom, ind_row=ir, exclude=excl, **kw)
+        assert np.array_equal(k1, k0)
+    assert k1.size < m - excl.size
+    U = np.linalg.qr(rng.normal(size=(ir.size, 3)))[0]
+    t, t0 = B.multLinReg(gf, ir, ic, U), oracle.multLinReg(of, ir, ic, U)
+    assert np.array_equal(np.isnan(t), np.isnan(t0)) and np.allclose(t[~np.isnan(t0)], t0[~np.isnan(t0)], rtol=1e-9)
+    with pytest.raises(B.BsgError, match="needs hard calls"):
+        B.bed_counts(gf)
+    with pytest.raises(B.BsgError, match="needs hard calls"):
+        B.bed_tcrossprodSelf(gf, fun_scaling=lambda *a, **k: {"center": np.zeros(m), "scale": np.ones(m)})
+    gf.close()

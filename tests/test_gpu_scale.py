@@ -12,7 +12,7 @@ itself -- on the shapes whose code paths do not exist at fixture size:
 The relational form is the reference's own (tests/testthat/test-5-bed-prod-vec.R:18-41: products == dense decode %*% vector,
 default and random center / scale); the oracle's loops are that dense product restated literally.  Tolerances are the
 north_star's: bit-exact for counts / indices, 1e-6 relative for floating point -- the tests ask for much less
-(1e-11 of the vector scale for the products, 1e-10 for r, 1e-9 for K).
+(1e-11 of the vector scale for the products, 1e-10 for r, 1e-8 for K: 28-bit weights).
 """
 import numpy as np
 import pytest
@@ -158,7 +158,7 @@ def test_cfg4_slice_grm_vs_oracle(B, oracle):
         K0, c0, s0 = oracle.bed_tcrossprodSelf(o, block_size=2000)
         assert np.array_equal(c, c0) and np.array_equal(s, s0)
         err = np.max(np.abs(K - K0)) / np.max(np.abs(K0))
-        assert err < 1e-9, err
+        assert err < 1e-8, err  # 28-bit weights (4 base-128 digit slices), exact integer Gram per slice
         assert np.array_equal(K, K.T)
         g.close()
 

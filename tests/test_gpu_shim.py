@@ -151,7 +151,7 @@ def test_shim_bed_entry_points(R, oracle, obed_na, rng):
     sc2 = oracle.bed_scaleBinom(o, alli, sub)
     K = R.vec(R.call("_bigsnpr_bed_tcrossprod_gpu", bed, R.ints(alli), R.ints(sub), R.reals(sc2["center"]), R.reals(sc2["scale"])))
     K0, _, _ = oracle.bed_tcrossprodSelf(o, ind_col=sub)
-    assert np.max(np.abs(K - K0)) < 1e-9 * np.max(np.abs(K0))
+    assert np.max(np.abs(K - K0)) < 1e-8 * np.max(np.abs(K0))
     sv = R.call("_bigsnpr_bed_randomSVD_gpu", bed, R.ints(alli), R.ints(sub), R.L.minir_nil(), R.L.minir_nil(), R.ints([5]), R.reals([1e-4]))
     d = R.vec(R.named(sv, "d"))
     assert np.max(np.abs(d - np.sqrt(np.linalg.eigvalsh(K0)[::-1][:5])) / d) < 1e-7  # tests/testthat/test-2-bed-clumping-SVD.R:76-78
@@ -161,7 +161,7 @@ def test_shim_bed_entry_points(R, oracle, obed_na, rng):
     bg = R.vec(R.call("_bigsnpr_group_pMatVec4_gpu", grp, R.ints(ir), R.ints(ic), R.reals(sc["center"]), R.reals(sc["scale"]), R.reals(y), R.L.minir_lgl(1)))
     assert np.array_equal(ag, a) and np.array_equal(bg, b)
     Kg = R.vec(R.call("_bigsnpr_group_tcrossprod_gpu", grp, R.ints(alli), R.ints(sub), R.reals(sc2["center"]), R.reals(sc2["scale"])))
-    assert np.max(np.abs(Kg - K0)) < 1e-9 * np.max(np.abs(K0))
+    assert np.max(np.abs(Kg - K0)) < 1e-8 * np.max(np.abs(K0))
     with pytest.raises(RuntimeError, match="Unknown object type."):  # src/corr.cpp:124
         R.call("_bigsnpr_ld_scores", R.env(nrow=R.ints([1])), R.ints(ir), R.ints(ics), R.reals([50e3]), R.reals(pos), one)
     R.L.minir_run_finalizers()  # what R's GC does with the external pointers
