@@ -215,7 +215,12 @@ def test_shim_fbm_entry_points(R, oracle, obed, rng, tmp_path):
     # writebina from the FBM (snp_writeBed) -> bytes of the original file; readbina2 back into a raw FBM
     outbed = tmp_path / "out.bed"
     R.call("_bigsnpr_writebina", R.s(str(outbed)), fbm, R.ints(np.zeros(1, dtype=np.int32)), R.ints(ir), R.ints(np.arange(1, m + 1)))
-    assert outbed.read_bytes() == open(path, "rb").read()
+    raw = np.frombuffer(outbed.read_bytes(), dtype=np.uint8)
+    assert bytes(raw[:3]) == bytes([108, 27, 1])
+    # the reference's writer pads the last byte of a column with genotype 0 (code 11), PLINK pads with 00: compare with the
+    # oracle's restatement of src/write-plink.cpp:29-47, and decode back to the same genotypes
+    assert np.array_equal(raw[3:].reshape(m, -1), oracle.write_bed_bytes(G))
+    assert np.array_equal(oracle.decode_dense(oracle.OracleBed.from_packed(raw[3:], n, m)), G)
     sub_r, sub_c = ir[::3], np.arange(1, m + 1, 7, dtype=np.int32)
     rb = tmp_path / "read.bk"
     np.zeros(sub_r.size * sub_c.size, dtype=np.uint8).tofile(rb)
