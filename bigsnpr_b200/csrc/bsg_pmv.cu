@@ -1202,6 +1202,100 @@ __global__ void k_quantT(int mode, const double *__restrict__ x, const double *_
     }
   }
 }
+
+// ---- two vectors per pass (PCA projection, bsg_prod_and_rowsumssq) ---------------------------------------------------
+// An IMMA always produces 8 columns; with the full 61-bit fixed point all 8 are digit slices of ONE vector.  For the K
+// columns of a projection the vectors are quantised to 30 bits instead (4 signed base-256 digits, |Q| < 2^30 relative to
+// the largest entry of the vector: ~1e-9 of the result, three orders inside the 1e-6 contract) and TWO vectors share a
+// pass: columns 0..3 = vector 1, 4..7 = vector 2.  Same kernels, same bytes read, twice the vectors.
+__global__ void k_pick_exp_pair(pmv::Scal *sc, int headroom_bits) {
+  const int v = threadIdx.x >> 1, p = threadIdx.x & 1;  // 4 threads: (vector, plane)
+  if (threadIdx.x >= 4) return;
+  const double m = sc[v].maxabs[p];
+  int ex = 0;
+  if (m > 0 && isfinite(m)) {
+    frexp(m, &ex);
+    sc[v].e[p] = 30 - ex - headroom_bits;  // |Q| < 2^30 fits 4 signed base-256 digits (max 127 * (2^32 - 1) / 255)
+  } else {
+    sc[v].e[p] = 0;
+  }
+}
+
+// dig[(t / 32) * 256 + slice * 32 + (t % 32)], slices 0..3 = vector 1, 4..7 = vector 2; dig2 = the (c - 3) z plane
+__global__ void k_quantT_pair(int mode, const double *__restrict__ xa, const double *__restrict__ xb,
+                              const double *__restrict__ center, const double *__restrict__ scale, int len, int len_pad,
+                              const pmv::Scal *sc, uint8_t *__restrict__ dig1, uint8_t *__restrict__ dig2) {
+  const int e0a = sc[0].e[0], e1a = sc[0].e[1], e0b = sc[1].e[0], e1b = sc[1].e[1];
+  const bool bada = sc[0].nonfinite != 0, badb = sc[1].nonfinite != 0;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < len_pad; t += gridDim.x * blockDim.x) {
+    long long q[2][2] = {{0, 0}, {0, 0}};  // [vector][plane]
+    if (t < len) {
+      double v0, v1;
+      if (!bada) {
+        pmv::make_vals(mode, xa, center, scale, t, v0, v1);
+        q[0][0] = __double2ll_rn(scalbn(v0, e0a));
+        if (dig2) q[0][1] = __double2ll_rn(scalbn(v1, e1a));
+      }
+      if (xb && !badb) {
+        pmv::make_vals(mode, xb, center, scale, t, v0, v1);
+        q[1][0] = __double2ll_rn(scalbn(v0, e0b));
+        if (dig2) q[1][1] = __double2ll_rn(scalbn(v1, e1b));
+      }
+    }
+    const int64_t base = (int64_t)(t >> 5) * 256 + (t & 31);
+#pragma unroll
+    for (int vv = 0; vv < 2; vv++)
+#pragma unroll
+      for (int sl = 0; sl < 4; sl++) {
+        int d = (int)(signed char)(q[vv][0] & 0xFF);
+        q[vv][0] = (q[vv][0] - d) >> 8;
+        dig1[base + (4 * vv + sl) * 32] = (uint8_t)d;
+        if (dig2) {
+          int d2 = (int)(signed char)(q[vv][1] & 0xFF);
+          q[vv][1] = (q[vv][1] - d2) >> 8;
+          dig2[base + (4 * vv + sl) * 32] = (uint8_t)d2;
+        }
+      }
+  }
+}
+
+// (raw-plane * c0 + NA-plane * c1) over the 4 slices of vector vv
+__device__ __forceinline__ double combine4(const long long *__restrict__ part, int64_t line, int vv, int c0, int c1, int e) {
+  const long long *p = part + line * 16 + 4 * vv;
+  double acc = 0;
+#pragma unroll
+  for (int s = 3; s >= 0; s--) {
+    long long v = 0;
+    if (c0) v += c0 * p[s];
+    if (c1) v += c1 * p[8 + s];
+    acc += scalbn((double)v, 8 * s - e);
+  }
+  return acc;
+}
+
+__global__ void k_finish_prod_pair(const long long *__restrict__ part, int nlines, const pmv::Scal *sc, int has_scaling,
+                                   int use_na, double *__restrict__ out1, double *__restrict__ out2) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= nlines) return;
+#pragma unroll
+  for (int vv = 0; vv < 2; vv++) {
+    double *out = vv ? out2 : out1;
+    if (!out) continue;
+    double r;
+    if (sc[vv].nonfinite) {
+      r = nan("");
+    } else if (has_scaling) {
+      double C = 0;
+      for (int b = 0; b < pmv::SUMCZ_BLOCKS; b++) C += sc[vv].cpart[b];
+      const double R = combine4(part, l, vv, 1, 0, sc[vv].e[0]);
+      const double Nw = use_na ? combine4(part, l, vv, 0, 1, sc[vv].e[1]) : 0.0;
+      r = (R + Nw) - C;
+    } else {
+      r = combine4(part, l, vv, 1, use_na ? -3 : 0, sc[vv].e[0]);
+    }
+    out[l] = r;
+  }
+}
 }  // namespace pmvt
 
 // =============================================================================================
@@ -1421,7 +1515,7 @@ int bsg_view_create(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, 
     rc = dev_copy((void **)&v->d_center, center, (size_t)nc * sizeof(double), s);
     if (!rc) rc = dev_copy((void **)&v->d_scale, scale, (size_t)nc * sizeof(double), s);
   }
-  if (!rc) rc = v->s_scal.ensure(sizeof(pmv::Scal));
+  if (!rc) rc = v->s_scal.ensure(2 * sizeof(pmv::Scal));  // the second block serves the two-vectors-per-pass mode
   cudaError_t e = cudaStreamSynchronize(s);  // host vectors go out of scope
   if (!rc && e != cudaSuccess) rc = cuda_fail(e, "view upload");
   if (rc) {
@@ -1607,9 +1701,27 @@ static int run_pmvT(bsg_view *v, const uint8_t *dig_raw, int plane, const uint8_
     const char *ev = getenv("BSG_PMVT_WAVES");
     waves = ev ? std::max(1, std::min(64, atoi(ev))) : 4;
   }
-  int ks = std::max(1, (waves * 2 * nsm) / a.nblocks);
-  ks = std::min(ks, std::max(1, nsteps / 32));                             // at least 32 steps per item
-  ks = std::max(ks, (nc + MAX_LINES_PER_ITEM - 1) / MAX_LINES_PER_ITEM);  // int32 accumulator head-room
+  // k-split: the grid (nblocks x ksplit CTAs, 2 resident per SM) should fill WHOLE waves -- 3.2 waves cost as much as 4
+  // (measured on the configs[4] 1/8 shard: 238 blocks x 4 splits = 952 CTAs over 296 slots, 0.79 instead of 0.89 of the HBM
+  // peak).  Among the admissible counts pick the one whose last wave is fullest, preferring >= `waves` waves.
+  auto pick_ks = [&](int nblocks) {
+    const int slots = 2 * nsm;
+    const int lo = std::max(1, (nc + MAX_LINES_PER_ITEM - 1) / MAX_LINES_PER_ITEM);  // int32 accumulator head-room
+    const int hi = std::max(lo, std::min(std::max(1, nsteps / 32), std::max(lo, (4 * waves * slots) / std::max(nblocks, 1))));
+    int best = lo;
+    double best_score = -1;
+    for (int ks = lo; ks <= hi; ks++) {
+      const double ctas = (double)nblocks * ks, nwav = ceil(ctas / slots);
+      double score = ctas / (nwav * slots);             // occupancy of the waves
+      if (nwav < waves) score *= 0.9 + 0.1 * nwav / waves;  // very few waves: the per-CTA ramp-up shows
+      if (score > best_score + 1e-9) {
+        best_score = score;
+        best = ks;
+      }
+    }
+    return best;
+  };
+  int ks = pick_ks(a.nblocks);
   a.lines_per_split = (int)round_up((nc + ks - 1) / ks, TLINES);
   a.ksplit = (nc + a.lines_per_split - 1) / a.lines_per_split;
   static unsigned attr_done = 0;  // one bit per device: function attributes are per device
@@ -1635,9 +1747,7 @@ static int run_pmvT(bsg_view *v, const uint8_t *dig_raw, int plane, const uint8_
   } else {
     // both planes in one pass: 32-byte strips per warp, twice the sample blocks
     a.nblocks = (int)((nbytes + T2BYTES - 1) / T2BYTES);
-    int ks2 = std::max(1, (waves * 2 * nsm) / a.nblocks);
-    ks2 = std::min(ks2, std::max(1, nsteps / 32));
-    ks2 = std::max(ks2, (nc + MAX_LINES_PER_ITEM - 1) / MAX_LINES_PER_ITEM);
+    const int ks2 = pick_ks(a.nblocks);
     a.lines_per_split = (int)round_up((nc + ks2 - 1) / ks2, TLINES);
     a.ksplit = (nc + a.lines_per_split - 1) / a.lines_per_split;
     const int grid = a.nblocks * a.ksplit;
@@ -1724,6 +1834,55 @@ static int prodvec_T(bsg_view *v, const double *x_dev, double *out_dev, cudaStre
   }
   BSG_CUDA(cudaGetLastError());
   if (comm) return comm_allreduce_oneshot(comm, out_dev, v->nr, s);
+  return BSG_OK;
+}
+
+// X~ [xa | xb] from the SNP-major copy in ONE pass over the matrix (two vectors, 4 + 4 digit slices; see k_quantT_pair).
+// xb / outb may be null (odd count).  Outputs in the caller's row order.
+static int prodvec_T_pair(bsg_view *v, const double *xa, const double *xb, double *outa, double *outb, cudaStream_t s) {
+  using namespace pmv;
+  using namespace pmvt;
+  bsg_bed *h = v->h;
+  Scal *sc = v->s_scal.as<Scal>();
+  const int n = h->n, nc = v->nc;
+  const int mode = v->has_scaling ? 1 : 0;
+  const bool two = v->has_scaling && h->has_na;  // the NA plane has its own digits ((c - 3) z); else it reuses the raw ones
+  const int nsteps = (nc + TLINES - 1) / TLINES;
+  BSG_TRY(v->s_dig1.ensure((size_t)std::max(nsteps, 1) * 256));
+  if (two) BSG_TRY(v->s_dig2.ensure((size_t)std::max(nsteps, 1) * 256));
+  for (int vv = 0; vv < 2; vv++) {
+    const double *x = vv ? xb : xa;
+    k_scal_reset<<<1, 1, 0, s>>>(sc + vv);
+    count_launch();
+    if (!x) continue;
+    k_maxabs<<<launch_cap(nc, 256, 592), 256, 0, s>>>(mode, x, v->d_center, v->d_scale, nc, sc + vv);
+    if (v->has_scaling) k_sum_cz<<<SUMCZ_BLOCKS, 256, 0, s>>>(x, v->d_center, v->d_scale, nc, sc[vv].cpart);
+    count_launch(v->has_scaling ? 2 : 1);
+  }
+  k_pick_exp_pair<<<1, 32, 0, s>>>(sc, 0);
+  k_quantT_pair<<<launch_cap((int64_t)std::max(nsteps, 1) * TLINES, 256, 1184), 256, 0, s>>>(
+      mode, xa, xb, v->d_center, v->d_scale, nc, nsteps * TLINES, sc, v->s_dig1.as<uint8_t>(),
+      two ? v->s_dig2.as<uint8_t>() : nullptr);
+  count_launch(2);
+  long long *part = nullptr;
+  BSG_TRY(run_pmvT(v, v->s_dig1.as<uint8_t>(), h->has_na ? 1 : 0, two ? v->s_dig2.as<uint8_t>() : v->s_dig1.as<uint8_t>(),
+                   &part, s));
+  double *fa = outa, *fb = outb;
+  if (!v->row_identity) {
+    BSG_TRY(v->s_full.ensure((size_t)n * 2 * sizeof(double)));
+    fa = v->s_full.as<double>();
+    fb = outb ? fa + n : nullptr;
+  }
+  if (n > 0) {
+    k_finish_prod_pair<<<(n + 255) / 256, 256, 0, s>>>(part, n, sc, v->has_scaling, h->has_na, fa, fb);
+    count_launch();
+  }
+  if (!v->row_identity && v->nr > 0) {
+    k_gather<<<(v->nr + 255) / 256, 256, 0, s>>>(fa, v->d_row, v->nr, outa);
+    if (outb) k_gather<<<(v->nr + 255) / 256, 256, 0, s>>>(fb, v->d_row, v->nr, outb);
+    count_launch(outb ? 2 : 1);
+  }
+  BSG_CUDA(cudaGetLastError());
   return BSG_OK;
 }
 
@@ -2163,10 +2322,27 @@ int bsg_prod_and_rowsumssq(bsg_bed *h, const int *ind_row, int nr, const int *in
   }
   int *d_bad = reinterpret_cast<int *>(d_cols + 3 * (size_t)nc + NP);  // any pass saw a non-finite quantity
   BSG_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), s));
-  for (int k = 0; k < K; k++) {
-    BSG_TRY(bsg_view_prodvec_dev(v, dV + (size_t)k * nc, dXV + (size_t)k * nr, s));
-    k_or_flag<<<1, 1, 0, s>>>(v->s_scal.as<pmv::Scal>(), d_bad);
-    count_launch();
+  static int pair_mode = -1;
+  if (pair_mode < 0) {
+    const char *ev = getenv("BSG_PROJ_PAIR");
+    pair_mode = (ev && ev[0] == '0') ? 0 : 1;
+  }
+  if (pair_mode && K >= 2) {
+    // two columns of V per pass over the matrix (30-bit fixed point per vector, see k_quantT_pair)
+    for (int k = 0; k < K; k += 2) {
+      const bool both = k + 1 < K;
+      BSG_TRY(prodvec_T_pair(v, dV + (size_t)k * nc, both ? dV + (size_t)(k + 1) * nc : nullptr, dXV + (size_t)k * nr,
+                             both ? dXV + (size_t)(k + 1) * nr : nullptr, s));
+      k_or_flag<<<1, 1, 0, s>>>(v->s_scal.as<pmv::Scal>(), d_bad);
+      k_or_flag<<<1, 1, 0, s>>>(v->s_scal.as<pmv::Scal>() + 1, d_bad);
+      count_launch(2);
+    }
+  } else {
+    for (int k = 0; k < K; k++) {
+      BSG_TRY(bsg_view_prodvec_dev(v, dV + (size_t)k * nc, dXV + (size_t)k * nr, s));
+      k_or_flag<<<1, 1, 0, s>>>(v->s_scal.as<pmv::Scal>(), d_bad);
+      count_launch();
+    }
   }
   bool need_simple = false;
   {

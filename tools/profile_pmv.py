@@ -35,13 +35,23 @@ def main():
     ox = torch.empty(a.n, dtype=torch.float64, device=dev)
     oy = torch.empty(a.m, dtype=torch.float64, device=dev)
     s = torch.cuda.current_stream().cuda_stream
+    import ctypes as C
+
+    from bigsnpr_b200 import _lib
+
+    L = _lib.lib()
+    L.bsg_set_kernel_timing(1)
     for _ in range(a.reps):
         if a.side in ("x", "both"):
             v.prodvec_dev(x.data_ptr(), ox.data_ptr(), s)
         if a.side in ("xt", "both"):
             v.cprodvec_dev(y.data_ptr(), oy.data_ptr(), s)
     torch.cuda.synchronize()
-    print("done", float(ox.sum()), float(oy.sum()))
+    cnt, tot = C.c_int(0), C.c_double(0)
+    L.bsg_kernel_time_stats(C.byref(cnt), C.byref(tot))
+    alg = ((a.n + 3) // 4) * a.m
+    ms = tot.value / max(cnt.value, 1)
+    print("done", float(ox.sum()), float(oy.sum()), "avg kernel ms %.4f over %d launches -> %.1f GB/s" % (ms, cnt.value, alg / ms / 1e6))
 
 
 if __name__ == "__main__":
