@@ -529,14 +529,14 @@ static int cor_common(bsg_bed *h, const int *ind_row, int nr, const int *ind_col
       BSG_TRY(to_dev(&d_dx, sv, s));
       sc.thr = d_sx;  // owned by the scratch (freed with it)
       sc.res = d_dx;
-      BSG_CUDA(cudaMalloc((void **)&sc.keep, tot));
+      BSG_CUDA(pool_alloc((void **)&sc.keep, tot, h->device, s));
     } else {
-      BSG_CUDA(cudaMalloc((void **)&sc.band, tot * sizeof(double)));
+      BSG_CUDA(pool_alloc((void **)&sc.band, tot * sizeof(double), h->device, s));
       if (!ld) {
         std::vector<double> t(thr, thr + nr);
         if (t.empty()) t.push_back(0.0);
         BSG_TRY(to_dev(&sc.thr, t, s));
-        BSG_CUDA(cudaMalloc((void **)&sc.keep, tot));
+        BSG_CUDA(pool_alloc((void **)&sc.keep, tot, h->device, s));
       }
     }
     BSG_TRY(generic_pairs(h, d_row, nr, d_col, nc, clump ? 3 : (ld ? 1 : 0), sc.wlen, sc.boff, w.total, clump ? nullptr : sc.thr,
@@ -577,14 +577,14 @@ static int cor_common(bsg_bed *h, const int *ind_row, int nr, const int *ind_col
     BSG_TRY(to_dev(&d_cs, sv, s));
     sc.thr = d_cc;   // owned by the scratch (freed with it)
     sc.res = d_cs;
-    BSG_CUDA(cudaMalloc((void **)&sc.keep, (size_t)(w.total ? w.total : 1)));
+    BSG_CUDA(pool_alloc((void **)&sc.keep, (size_t)(w.total ? w.total : 1), h->device, s));
   } else {
-    BSG_CUDA(cudaMalloc((void **)&sc.band, (size_t)(w.total ? w.total : 1) * sizeof(double)));
+    BSG_CUDA(pool_alloc((void **)&sc.band, (size_t)(w.total ? w.total : 1) * sizeof(double), h->device, s));
     if (!ld) {
       std::vector<double> t(thr, thr + nr);
       if (t.empty()) t.push_back(0.0);
       BSG_TRY(to_dev(&sc.thr, t, s));
-      BSG_CUDA(cudaMalloc((void **)&sc.keep, (size_t)(w.total ? w.total : 1)));
+      BSG_CUDA(pool_alloc((void **)&sc.keep, (size_t)(w.total ? w.total : 1), h->device, s));
     }
   }
   static int use_popc = -1;
@@ -679,7 +679,7 @@ static int cor_common(bsg_bed *h, const int *ind_row, int nr, const int *ind_col
       int *d_sums = nullptr;
       BSG_CUDA(cudaMalloc((void **)&d_tiles, tiles.size() * sizeof(Tile)));
       BSG_CUDA(cudaMalloc((void **)&d_rbs, rbs.size() * sizeof(RowBlock)));
-      cudaError_t e = cudaMalloc((void **)&d_sums, used * sizeof(int));
+      cudaError_t e = pool_alloc((void **)&d_sums, used * sizeof(int), h->device, s);
       if (e != cudaSuccess) {
         cudaFree(d_tiles);
         cudaFree(d_rbs);
@@ -692,7 +692,7 @@ static int cor_common(bsg_bed *h, const int *ind_row, int nr, const int *ind_col
         for (const Tile &tl : tiles) (tl.mode ? any1 : any0) = true;
         // TMA-fed 2-CTA tiles over operands expanded once (bsg_gramt.cu); in-kernel expansion when they do not fit
         bool done = false;
-        int rc5 = gramt_enabled() ? gramt_cor(sc.M, stride, nc, tiles.data(), (int)tiles.size(), d_sums, s, &done) : BSG_OK;
+        int rc5 = gramt_enabled() ? gramt_cor(sc.M, stride, nc, tiles.data(), (int)tiles.size(), d_sums, h->device, s, &done) : BSG_OK;
         if (!rc5 && !done) rc5 = gram5_launch(sc.M, stride, nc, stride, d_tiles, (int)tiles.size(), d_sums, any0, any1, s);
         if (rc5) {
           cudaFree(d_tiles);

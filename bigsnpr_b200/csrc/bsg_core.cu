@@ -52,6 +52,32 @@ void DevBuf::release() {
   cap = 0;
 }
 
+// Large per-call work buffers (expanded Gram operands, pair statistics) come from the device's stream-ordered pool with a
+// high release threshold: the second call of a session (LD scores, then correlations, then clumping on the same data) reuses
+// the pages instead of paying cudaMalloc / cudaFree of tens of GB each time.  cudaFree on such a pointer returns it to
+// the pool.
+cudaError_t pool_alloc(void **p, size_t bytes, int device, cudaStream_t s) {
+  static unsigned configured = 0;  // one bit per device
+  if (!(configured >> (device & 31) & 1u)) {
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long thr = (unsigned long long)48 << 30;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    cudaGetLastError();
+    configured |= 1u << (device & 31);
+  }
+  cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 16, s);
+  if (e != cudaSuccess) {  // pool exhausted or fragmented: trim and take the plain path
+    cudaGetLastError();
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    cudaGetLastError();
+    e = cudaMalloc(p, bytes ? bytes : 16);
+  }
+  return e;
+}
+
 int bind_device(const bsg_bed *h) {
   BSG_CUDA(cudaSetDevice(h->device));
   return BSG_OK;
@@ -658,7 +684,8 @@ void bsg_close(bsg_bed *h) {
     bsg_view_destroy(h->cv);
     h->cv = nullptr;
   }
-  void *ptrs[] = {h->A, h->B, h->cntA, h->cntB, h->naA, h->naB, h->naColOff, h->naRowOff, h->naColIdx, h->naRowIdx, h->raw, h->d_code};
+  void *ptrs[] = {h->A, h->B, h->cntA, h->cntB, h->naA, h->naB, h->raw, h->d_code, h->ellCnt[0], h->ellCnt[1], h->ellEnt[0],
+                  h->ellEnt[1], h->ellOff[0], h->ellOff[1], h->ellOut[0], h->ellOut[1]};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   DevBuf *bufs[] = {&h->w_idx_row, &h->w_idx_col, &h->w_center, &h->w_scale, &h->w_x, &h->w_out, &h->w_tmp0,

@@ -400,7 +400,7 @@ bool gramt_enabled() {
 // Columns are processed in blocks of at most KBLK codes: expand -> one launch per plane product -> K accumulates in fp64.
 // ---------------------------------------------------------------------------------------------------------------------------
 int gramt_grm(const uint8_t *P, int64_t stride, int nr, int nc, const double *const Ws[3], const double wmax[3],
-              const uint8_t *na, int nslices, double *K, int64_t ldk, cudaStream_t s) {
+              const uint8_t *na, int nslices, double *K, int64_t ldk, int device, cudaStream_t s) {
   using namespace gt;
   if (nslices > NBMAX) nslices = NBMAX;
   const int dbits = 7;
@@ -420,7 +420,7 @@ int gramt_grm(const uint8_t *P, int64_t stride, int nr, int nc, const double *co
     }
   } fr;
   auto alloc = [&](void **q, size_t bytes) -> int {
-    cudaError_t e = cudaMalloc(q, bytes ? bytes : 16);
+    cudaError_t e = pool_alloc(q, bytes, device, s);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(Gram operand buffers)");
     fr.p.push_back(*q);
     return BSG_OK;
@@ -506,8 +506,8 @@ int gramt_grm(const uint8_t *P, int64_t stride, int nr, int nc, const double *co
 // list the epilogue kernels use; mode 0: product aa only, mode 1: the six plane products).  M = packed SNP-major lines.
 // Returns BSG_OK with *done = false when the operand buffers do not fit (the caller then runs the in-kernel-expansion path).
 // ---------------------------------------------------------------------------------------------------------------------------
-int gramt_cor(const uint8_t *M, int64_t stride, int nlines, const gram::Tile *tiles, int ntiles, int *d_sums, cudaStream_t s,
-              bool *done) {
+int gramt_cor(const uint8_t *M, int64_t stride, int nlines, const gram::Tile *tiles, int ntiles, int *d_sums, int device,
+              cudaStream_t s, bool *done) {
   using namespace gt;
   *done = false;
   if (ntiles == 0) {
@@ -527,13 +527,13 @@ int gramt_cor(const uint8_t *M, int64_t stride, int nlines, const gram::Tile *ti
   const int64_t lines_pad = round_up(nl, 256);
   const int64_t pitch = stride * 4;  // every code slot of the line, pads included (they count as valid on both sides)
   const int nplanes = any_na ? 3 : 1;  // a, b, h (or the raw codes alone)
-  size_t fr = 0, tot = 0;
-  cudaMemGetInfo(&fr, &tot);
   const size_t need = (size_t)nplanes * lines_pad * pitch;
-  if (need + ((size_t)2 << 30) > fr) return BSG_OK;  // not enough room: fall back
   uint8_t *E = nullptr;
   GtTile *d_gt = nullptr;
-  BSG_CUDA(cudaMalloc((void **)&E, need));
+  if (pool_alloc((void **)&E, need, device, s) != cudaSuccess) {  // not enough room: the caller falls back
+    cudaGetLastError();
+    return BSG_OK;
+  }
   struct Free {
     void *a, *b;
     ~Free() {

@@ -87,11 +87,12 @@ struct bsg_bed {
   int32_t *cntB = nullptr;   // [n][4] counts per sample over all m SNPs (only with copy B)
   uint8_t *naA = nullptr;    // [m] 1 if the SNP line has a missing value
   uint8_t *naB = nullptr;    // [n]
-  // sparse missing-value lists, built on first use when the missing rate is low (bsg_pmv.cu: ensure_na_lists)
-  int64_t *naColOff = nullptr, *naRowOff = nullptr;  // [m + 1] / [n + 1]
-  int32_t *naColIdx = nullptr, *naRowIdx = nullptr;  // sample indices per SNP line / SNP indices per sample
+  // missing-value positions as blocked-ELL lists (bsg_naell.cu), built on first use; side 0: lines = samples, 1: lines = SNPs
+  uint16_t *ellCnt[2] = {nullptr, nullptr}, *ellEnt[2] = {nullptr, nullptr};
+  long long *ellOff[2] = {nullptr, nullptr}, *ellOut[2] = {nullptr, nullptr};
+  int ellChunks[2] = {0, 0}, ellGroups[2] = {0, 0};
   int64_t na_nnz = 0;
-  int na_lists = 0;          // 0 not tried yet, 1 resident, -1 not used (rate too high, no memory, disabled)
+  int na_ell = 0;            // 0 not tried yet, 1 resident, -1 not used (rate too high, no memory, disabled)
   double code256[256];       // FBM handles: value of each raw byte code (bigstatsr code256)
   int fbm_generic = 0;       // FBM whose codes are not {0,1,2,NA} (dosages ...): served by the fp64 kernels of bsg_generic.cu
   uint8_t *raw = nullptr;    // generic FBM: the n x m code bytes, column-major, as in the .bk file
@@ -113,6 +114,7 @@ namespace bsg {
 int stage_finish(bsg_bed *h);  // counts and NA flags from copy A; copy B only when requested
 int build_copy_B(bsg_bed *h);  // sample-major copy on demand (no-op when resident)
 int bind_device(const bsg_bed *h);
+cudaError_t pool_alloc(void **p, size_t bytes, int device, cudaStream_t s);  // stream-ordered pool, freed with cudaFree
 
 // ---- index helpers (bsg_core.cu) -------------------------------------------------------------
 // validates 1-based host indices against `limit` (src/bed-acc.h:64-65) and uploads them 0-based.
@@ -154,6 +156,10 @@ int wgram5_launch(const uint8_t *P, int64_t stride, int nlines, int nslices, con
                   int64_t dig_stride, const double (*scale)[10], const int *h_tiles, int ntiles, double *K,
                   int64_t ldk, cudaStream_t s);
 
+// ---- bsg_naell.cu: missing values of the matvecs as blocked-ELL lists gathered from shared memory -------------------
+bool na_ell_ready(bsg_bed *h);
+int na_ell_correction(bsg_bed *h, int side, const int *lines, int nlines, const long long *Q, long long *part, cudaStream_t s);
+
 // ---- bsg_generic.cu: fp64 fallback for FBM.code256 handles whose codes are not 0 / 1 / 2 / NA (dosages) --------------
 #define BSG_PACKED_ONLY(h, what)                                                                                          \
   do {                                                                                                                    \
@@ -176,9 +182,9 @@ int generic_multlinreg(bsg_bed *h, const int *d_row, int nr, const int *d_col, i
 namespace gram { struct Tile; }
 bool gramt_enabled();  // BSG_GRAM_TMA=0 selects the round-1 kernels (in-kernel expansion) for cross-checks
 int gramt_grm(const uint8_t *P, int64_t stride, int nr, int nc, const double *const Ws[3], const double wmax[3],
-              const uint8_t *na, int nslices, double *K, int64_t ldk, cudaStream_t s);
-int gramt_cor(const uint8_t *M, int64_t stride, int nlines, const gram::Tile *tiles, int ntiles, int *d_sums, cudaStream_t s,
-              bool *done);
+              const uint8_t *na, int nslices, double *K, int64_t ldk, int device, cudaStream_t s);
+int gramt_cor(const uint8_t *M, int64_t stride, int nlines, const gram::Tile *tiles, int ntiles, int *d_sums, int device,
+              cudaStream_t s, bool *done);
 
 // ---- bsg_pmv.cu: packed matrix x vector on the integer tensor pipe ----------------------------
 struct PmvPlan;  // opaque, owned by a view

@@ -910,7 +910,7 @@ static int tcrossprod_impl(bsg_bed *h, const int *ind_row, int nr, const int *in
     // TMA-fed 2-CTA tcgen05 tiles over operands expanded once to uint8 (bsg_gramt.cu): all digit slices in one pass
     const double *Ws3[3] = {W1, W2p, W3};
     const double wmax[3] = {stats[0], stats[1], stats[2]};
-    BSG_TRY(gramt_grm(P, stride, nr, nc, Ws3, wmax, na.data(), nslices, dK, nr, s));
+    BSG_TRY(gramt_grm(P, stride, nr, nc, Ws3, wmax, na.data(), nslices, dK, nr, h->device, s));
   } else {
   // ---- weight digits (base 64, nslices digits) in fragment order
   WArgs a;

@@ -1,0 +1,343 @@
+// bsg_naell.cu -- missing values of the matvecs as blocked-ELL lists (DESIGN.md "Missing values").
+//
+// With missing values X.y and Xt.y need, per output line l, the sum N_l = sum_{t : code(l, t) missing} v[t] of the quantised
+// vector over the line's missing entries (src/bed-acc.h:98-111: a missing genotype contributes 0 after centering).  Round 1
+// had two ways to get it: a second plane of IMMAs over the whole matrix (X.y 1.68 ms instead of 1.07 ms at configs[1] with
+// 1 % missing: the kernel becomes issue-bound) or CSR lists gathered warp-per-line from global memory, which cost one L1
+// tag lookup per missing value (0.9 ms per 1 %) and lost to the plane above 0.5 %.
+//
+// Here the positions are stored so that the gather runs out of SHARED memory with coalesced index loads:
+//   * the contraction index is cut into chunks of 4096; the quantised vector of one chunk (4096 x int64 = 32 KB) sits in
+//     shared memory while every line group consumes its entries of that chunk;
+//   * lines are grouped by 32; a block (group g, chunk c) stores its entries ELL style -- entry t of the 32 lines contiguous,
+//     16-bit chunk-local indices, padded to the longest line of the block -- so a warp reads 64 contiguous bytes per step and
+//     each lane adds shared[idx] to its own line's exact 64-bit sum (split in 32-bit halves: no overflow, order free);
+//   * a warp keeps the sums of its groups in registers across all chunks: one plain store per line at the end, no atomics.
+// 2 bytes per missing value and side (+ padding ~35 % at 1 %), built once per handle from the SNP-major copy.  The matvec
+// kernels then always run in their no-missing mode.  Results equal the flag-plane path up to fp64 rounding of the last
+// combination (the sums themselves are exact integers).
+#include <stdint.h>
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include <cub/device/device_scan.cuh>
+
+#include "bsg_internal.cuh"
+
+namespace bsg {
+namespace naell {
+
+constexpr int CH = 4096;      // contraction indices per chunk (16-bit local index, 32 KB of int64 in shared memory)
+constexpr int GW = 16;        // line groups per warp and pass
+constexpr int CORR_WARPS = 8;
+
+__device__ __forceinline__ uint32_t na_flags(uint32_t x) { return x & (x >> 1) & 0x55555555u; }
+
+// ---- side 1: lines = SNPs (rows of the SNP-major copy), contraction over samples ------------------------------------
+// warp per (line j, chunk c): the chunk is 1024 bytes = 256 words of the line
+__global__ void k_cnt_lines(const uint8_t *__restrict__ A, int64_t stride, int n, int m, int nchunks, uint16_t *__restrict__ cnt) {
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int wpl = (int)(stride / 4);
+  for (int64_t it = warp; it < (int64_t)m * nchunks; it += nw) {
+    const int j = (int)(it / nchunks), c = (int)(it - (int64_t)j * nchunks);
+    const uint32_t *line = reinterpret_cast<const uint32_t *>(A + (int64_t)j * stride);
+    int k = 0;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      const int w = c * (CH / 16) + r * 32 + lane;
+      k += __popc(w < wpl ? na_flags(line[w]) : 0u);  // pad slots are code 0, never missing
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) k += __shfl_xor_sync(0xffffffffu, k, o);
+    if (lane == 0) cnt[((int64_t)(j >> 5) * nchunks + c) * 32 + (j & 31)] = (uint16_t)k;
+  }
+}
+__global__ void k_fill_lines(const uint8_t *__restrict__ A, int64_t stride, int n, int m, int nchunks,
+                             const long long *__restrict__ off, uint16_t *__restrict__ ent) {
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int wpl = (int)(stride / 4);
+  for (int64_t it = warp; it < (int64_t)m * nchunks; it += nw) {
+    const int j = (int)(it / nchunks), c = (int)(it - (int64_t)j * nchunks);
+    const uint32_t *line = reinterpret_cast<const uint32_t *>(A + (int64_t)j * stride);
+    uint16_t *dst = ent + off[(int64_t)(j >> 5) * nchunks + c] * 32 + (j & 31);
+    int base = 0;
+    for (int r = 0; r < 8; r++) {
+      const int w = c * (CH / 16) + r * 32 + lane;
+      uint32_t f = w < wpl ? na_flags(line[w]) : 0u;
+      const int k = __popc(f);
+      int pre = k;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, pre, o);
+        if (lane >= o) pre += v;
+      }
+      const int tot = __shfl_sync(0xffffffffu, pre, 31);
+      int t = base + pre - k;
+      while (f) {
+        const int b = __ffs(f) - 1;
+        f &= f - 1;
+        dst[(int64_t)t * 32] = (uint16_t)((r * 32 + lane) * 16 + (b >> 1));
+        t++;
+      }
+      base += tot;
+    }
+  }
+}
+
+// ---- side 0: lines = samples, contraction over SNPs: a CTA owns 512 samples (32 words) x the 4096 SNP lines of a chunk ----
+__global__ void __launch_bounds__(256) k_cnt_samples(const uint8_t *__restrict__ A, int64_t stride, int n, int m, int nchunks,
+                                                     uint16_t *__restrict__ cnt) {
+  __shared__ unsigned int sc[512];
+  const int c = blockIdx.x, wb = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int t = threadIdx.x; t < 512; t += 256) sc[t] = 0;
+  __syncthreads();
+  const int64_t byte = ((int64_t)wb * 32 + lane) * 4;
+  const int j1 = min(m, (c + 1) * CH);
+  if (byte + 4 <= stride) {
+    for (int j = c * CH + warp; j < j1; j += 8) {
+      uint32_t f = na_flags(*reinterpret_cast<const uint32_t *>(A + (int64_t)j * stride + byte));
+      while (f) {
+        const int b = __ffs(f) - 1;
+        f &= f - 1;
+        atomicAdd(&sc[lane * 16 + (b >> 1)], 1u);
+      }
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < 512; t += 256) {
+    const int64_t i = (int64_t)wb * 512 + t;
+    if (i < n) cnt[((i >> 5) * nchunks + c) * 32 + (i & 31)] = (uint16_t)sc[t];
+  }
+}
+__global__ void __launch_bounds__(256) k_fill_samples(const uint8_t *__restrict__ A, int64_t stride, int n, int m, int nchunks,
+                                                      const long long *__restrict__ off, uint16_t *__restrict__ ent) {
+  __shared__ unsigned int cur[512];
+  const int c = blockIdx.x, wb = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int t = threadIdx.x; t < 512; t += 256) cur[t] = 0;
+  __syncthreads();
+  const int64_t byte = ((int64_t)wb * 32 + lane) * 4;
+  const int j1 = min(m, (c + 1) * CH);
+  if (byte + 4 <= stride) {
+    for (int j = c * CH + warp; j < j1; j += 8) {
+      uint32_t f = na_flags(*reinterpret_cast<const uint32_t *>(A + (int64_t)j * stride + byte));
+      while (f) {
+        const int b = __ffs(f) - 1;
+        f &= f - 1;
+        const int sl = lane * 16 + (b >> 1);
+        const int64_t i = (int64_t)wb * 512 + sl;
+        if (i < n) {
+          const unsigned int t = atomicAdd(&cur[sl], 1u);  // any order: the sums are integers
+          ent[(off[(i >> 5) * nchunks + c] + t) * 32 + (i & 31)] = (uint16_t)(j - c * CH);
+        }
+      }
+    }
+  }
+}
+
+// longest line of every block (32 lines x one chunk)
+__global__ void k_block_max(const uint16_t *__restrict__ cnt, int64_t nblocks, long long *__restrict__ blk) {
+  for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b <= nblocks; b += (int64_t)gridDim.x * blockDim.x) {
+    int mx = 0;
+    if (b < nblocks)
+      for (int r = 0; r < 32; r++) mx = max(mx, (int)cnt[b * 32 + r]);
+    blk[b] = mx;
+  }
+}
+
+// N[line] = sum of Q over the line's missing entries, as (low 32-bit halves, high halves) exact 64-bit sums
+__global__ void __launch_bounds__(CORR_WARPS * 32) k_corr(const uint16_t *__restrict__ cnt, const long long *__restrict__ off,
+                                                          const uint16_t *__restrict__ ent, int nchunks, int ngroups,
+                                                          const long long *__restrict__ Q, int64_t qlen,
+                                                          long long *__restrict__ outN) {
+  __shared__ long long sq[CH];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t W = (int64_t)blockIdx.x * CORR_WARPS + warp, TW = (int64_t)gridDim.x * CORR_WARPS;
+  const int npass = (int)((ngroups + TW * GW - 1) / (TW * GW));
+  for (int pass = 0; pass < npass; pass++) {
+    // groups are dealt round-robin over the warps of the grid: group (pass * GW + k) * TW + W
+    long long lo[GW], hi[GW];
+#pragma unroll
+    for (int k = 0; k < GW; k++) lo[k] = hi[k] = 0;
+    for (int c = 0; c < nchunks; c++) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < CH; t += CORR_WARPS * 32) {
+        const int64_t q = (int64_t)c * CH + t;
+        sq[t] = q < qlen ? Q[q] : 0;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < GW; k++) {
+        const int64_t g = ((int64_t)pass * GW + k) * TW + W;
+        if (g < ngroups) {  // warp-uniform
+          const int64_t blk = g * nchunks + c;
+          const int nme = cnt[blk * 32 + lane];
+          int mx = nme;
+#pragma unroll
+          for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+          const uint16_t *e = ent + off[blk] * 32 + lane;
+          for (int t = 0; t < mx; t++) {
+            const uint16_t idx = e[(int64_t)t * 32];
+            if (t < nme) {
+              const long long q = sq[idx];
+              lo[k] += (long long)(unsigned int)(q & 0xFFFFFFFFll);
+              hi[k] += q >> 32;
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < GW; k++) {
+      const int64_t g = ((int64_t)pass * GW + k) * TW + W;
+      if (g < ngroups) {
+        outN[(g * 32 + lane) * 2] = lo[k];
+        outN[(g * 32 + lane) * 2 + 1] = hi[k];
+      }
+    }
+  }
+}
+
+// part[l][8] = low sum, part[l][12] = high sum (x 2^32 = 256^4): the finish kernels read the eight NA slices as
+// sum_s part[l][8 + s] * 256^s, which this representation satisfies exactly
+__global__ void k_apply(const long long *__restrict__ outN, const int *__restrict__ lines, int nlines, long long *__restrict__ part) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= nlines) return;
+  const int64_t phys = lines ? lines[l] : l;
+  part[(int64_t)l * 16 + 8] = outN[phys * 2];
+  part[(int64_t)l * 16 + 12] = outN[phys * 2 + 1];
+}
+
+static int grid_cap(int64_t work, int block) { return (int)std::max<int64_t>(1, std::min<int64_t>((work + block - 1) / block, 148 * 32)); }
+
+}  // namespace naell
+
+// Build (once) the blocked-ELL lists of both sides.  Returns true when resident; false = use the flag-plane kernels
+// (no missing value, rate above BSG_NA_LIST_MAX_RATE, not enough memory, BSG_NA_LISTS=0).
+bool na_ell_ready(bsg_bed *h) {
+  using namespace naell;
+  if (h->na_ell != 0) return h->na_ell == 1;
+  h->na_ell = -1;
+  if (!h->has_na) return false;
+  const char *ev = getenv("BSG_NA_LISTS");
+  if (ev && ev[0] == '0') return false;
+  double max_rate = 0.04;  // above ~4 % the lists (2 x 2 bytes x 1.3 per missing value) approach the size of the matrix itself
+  if (const char *er = getenv("BSG_NA_LIST_MAX_RATE")) max_rate = atof(er);
+  cudaStream_t s = h->stream;
+  const int n = h->n, m = h->m;
+  // missing values in total (exact counts cached at staging)
+  long long nnz = 0;
+  {
+    std::vector<int32_t> c4((size_t)m * 4);
+    if (cudaMemcpyAsync(c4.data(), h->cntA, c4.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    for (int j = 0; j < m; j++) nnz += c4[4 * (size_t)j + 3];
+  }
+  if (nnz <= 0 || (double)nnz > max_rate * (double)n * (double)m) return false;
+  bool ok = true;
+  for (int side = 0; side < 2 && ok; side++) {
+    const int nlines = side == 0 ? n : m, qlen = side == 0 ? m : n;
+    const int nchunks = (qlen + CH - 1) / CH, ngroups = (nlines + 31) / 32;
+    const int64_t nblocks = (int64_t)ngroups * nchunks;
+    uint16_t *cnt = nullptr, *ent = nullptr;
+    long long *blk = nullptr, *off = nullptr, *outN = nullptr;
+    void *tmp = nullptr;
+    do {
+      ok = false;
+      size_t fr = 0, tot = 0;
+      cudaMemGetInfo(&fr, &tot);
+      const size_t meta = (size_t)nblocks * 64 + (size_t)(nblocks + 1) * 16 + (size_t)ngroups * 32 * 16;
+      if (meta + (size_t)(2.8 * (double)nnz) + ((size_t)2 << 30) > fr) break;  // expected entries incl. padding
+      if (cudaMalloc((void **)&cnt, (size_t)nblocks * 32 * sizeof(uint16_t)) != cudaSuccess ||
+          cudaMalloc((void **)&blk, (size_t)(nblocks + 1) * sizeof(long long)) != cudaSuccess ||
+          cudaMalloc((void **)&off, (size_t)(nblocks + 1) * sizeof(long long)) != cudaSuccess ||
+          cudaMalloc((void **)&outN, (size_t)ngroups * 32 * 2 * sizeof(long long)) != cudaSuccess)
+        break;
+      if (cudaMemsetAsync(cnt, 0, (size_t)nblocks * 32 * sizeof(uint16_t), s) != cudaSuccess) break;
+      if (side == 1) {
+        k_cnt_lines<<<grid_cap((int64_t)m * nchunks * 32, 256), 256, 0, s>>>(h->A, h->strideA, n, m, nchunks, cnt);
+      } else {
+        dim3 grid((unsigned)nchunks, (unsigned)((h->strideA / 4 + 31) / 32));
+        k_cnt_samples<<<grid, 256, 0, s>>>(h->A, h->strideA, n, m, nchunks, cnt);
+      }
+      k_block_max<<<grid_cap(nblocks + 1, 256), 256, 0, s>>>(cnt, nblocks, blk);
+      size_t tb = 0;
+      cub::DeviceScan::ExclusiveSum(nullptr, tb, blk, off, (int)(nblocks + 1), s);
+      if (cudaMalloc(&tmp, tb ? tb : 16) != cudaSuccess) break;
+      cub::DeviceScan::ExclusiveSum(tmp, tb, blk, off, (int)(nblocks + 1), s);
+      long long rows = 0;
+      if (cudaMemcpyAsync(&rows, off + nblocks, sizeof rows, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+          cudaStreamSynchronize(s) != cudaSuccess)
+        break;
+      cudaMemGetInfo(&fr, &tot);
+      if ((size_t)rows * 64 + ((size_t)2 << 30) > fr) break;
+      if (cudaMalloc((void **)&ent, std::max<size_t>((size_t)rows * 32 * sizeof(uint16_t), 64)) != cudaSuccess) break;
+      if (cudaMemsetAsync(ent, 0, std::max<size_t>((size_t)rows * 32 * sizeof(uint16_t), 64), s) != cudaSuccess) break;
+      if (side == 1) {
+        k_fill_lines<<<grid_cap((int64_t)m * nchunks * 32, 256), 256, 0, s>>>(h->A, h->strideA, n, m, nchunks, off, ent);
+      } else {
+        dim3 grid((unsigned)nchunks, (unsigned)((h->strideA / 4 + 31) / 32));
+        k_fill_samples<<<grid, 256, 0, s>>>(h->A, h->strideA, n, m, nchunks, off, ent);
+      }
+      count_launch(4);
+      if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) break;
+      ok = true;
+    } while (0);
+    cudaGetLastError();
+    cudaFree(tmp);
+    cudaFree(blk);
+    if (!ok) {
+      cudaFree(cnt);
+      cudaFree(off);
+      cudaFree(ent);
+      cudaFree(outN);
+      break;
+    }
+    h->ellCnt[side] = cnt;
+    h->ellOff[side] = off;
+    h->ellEnt[side] = ent;
+    h->ellOut[side] = outN;
+    h->ellChunks[side] = nchunks;
+    h->ellGroups[side] = ngroups;
+  }
+  if (!ok) {
+    for (int side = 0; side < 2; side++) {
+      cudaFree(h->ellCnt[side]);
+      cudaFree(h->ellOff[side]);
+      cudaFree(h->ellEnt[side]);
+      cudaFree(h->ellOut[side]);
+      h->ellCnt[side] = nullptr;
+      h->ellOff[side] = nullptr;
+      h->ellEnt[side] = nullptr;
+      h->ellOut[side] = nullptr;
+    }
+    return false;
+  }
+  h->na_nnz = nnz;
+  h->na_ell = 1;
+  return true;
+}
+
+// NA-plane sums of `nlines` output lines (side 0: lines = samples, Q over the SNPs; side 1: lines = SNPs, Q over the
+// samples; lines[l] = physical line of output l, null = identity) written into part[l][8 ..]
+int na_ell_correction(bsg_bed *h, int side, const int *lines, int nlines, const long long *Q, long long *part, cudaStream_t s) {
+  using namespace naell;
+  if (nlines <= 0) return BSG_OK;
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
+  const int ngroups = h->ellGroups[side];
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(2 * nsm, ((int64_t)ngroups + CORR_WARPS - 1) / CORR_WARPS));  // one wave
+  k_corr<<<grid, CORR_WARPS * 32, 0, s>>>(h->ellCnt[side], h->ellOff[side], h->ellEnt[side], h->ellChunks[side], ngroups, Q,
+                                          side == 0 ? h->m : h->n, h->ellOut[side]);
+  k_apply<<<(nlines + 255) / 256, 256, 0, s>>>(h->ellOut[side], lines, nlines, part);
+  count_launch(2);
+  BSG_CUDA(cudaGetLastError());
+  return BSG_OK;
+}
+
+}  // namespace bsg

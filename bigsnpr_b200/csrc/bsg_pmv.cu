@@ -1298,121 +1298,6 @@ __global__ void k_finish_prod_pair(const long long *__restrict__ part, int nline
 }
 }  // namespace pmvt
 
-// =============================================================================================
-// Sparse missing-value correction.  The plane sum N_l = sum_{t : code(l, t) == 3} v[t] costs a second set of IMMAs
-// over the whole matrix although only a few per cent of the entries contribute.  With the positions of the missing
-// values kept as two CSR lists (per SNP line: sample indices; per sample: SNP indices; 8 bytes per missing value in
-// total), the matvec kernels run in their no-missing mode and N_l is a gather over the line's list from the
-// quantised vector -- the same integers the plane would have summed, slice by slice, so results are unchanged.
-// The gather is bound by L2 sector traffic (one 32-byte sector per missing value): ~0.9 ms per 1 % missing at cfg2,
-// against ~0.65 ms for the flag plane, so the lists are built (on first use) only when the missing rate is at most
-// BSG_NA_LIST_MAX_RATE (default 0.5 %).
-// =============================================================================================
-namespace nalist {
-__global__ void k_col_na_counts(const int32_t *__restrict__ cnt4, int m, long long *__restrict__ out) {
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j <= m; j += gridDim.x * blockDim.x) out[j] = j < m ? cnt4[4 * (int64_t)j + 3] : 0;
-}
-// one thread per (line, 32-bit word): missing codes have both bits set
-__global__ void k_row_na_counts(const uint8_t *__restrict__ A, int64_t stride, int n, int m, long long *__restrict__ rowcnt) {
-  const int wpl = (int)(stride / 4);
-  const int64_t total = (int64_t)m * wpl;
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int j = (int)(t / wpl), w = (int)(t - (int64_t)j * wpl);
-    uint32_t x = reinterpret_cast<const uint32_t *>(A + (int64_t)j * stride)[w];
-    uint32_t f = x & (x >> 1) & 0x55555555u;
-    while (f) {
-      const int b = __ffs(f) - 1;
-      f &= f - 1;
-      const int i = 16 * w + (b >> 1);
-      if (i < n) atomicAdd(reinterpret_cast<unsigned long long *>(rowcnt + i), 1ull);
-    }
-  }
-}
-__global__ void k_fill_row(const uint8_t *__restrict__ A, int64_t stride, int n, int m, const long long *__restrict__ off,
-                           unsigned long long *__restrict__ cursor, int32_t *__restrict__ idx) {
-  const int wpl = (int)(stride / 4);
-  const int64_t total = (int64_t)m * wpl;
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int j = (int)(t / wpl), w = (int)(t - (int64_t)j * wpl);
-    uint32_t x = reinterpret_cast<const uint32_t *>(A + (int64_t)j * stride)[w];
-    uint32_t f = x & (x >> 1) & 0x55555555u;
-    while (f) {
-      const int b = __ffs(f) - 1;
-      f &= f - 1;
-      const int i = 16 * w + (b >> 1);
-      if (i < n) idx[off[i] + (long long)atomicAdd(cursor + i, 1ull)] = j;
-    }
-  }
-}
-// warp per SNP line, sample indices in increasing order
-__global__ void k_fill_col(const uint8_t *__restrict__ A, int64_t stride, int n, int m, const long long *__restrict__ off,
-                           int32_t *__restrict__ idx) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int nw = (gridDim.x * blockDim.x) >> 5, wpl = (int)(stride / 4);
-  for (int j = warp; j < m; j += nw) {
-    long long pos = off[j];
-    if (off[j + 1] == pos) continue;
-    const uint32_t *line = reinterpret_cast<const uint32_t *>(A + (int64_t)j * stride);
-    for (int w0 = 0; w0 < wpl; w0 += 32) {
-      const int w = w0 + lane;
-      uint32_t x = w < wpl ? line[w] : 0u;
-      uint32_t f = x & (x >> 1) & 0x55555555u;
-      if (w < wpl && 16 * w + 15 >= n) {  // pads are code 0, never missing -- mask anyway
-        for (int c = 0; c < 16; c++)
-          if (16 * w + c >= n) f &= ~(1u << (2 * c));
-      }
-      const int c = __popc(f);
-      int pre = c;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int v = __shfl_up_sync(0xffffffffu, pre, o);
-        if (lane >= o) pre += v;
-      }
-      const int tot = __shfl_sync(0xffffffffu, pre, 31);
-      long long p = pos + pre - c;
-      while (f) {
-        const int b = __ffs(f) - 1;
-        f &= f - 1;
-        idx[p++] = 16 * w + (b >> 1);
-      }
-      pos += tot;
-    }
-  }
-}
-// warp per output line: part[lpos][8 + s] = sum over the line's missing entries of digit s of Q[entry]
-__global__ void k_na_corr(const long long *__restrict__ off, const int32_t *__restrict__ idx, const int *__restrict__ lines,
-                          int nlines, const long long *__restrict__ Q, long long *__restrict__ part) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int nw = (gridDim.x * blockDim.x) >> 5;
-  for (int l = warp; l < nlines; l += nw) {
-    const int phys = lines ? lines[l] : l;
-    const long long b = off[phys], e = off[phys + 1];
-    if (b == e) continue;  // part is zeroed
-    int acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (long long t = b + lane; t < e; t += 32) {
-      long long q = Q[idx[t]];
-#pragma unroll
-      for (int sl = 0; sl < 8; sl++) {
-        const int d = (int)(signed char)(q & 0xFF);
-        q = (q - d) >> 8;
-        acc[sl] += d;
-      }
-    }
-#pragma unroll
-    for (int sl = 0; sl < 8; sl++) {
-#pragma unroll
-      for (int o = 16; o; o >>= 1) acc[sl] += __shfl_xor_sync(0xffffffffu, acc[sl], o);
-    }
-    if (lane < 8) {
-      int v = acc[0];
-#pragma unroll
-      for (int sl = 1; sl < 8; sl++)
-        if (lane == sl) v = acc[sl];
-      part[(int64_t)l * 16 + 8 + lane] = (long long)v;
-    }
-  }
-}
-}  // namespace nalist
 
 static int launch_cap_pub(int64_t work) { return pmv::launch_cap_pub_impl(work); }
 
@@ -1539,10 +1424,6 @@ void bsg_view_destroy(bsg_view *v) {
   delete v;
 }
 
-static bool na_lists_ready(bsg_bed *h);
-static int na_correction(bsg_bed *h, bool by_column, const int *lines, int nlines, const long long *Q, long long *part,
-                         cudaStream_t s);
-
 // t(X~) x : lines = SNP columns of copy A, contraction over samples
 int bsg_view_cprodvec_dev(bsg_view *v, const double *x_dev, double *out_dev, void *stream) {
   if (!v || !x_dev || !out_dev) return fail(BSG_ERR_ARG, "null argument");
@@ -1561,7 +1442,7 @@ int bsg_view_cprodvec_dev(bsg_view *v, const double *x_dev, double *out_dev, voi
   long long *Q = v->s_q0.as<long long>();
   const int hb = hb_bits(v->row_maxmult);
   // few missing values: the kernel runs in its no-missing mode and the N plane comes from the per-SNP lists
-  const bool lists = h->has_na && na_lists_ready(h);
+  const bool lists = h->has_na && na_ell_ready(h);
   if (v->row_identity) {
     // direct path: memset + 2 kernels
     BSG_CUDA(cudaMemsetAsync(sc, 0, sizeof(Scal), s));
@@ -1583,88 +1464,9 @@ int bsg_view_cprodvec_dev(bsg_view *v, const double *x_dev, double *out_dev, voi
   Args a;
   BSG_TRY(run_pmv(v, h->A, h->strideA, n, v->d_col, v->nc, v->s_dig1.as<uint8_t>(), nullptr, h->naA,
                   lists ? 0 : h->has_na, &a, s));
-  if (lists) BSG_TRY(na_correction(h, true, v->d_col, v->nc, Q, a.part, s));
+  if (lists) BSG_TRY(na_ell_correction(h, 1, v->d_col, v->nc, Q, a.part, s));
   k_finish_cprod<<<(v->nc + 255) / 256, 256, 0, s>>>(a.part, a.ksplit, a.nlines_pad, v->nc, sc, v->d_center, v->d_scale,
                                                       h->has_na, out_dev);
-  count_launch();
-  BSG_CUDA(cudaGetLastError());
-  return BSG_OK;
-}
-
-// Build (once) the two CSR lists of missing-value positions from the SNP-major copy.  Returns true when resident.
-static bool na_lists_ready(bsg_bed *h) {
-  using namespace nalist;
-  if (h->na_lists != 0) return h->na_lists == 1;
-  h->na_lists = -1;
-  if (!h->has_na) return false;
-  const char *ev = getenv("BSG_NA_LISTS");
-  if (ev && ev[0] == '0') return false;
-  double max_rate = 0.005;  // measured break-even at cfg2: gather cost ~0.9 ms per 1 % missing vs ~0.65 ms for the plane
-  if (const char *er = getenv("BSG_NA_LIST_MAX_RATE")) max_rate = atof(er);
-  cudaStream_t s = h->stream;
-  const int n = h->n, m = h->m;
-  long long *colOff = nullptr, *rowOff = nullptr, *tmp = nullptr;
-  int32_t *colIdx = nullptr, *rowIdx = nullptr;
-  void *scan_tmp = nullptr;
-  unsigned long long *cursor = nullptr;
-  bool ok = false;
-  do {
-    const size_t big = (size_t)std::max(n, m) + 1;
-    if (cudaMalloc(&colOff, ((size_t)m + 1) * 8) != cudaSuccess || cudaMalloc(&rowOff, ((size_t)n + 1) * 8) != cudaSuccess ||
-        cudaMalloc(&tmp, big * 8) != cudaSuccess)
-      break;
-    size_t tb = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tb, tmp, colOff, (int)big, s);
-    if (cudaMalloc(&scan_tmp, tb ? tb : 16) != cudaSuccess) break;
-    k_col_na_counts<<<launch_cap_pub(m + 1), 256, 0, s>>>(h->cntA, m, tmp);
-    cub::DeviceScan::ExclusiveSum(scan_tmp, tb, tmp, colOff, m + 1, s);
-    long long nnz = 0;
-    if (cudaMemcpyAsync(&nnz, colOff + m, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) break;
-    if (nnz <= 0 || (double)nnz > max_rate * (double)n * (double)m) break;  // the plane kernels are the better tool
-    size_t fr = 0, tot = 0;
-    cudaMemGetInfo(&fr, &tot);
-    if ((size_t)nnz * 8 + ((size_t)2 << 30) > fr) break;
-    if (cudaMalloc(&colIdx, (size_t)nnz * 4) != cudaSuccess || cudaMalloc(&rowIdx, (size_t)nnz * 4) != cudaSuccess ||
-        cudaMalloc(&cursor, ((size_t)n + 1) * 8) != cudaSuccess)
-      break;
-    if (cudaMemsetAsync(tmp, 0, ((size_t)n + 1) * 8, s) != cudaSuccess) break;
-    const int64_t words = (int64_t)m * (h->strideA / 4);
-    k_row_na_counts<<<launch_cap_pub(words), 256, 0, s>>>(h->A, h->strideA, n, m, tmp);
-    cub::DeviceScan::ExclusiveSum(scan_tmp, tb, tmp, rowOff, n + 1, s);
-    if (cudaMemsetAsync(cursor, 0, ((size_t)n + 1) * 8, s) != cudaSuccess) break;
-    k_fill_row<<<launch_cap_pub(words), 256, 0, s>>>(h->A, h->strideA, n, m, rowOff, cursor, rowIdx);
-    k_fill_col<<<launch_cap_pub((int64_t)m * 32), 256, 0, s>>>(h->A, h->strideA, n, m, colOff, colIdx);
-    count_launch(5);
-    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) break;
-    h->na_nnz = nnz;
-    ok = true;
-  } while (0);
-  cudaGetLastError();
-  cudaFree(tmp);
-  cudaFree(scan_tmp);
-  cudaFree(cursor);
-  if (!ok) {
-    cudaFree(colOff);
-    cudaFree(rowOff);
-    cudaFree(colIdx);
-    cudaFree(rowIdx);
-    return false;
-  }
-  h->naColOff = (int64_t *)colOff;
-  h->naRowOff = (int64_t *)rowOff;
-  h->naColIdx = colIdx;
-  h->naRowIdx = rowIdx;
-  h->na_lists = 1;
-  return true;
-}
-
-// N-plane slices of `nlines` output lines from the lists (Q = quantised vector over the contraction index)
-static int na_correction(bsg_bed *h, bool by_column, const int *lines, int nlines, const long long *Q, long long *part,
-                         cudaStream_t s) {
-  if (nlines <= 0) return BSG_OK;
-  nalist::k_na_corr<<<launch_cap_pub((int64_t)nlines * 32), 256, 0, s>>>(
-      reinterpret_cast<const long long *>(by_column ? h->naColOff : h->naRowOff), by_column ? h->naColIdx : h->naRowIdx, lines,
-      nlines, Q, part);
   count_launch();
   BSG_CUDA(cudaGetLastError());
   return BSG_OK;
@@ -1708,11 +1510,18 @@ static int run_pmvT(bsg_view *v, const uint8_t *dig_raw, int plane, const uint8_
     const int slots = 2 * nsm;
     const int lo = std::max(1, (nc + MAX_LINES_PER_ITEM - 1) / MAX_LINES_PER_ITEM);  // int32 accumulator head-room
     const int hi = std::max(lo, std::min(std::max(1, nsteps / 32), std::max(lo, (4 * waves * slots) / std::max(nblocks, 1))));
+    static int force_ks = -1;
+    if (force_ks < 0) {
+      const char *ev = getenv("BSG_PMVT_KS");
+      force_ks = ev ? std::max(0, atoi(ev)) : 0;
+    }
+    if (force_ks > 0) return std::max(lo, force_ks);
     int best = lo;
     double best_score = -1;
     for (int ks = lo; ks <= hi; ks++) {
       const double ctas = (double)nblocks * ks, nwav = ceil(ctas / slots);
       double score = ctas / (nwav * slots);             // occupancy of the waves
+      score *= 1.0 - 0.003 * ks;                        // every split adds a pipeline ramp and n x 8 integer atomics
       if (nwav < waves) score *= 0.9 + 0.1 * nwav / waves;  // very few waves: the per-CTA ramp-up shows
       if (score > best_score + 1e-9) {
         best_score = score;
@@ -1800,7 +1609,7 @@ static int prodvec_T(bsg_view *v, const double *x_dev, double *out_dev, cudaStre
   Scal *sc = v->s_scal.as<Scal>();
   const int n = h->n, nc = v->nc;
   const int mode = v->has_scaling ? 1 : 0;
-  const bool lists = h->has_na && na_lists_ready(h);  // few missing values: per-sample lists instead of the flag plane
+  const bool lists = h->has_na && na_ell_ready(h);  // few missing values: per-sample lists instead of the flag plane
   const bool two = v->has_scaling && h->has_na && !lists;
   long long *qna = nullptr;
   if (lists) {  // the missing-value vector ((c - 3) z with scaling, else y) by physical SNP
@@ -1816,7 +1625,7 @@ static int prodvec_T(bsg_view *v, const double *x_dev, double *out_dev, cudaStre
   long long *part = nullptr;
   BSG_TRY(run_pmvT(v, v->s_dig1.as<uint8_t>(), (h->has_na && !lists) ? 1 : 0,
                    two ? v->s_dig2.as<uint8_t>() : v->s_dig1.as<uint8_t>(), &part, s));
-  if (lists) BSG_TRY(na_correction(h, false, nullptr, n, qna, part, s));
+  if (lists) BSG_TRY(na_ell_correction(h, 0, nullptr, n, qna, part, s));
   double *full = out_dev;
   if (!v->row_identity) {
     BSG_TRY(v->s_full.ensure((size_t)n * sizeof(double)));
