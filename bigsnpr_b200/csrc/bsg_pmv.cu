@@ -1521,8 +1521,11 @@ static int run_pmvT(bsg_view *v, const uint8_t *dig_raw, int plane, const uint8_
     for (int ks = lo; ks <= hi; ks++) {
       const double ctas = (double)nblocks * ks, nwav = ceil(ctas / slots);
       double score = ctas / (nwav * slots);             // occupancy of the waves
-      score *= 1.0 - 0.003 * ks;                        // every split adds a pipeline ramp and n x 8 integer atomics
-      if (nwav < waves) score *= 0.9 + 0.1 * nwav / waves;  // very few waves: the per-CTA ramp-up shows
+      // every split adds a pipeline ramp and n x 8 integer atomics: worth ~1000 lines of streaming (sweeps on the
+      // configs[4] 1/8 shard and on configs[1], profiles/r02_results.md)
+      const double lines = (double)nc / ks;
+      score *= lines / (lines + 1000.0);
+      if (nwav < waves) score *= 0.9 + 0.1 * nwav / waves;  // very few waves: tail imbalance shows
       if (score > best_score + 1e-9) {
         best_score = score;
         best = ks;
