@@ -9,9 +9,10 @@
 // Here the positions are stored so that the gather runs out of SHARED memory with coalesced index loads:
 //   * the contraction index is cut into chunks of 4096; the quantised vector of one chunk (4096 x int64 = 32 KB) sits in
 //     shared memory while every line group consumes its entries of that chunk;
-//   * lines are grouped by 32; a block (group g, chunk c) stores its entries ELL style -- entry t of the 32 lines contiguous,
-//     16-bit chunk-local indices, padded to the longest line of the block -- so a warp reads 64 contiguous bytes per step and
-//     each lane adds shared[idx] to its own line's exact 64-bit sum (split in 32-bit halves: no overflow, order free);
+//   * lines are grouped by 32; a block (group g, chunk c) stores its entries ELL style in rows of 8 entries per line -- row r
+//     holds entries 8r..8r+7 of the 32 lines, lane after lane, 16-bit chunk-local indices, padded to the longest line of the
+//     block -- so one warp load is 512 contiguous bytes (a uint4 = 8 indices per lane), all rows of a block are in flight
+//     together, and each lane adds shared[idx] to its own line's exact 64-bit sum (32-bit halves: no overflow, order free);
 //   * a warp keeps the sums of its groups in registers across all chunks: one plain store per line at the end, no atomics.
 // 2 bytes per missing value and side (+ padding ~35 % at 1 %), built once per handle from the SNP-major copy.  The matvec
 // kernels then always run in their no-missing mode.  Results equal the flag-plane path up to fp64 rounding of the last
@@ -62,7 +63,7 @@ __global__ void k_fill_lines(const uint8_t *__restrict__ A, int64_t stride, int 
   for (int64_t it = warp; it < (int64_t)m * nchunks; it += nw) {
     const int j = (int)(it / nchunks), c = (int)(it - (int64_t)j * nchunks);
     const uint32_t *line = reinterpret_cast<const uint32_t *>(A + (int64_t)j * stride);
-    uint16_t *dst = ent + off[(int64_t)(j >> 5) * nchunks + c] * 32 + (j & 31);
+    uint16_t *dst = ent + (off[(int64_t)(j >> 5) * nchunks + c] * 32 + (j & 31)) * 8;  // row r of this lane at + r * 256
     int base = 0;
     for (int r = 0; r < 8; r++) {
       const int w = c * (CH / 16) + r * 32 + lane;
@@ -79,7 +80,7 @@ __global__ void k_fill_lines(const uint8_t *__restrict__ A, int64_t stride, int 
       while (f) {
         const int b = __ffs(f) - 1;
         f &= f - 1;
-        dst[(int64_t)t * 32] = (uint16_t)((r * 32 + lane) * 16 + (b >> 1));
+        dst[(int64_t)(t >> 3) * 256 + (t & 7)] = (uint16_t)((r * 32 + lane) * 16 + (b >> 1));
         t++;
       }
       base += tot;
@@ -130,20 +131,20 @@ __global__ void __launch_bounds__(256) k_fill_samples(const uint8_t *__restrict_
         const int64_t i = (int64_t)wb * 512 + sl;
         if (i < n) {
           const unsigned int t = atomicAdd(&cur[sl], 1u);  // any order: the sums are integers
-          ent[(off[(i >> 5) * nchunks + c] + t) * 32 + (i & 31)] = (uint16_t)(j - c * CH);
+          ent[((off[(i >> 5) * nchunks + c] + (t >> 3)) * 32 + (i & 31)) * 8 + (t & 7)] = (uint16_t)(j - c * CH);
         }
       }
     }
   }
 }
 
-// longest line of every block (32 lines x one chunk)
+// rows of 8 entries needed by the longest line of every block (32 lines x one chunk)
 __global__ void k_block_max(const uint16_t *__restrict__ cnt, int64_t nblocks, long long *__restrict__ blk) {
   for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b <= nblocks; b += (int64_t)gridDim.x * blockDim.x) {
     int mx = 0;
     if (b < nblocks)
       for (int r = 0; r < 32; r++) mx = max(mx, (int)cnt[b * 32 + r]);
-    blk[b] = mx;
+    blk[b] = (mx + 7) >> 3;
   }
 }
 
@@ -174,16 +175,23 @@ __global__ void __launch_bounds__(CORR_WARPS * 32) k_corr(const uint16_t *__rest
         if (g < ngroups) {  // warp-uniform
           const int64_t blk = g * nchunks + c;
           const int nme = cnt[blk * 32 + lane];
-          int mx = nme;
+          const int nrows = (int)(off[blk + 1] - off[blk]);  // rows of 8 entries per line (warp-uniform)
+          const uint4 *e = reinterpret_cast<const uint4 *>(ent) + off[blk] * 32 + lane;
+          for (int r0 = 0; r0 < nrows; r0 += 4) {  // up to 4 rows = 2 KB per warp in flight
+            uint4 v[4];
 #pragma unroll
-          for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-          const uint16_t *e = ent + off[blk] * 32 + lane;
-          for (int t = 0; t < mx; t++) {
-            const uint16_t idx = e[(int64_t)t * 32];
-            if (t < nme) {
-              const long long q = sq[idx];
-              lo[k] += (long long)(unsigned int)(q & 0xFFFFFFFFll);
-              hi[k] += q >> 32;
+            for (int u = 0; u < 4; u++) v[u] = (r0 + u < nrows) ? __ldg(e + (int64_t)(r0 + u) * 32) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+              for (int q8 = 0; q8 < 8; q8++) {
+                if ((r0 + u) * 8 + q8 < nme) {
+                  const long long q = sq[(w[q8 >> 1] >> (16 * (q8 & 1))) & 0xFFFFu];
+                  lo[k] += (long long)(unsigned int)(q & 0xFFFFFFFFll);
+                  hi[k] += q >> 32;
+                }
+              }
             }
           }
         }
@@ -275,9 +283,9 @@ bool na_ell_ready(bsg_bed *h) {
           cudaStreamSynchronize(s) != cudaSuccess)
         break;
       cudaMemGetInfo(&fr, &tot);
-      if ((size_t)rows * 64 + ((size_t)2 << 30) > fr) break;
-      if (cudaMalloc((void **)&ent, std::max<size_t>((size_t)rows * 32 * sizeof(uint16_t), 64)) != cudaSuccess) break;
-      if (cudaMemsetAsync(ent, 0, std::max<size_t>((size_t)rows * 32 * sizeof(uint16_t), 64), s) != cudaSuccess) break;
+      if ((size_t)rows * 512 + ((size_t)2 << 30) > fr) break;
+      if (cudaMalloc((void **)&ent, std::max<size_t>((size_t)rows * 512, 512)) != cudaSuccess) break;
+      if (cudaMemsetAsync(ent, 0, std::max<size_t>((size_t)rows * 512, 512), s) != cudaSuccess) break;
       if (side == 1) {
         k_fill_lines<<<grid_cap((int64_t)m * nchunks * 32, 256), 256, 0, s>>>(h->A, h->strideA, n, m, nchunks, off, ent);
       } else {
