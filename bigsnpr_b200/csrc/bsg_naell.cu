@@ -30,8 +30,8 @@ namespace bsg {
 namespace naell {
 
 constexpr int CH = 4096;      // contraction indices per chunk (16-bit local index, 32 KB of int64 in shared memory)
-constexpr int GW = 16;        // line groups per warp and pass
-constexpr int CORR_WARPS = 8;
+constexpr int GW = 4;         // line groups per warp and pass (register accumulators)
+constexpr int CORR_WARPS = 32;
 
 __device__ __forceinline__ uint32_t na_flags(uint32_t x) { return x & (x >> 1) & 0x55555555u; }
 
@@ -148,21 +148,27 @@ __global__ void k_block_max(const uint16_t *__restrict__ cnt, int64_t nblocks, l
   }
 }
 
-// N[line] = sum of Q over the line's missing entries, as (low 32-bit halves, high halves) exact 64-bit sums
-__global__ void __launch_bounds__(CORR_WARPS * 32) k_corr(const uint16_t *__restrict__ cnt, const long long *__restrict__ off,
-                                                          const uint16_t *__restrict__ ent, int nchunks, int ngroups,
-                                                          const long long *__restrict__ Q, int64_t qlen,
-                                                          long long *__restrict__ outN) {
+// N[line] = sum of Q over the line's missing entries, as (low 32-bit halves, high halves) exact 64-bit sums.
+// grid = (group CTAs, chunk splits): a CTA of 32 warps walks its range of chunks -- per chunk one cooperative load of the
+// 32 KB vector slice into shared memory, then every warp consumes the block(s) of its line group(s).  The per-chunk phase
+// costs a few microseconds of latency whatever the work, so the chunks are split over several CTAs when there are few
+// groups (the partial sums are then combined with 64-bit integer atomics: exact, order free).
+__global__ void __launch_bounds__(CORR_WARPS * 32, 1)
+    k_corr(const uint16_t *__restrict__ cnt, const long long *__restrict__ off, const uint16_t *__restrict__ ent, int nchunks,
+           int ngroups, int gw, const long long *__restrict__ Q, int64_t qlen, long long *__restrict__ outN) {
   __shared__ long long sq[CH];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t W = (int64_t)blockIdx.x * CORR_WARPS + warp, TW = (int64_t)gridDim.x * CORR_WARPS;
-  const int npass = (int)((ngroups + TW * GW - 1) / (TW * GW));
+  const int cper = (nchunks + gridDim.y - 1) / gridDim.y;
+  const int c0 = blockIdx.y * cper, c1 = min(nchunks, c0 + cper);
+  const bool atomic = gridDim.y > 1;
+  const int npass = (int)((ngroups + TW * gw - 1) / (TW * gw));
   for (int pass = 0; pass < npass; pass++) {
-    // groups are dealt round-robin over the warps of the grid: group (pass * GW + k) * TW + W
+    // groups are dealt round-robin over the warps of the grid: group (pass * gw + k) * TW + W
     long long lo[GW], hi[GW];
 #pragma unroll
     for (int k = 0; k < GW; k++) lo[k] = hi[k] = 0;
-    for (int c = 0; c < nchunks; c++) {
+    for (int c = c0; c < c1; c++) {
       __syncthreads();
       for (int t = threadIdx.x; t < CH; t += CORR_WARPS * 32) {
         const int64_t q = (int64_t)c * CH + t;
@@ -171,12 +177,13 @@ __global__ void __launch_bounds__(CORR_WARPS * 32) k_corr(const uint16_t *__rest
       __syncthreads();
 #pragma unroll
       for (int k = 0; k < GW; k++) {
-        const int64_t g = ((int64_t)pass * GW + k) * TW + W;
-        if (g < ngroups) {  // warp-uniform
+        const int64_t g = ((int64_t)pass * gw + k) * TW + W;
+        if (k < gw && g < ngroups) {  // warp-uniform
           const int64_t blk = g * nchunks + c;
           const int nme = cnt[blk * 32 + lane];
-          const int nrows = (int)(off[blk + 1] - off[blk]);  // rows of 8 entries per line (warp-uniform)
-          const uint4 *e = reinterpret_cast<const uint4 *>(ent) + off[blk] * 32 + lane;
+          const long long o0 = off[blk];
+          const int nrows = (int)(off[blk + 1] - o0);  // rows of 8 entries per line (warp-uniform)
+          const uint4 *e = reinterpret_cast<const uint4 *>(ent) + o0 * 32 + lane;
           for (int r0 = 0; r0 < nrows; r0 += 4) {  // up to 4 rows = 2 KB per warp in flight
             uint4 v[4];
 #pragma unroll
@@ -199,10 +206,16 @@ __global__ void __launch_bounds__(CORR_WARPS * 32) k_corr(const uint16_t *__rest
     }
 #pragma unroll
     for (int k = 0; k < GW; k++) {
-      const int64_t g = ((int64_t)pass * GW + k) * TW + W;
-      if (g < ngroups) {
-        outN[(g * 32 + lane) * 2] = lo[k];
-        outN[(g * 32 + lane) * 2 + 1] = hi[k];
+      const int64_t g = ((int64_t)pass * gw + k) * TW + W;
+      if (k < gw && g < ngroups) {
+        long long *dst = outN + (g * 32 + lane) * 2;
+        if (atomic) {
+          if (lo[k]) atomicAdd(reinterpret_cast<unsigned long long *>(dst), (unsigned long long)lo[k]);
+          if (hi[k]) atomicAdd(reinterpret_cast<unsigned long long *>(dst + 1), (unsigned long long)hi[k]);
+        } else {
+          dst[0] = lo[k];
+          dst[1] = hi[k];
+        }
       }
     }
   }
@@ -338,9 +351,17 @@ int na_ell_correction(bsg_bed *h, int side, const int *lines, int nlines, const 
   if (nlines <= 0) return BSG_OK;
   int nsm = 148;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
-  const int ngroups = h->ellGroups[side];
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(2 * nsm, ((int64_t)ngroups + CORR_WARPS - 1) / CORR_WARPS));  // one wave
-  k_corr<<<grid, CORR_WARPS * 32, 0, s>>>(h->ellCnt[side], h->ellOff[side], h->ellEnt[side], h->ellChunks[side], ngroups, Q,
+  const int ngroups = h->ellGroups[side], nchunks = h->ellChunks[side];
+  // one CTA of 32 warps per SM: few groups -> one group per warp and the chunks split over several CTAs (about two waves,
+  // at least ~8 chunks each); many groups -> up to GW groups per warp, one wave
+  const int64_t warp_slots = (int64_t)nsm * CORR_WARPS;
+  int gw = (int)std::min<int64_t>(GW, std::max<int64_t>(1, (ngroups + warp_slots - 1) / warp_slots));
+  int gctas = (int)std::min<int64_t>(nsm, ((int64_t)ngroups + (int64_t)CORR_WARPS * gw - 1) / ((int64_t)CORR_WARPS * gw));
+  gctas = std::max(gctas, 1);
+  int nsplit = std::max(1, std::min(std::max(1, nchunks / 8), (2 * nsm) / gctas));
+  if (nsplit > 1) BSG_CUDA(cudaMemsetAsync(h->ellOut[side], 0, (size_t)ngroups * 32 * 2 * sizeof(long long), s));
+  dim3 grid((unsigned)gctas, (unsigned)nsplit);
+  k_corr<<<grid, CORR_WARPS * 32, 0, s>>>(h->ellCnt[side], h->ellOff[side], h->ellEnt[side], nchunks, ngroups, gw, Q,
                                           side == 0 ? h->m : h->n, h->ellOut[side]);
   k_apply<<<(nlines + 255) / 256, 256, 0, s>>>(h->ellOut[side], lines, nlines, part);
   count_launch(2);
