@@ -153,6 +153,7 @@ __global__ void k_block_max(const uint16_t *__restrict__ cnt, int64_t nblocks, l
 // 32 KB vector slice into shared memory, then every warp consumes the block(s) of its line group(s).  The per-chunk phase
 // costs a few microseconds of latency whatever the work, so the chunks are split over several CTAs when there are few
 // groups (the partial sums are then combined with 64-bit integer atomics: exact, order free).
+template <int GWT>
 __global__ void __launch_bounds__(CORR_WARPS * 32, 1)
     k_corr(const uint16_t *__restrict__ cnt, const long long *__restrict__ off, const uint16_t *__restrict__ ent, int nchunks,
            int ngroups, int gw, const long long *__restrict__ Q, int64_t qlen, long long *__restrict__ outN) {
@@ -165,18 +166,53 @@ __global__ void __launch_bounds__(CORR_WARPS * 32, 1)
   const int npass = (int)((ngroups + TW * gw - 1) / (TW * gw));
   for (int pass = 0; pass < npass; pass++) {
     // groups are dealt round-robin over the warps of the grid: group (pass * gw + k) * TW + W
-    long long lo[GW], hi[GW];
+    long long lo[GWT], hi[GWT];
 #pragma unroll
-    for (int k = 0; k < GW; k++) lo[k] = hi[k] = 0;
+    for (int k = 0; k < GWT; k++) lo[k] = hi[k] = 0;
     for (int c = c0; c < c1; c++) {
+      // GWT == 1 (few groups: the per-chunk phase latency dominates): the block's counts, offsets and first 8 rows are
+      // requested BEFORE the vector slice is staged, so their latency chain overlaps the cooperative load and its barriers
+      uint4 pre[GWT == 1 ? 8 : 1];
+      int pre_nme = 0, pre_nrows = 0;
+      const uint4 *pre_e = nullptr;
+      if (GWT == 1) {
+        const int64_t g = (int64_t)pass * TW + W;
+        if (g < ngroups) {
+          const int64_t blk = g * nchunks + c;
+          pre_nme = cnt[blk * 32 + lane];
+          const long long o0 = off[blk];
+          pre_nrows = (int)(off[blk + 1] - o0);
+          pre_e = reinterpret_cast<const uint4 *>(ent) + o0 * 32 + lane;
+#pragma unroll
+          for (int u = 0; u < 8; u++) pre[u] = (u < pre_nrows) ? __ldg(pre_e + (int64_t)u * 32) : make_uint4(0, 0, 0, 0);
+        }
+      }
       __syncthreads();
       for (int t = threadIdx.x; t < CH; t += CORR_WARPS * 32) {
         const int64_t q = (int64_t)c * CH + t;
         sq[t] = q < qlen ? Q[q] : 0;
       }
       __syncthreads();
+      auto consume = [&](const uint4 &v, int row, int nme, long long &l, long long &hh) {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int k = 0; k < GW; k++) {
+        for (int q8 = 0; q8 < 8; q8++) {
+          if (row * 8 + q8 < nme) {
+            const long long q = sq[(w[q8 >> 1] >> (16 * (q8 & 1))) & 0xFFFFu];
+            l += (long long)(unsigned int)(q & 0xFFFFFFFFll);
+            hh += q >> 32;
+          }
+        }
+      };
+      if (GWT == 1) {
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+          if (u < pre_nrows) consume(pre[u], u, pre_nme, lo[0], hi[0]);
+        for (int r = 8; r < pre_nrows; r++) consume(__ldg(pre_e + (int64_t)r * 32), r, pre_nme, lo[0], hi[0]);
+        continue;
+      }
+#pragma unroll
+      for (int k = 0; k < GWT; k++) {
         const int64_t g = ((int64_t)pass * gw + k) * TW + W;
         if (k < gw && g < ngroups) {  // warp-uniform
           const int64_t blk = g * nchunks + c;
@@ -205,7 +241,7 @@ __global__ void __launch_bounds__(CORR_WARPS * 32, 1)
       }
     }
 #pragma unroll
-    for (int k = 0; k < GW; k++) {
+    for (int k = 0; k < GWT; k++) {
       const int64_t g = ((int64_t)pass * gw + k) * TW + W;
       if (k < gw && g < ngroups) {
         long long *dst = outN + (g * 32 + lane) * 2;
@@ -361,8 +397,12 @@ int na_ell_correction(bsg_bed *h, int side, const int *lines, int nlines, const 
   int nsplit = std::max(1, std::min(std::max(1, nchunks / 8), (2 * nsm) / gctas));
   if (nsplit > 1) BSG_CUDA(cudaMemsetAsync(h->ellOut[side], 0, (size_t)ngroups * 32 * 2 * sizeof(long long), s));
   dim3 grid((unsigned)gctas, (unsigned)nsplit);
-  k_corr<<<grid, CORR_WARPS * 32, 0, s>>>(h->ellCnt[side], h->ellOff[side], h->ellEnt[side], nchunks, ngroups, gw, Q,
-                                          side == 0 ? h->m : h->n, h->ellOut[side]);
+  if (gw == 1)
+    k_corr<1><<<grid, CORR_WARPS * 32, 0, s>>>(h->ellCnt[side], h->ellOff[side], h->ellEnt[side], nchunks, ngroups, gw, Q,
+                                               side == 0 ? h->m : h->n, h->ellOut[side]);
+  else
+    k_corr<GW><<<grid, CORR_WARPS * 32, 0, s>>>(h->ellCnt[side], h->ellOff[side], h->ellEnt[side], nchunks, ngroups, gw, Q,
+                                                side == 0 ? h->m : h->n, h->ellOut[side]);
   k_apply<<<(nlines + 255) / 256, 256, 0, s>>>(h->ellOut[side], lines, nlines, part);
   count_launch(2);
   BSG_CUDA(cudaGetLastError());
