@@ -369,7 +369,7 @@ def test_randomsvd_and_grm(B, gbed, gbed_na, oracle, obed, obed_na):
 
 def test_clumping_identical_to_oracle(B, gbed, gbed_na, oracle, obed, obed_na, rng):
     # tests/testthat/test-2-bed-clumping-SVD.R:28-49,62-70,83: kept indices identical; window rescaling invariance;
-    # `exclude`; ncores accepted.  (clumping.rds pins snp_clumping with a GWAS-derived S: not reproducible here.)
+    # `exclude`; ncores accepted.  (The clumping.rds golden: test_clumping_against_reference_rds_golden below.)
     for g, o in ((gbed, obed), (gbed_na, obed_na)):
         want = oracle.bed_clumping(o)
         got = B.bed_clumping(g, ncores=2)
@@ -386,6 +386,25 @@ def test_clumping_identical_to_oracle(B, gbed, gbed_na, oracle, obed, obed_na, r
     assert B.bed_clumping(gbed, exclude=np.arange(1, 101)).min() > 100
     with pytest.raises(ValueError, match="can't be `NULL`"):
         B.bed_clumping(gbed, ind_row=None)
+
+
+def test_clumping_against_reference_rds_golden(B, gbed, oracle, obed, golden_dir):
+    # tests/testthat/test-6-PRS.R:25-31: the reference's stored snp_clumping result (testdata/clumping.rds) with the priority
+    # order recovered from testdata/pval.rds (p-value = decreasing function of abs(gwas$score); only the order of S matters).
+    # Fixture: tests/golden/prs_clumping.npz, made from the two RDS files by tests/golden/make_rds_golden.py.  The bar is the
+    # reference's own (> 98 % of the kept variants are in the stored set); against the oracle the indices are identical.
+    import os
+
+    gold = np.load(os.path.join(golden_dir, "prs_clumping.npz"))
+    pval, keep2 = gold["pval"], gold["keep"]
+    chrom, pos = oracle.read_bim(obed.bedfile)
+    G = oracle.read_bed(obed, obed.rows_along(), obed.cols_along(), na_val=3).astype(np.uint8)
+    gf, of = B.Bed.from_fbm(G), oracle.OracleFBM(G)
+    keep = B.snp_clumping(gf, chrom, S=-pval, size=250, infos_pos=pos)
+    assert np.mean(np.isin(keep, keep2)) > 0.98
+    assert np.array_equal(keep, oracle.snp_clumping(of, chrom, S=-pval, size=250, infos_pos=pos))
+    assert np.array_equal(B.bed_clumping(gbed, S=-pval, size=250), keep)
+    gf.close()
 
 
 def test_prod_and_rowSumsSq_and_projection(B, gbed, gbed_na, oracle, obed, obed_na, rng):

@@ -232,6 +232,25 @@ def test_snp_clumping_fbm_twin(oracle, obed):
     assert np.nanmax(R2[near & off]) <= 0.1 + 1e-12
 
 
+def test_snp_clumping_against_reference_rds_golden(oracle, obed, golden_dir):
+    # tests/testthat/test-6-PRS.R:25-31: snp_clumping(G, S = abs(gwas$score), size = 250, infos.pos) against the kept
+    # indices stored in testdata/clumping.rds, `expect_gt(mean(ind.keep %in% ind.keep2), 0.98)`.  The priority vector is
+    # recovered from testdata/pval.rds (the same test pins predict(gwas, log10 = FALSE) to it, :19-22): the p-value is a
+    # decreasing function of |score| and clumping only uses the ORDER of S, so S = -pval ranks the variants like
+    # abs(gwas$score).  Both vectors were parsed from the reference's RDS files by tests/golden/make_rds_golden.py.
+    gold = np.load(os.path.join(golden_dir, "prs_clumping.npz"))
+    pval, keep2 = gold["pval"], gold["keep"]
+    assert pval.size == obed.ncol == 4542 and keep2.size == 4390 and np.unique(keep2).size == 4390
+    chrom, pos = oracle.read_bim(obed.bedfile)
+    G = oracle.read_bed(obed, obed.rows_along(), obed.cols_along(), na_val=3).astype(np.uint8)
+    keep = oracle.snp_clumping(oracle.OracleFBM(G), chrom, S=-pval, size=250, infos_pos=pos)
+    frac = np.mean(np.isin(keep, keep2))
+    assert frac > 0.98, frac                      # the reference's own bar
+    assert abs(keep.size - keep2.size) <= 0.02 * keep2.size
+    # bed twin on the same file (no missing values): identical indices (test-2-bed-clumping-SVD.R:47-48)
+    assert np.array_equal(oracle.bed_clumping(obed, S=-pval, size=250), keep)
+
+
 def test_projection_and_pcadapt_oracle_against_numpy(oracle, obed_na):
     # src/bed-fun.cpp:103-133 and src/multLinReg.cpp:8-60 restated in the oracle, pinned on independent NumPy / SciPy
     # formulations: X~ V and row sums of squares of the dense scaled matrix; t-score = slope / stderr of the simple
