@@ -13,8 +13,14 @@
 //     holds entries 8r..8r+7 of the 32 lines, lane after lane, 16-bit chunk-local indices, padded to the longest line of the
 //     block -- so one warp load is 512 contiguous bytes (a uint4 = 8 indices per lane), all rows of a block are in flight
 //     together, and each lane adds shared[idx] to its own line's exact 64-bit sum (32-bit halves: no overflow, order free);
-//   * a warp keeps the sums of its groups in registers across all chunks: one plain store per line at the end, no atomics.
-// 2 bytes per missing value and side (+ padding ~35 % at 1 %), built once per handle from the SNP-major copy.  The matvec
+//   * a warp keeps the sums of its groups in registers across all chunks: one plain store per line at the end, no atomics;
+//   * the ORDER of a line's entries is free (integer sums), so each block is re-ordered once at build time such that the 16
+//     lanes of a half-warp hit 16 different shared-memory banks in every slot: a greedy edge colouring of the bipartite
+//     multigraph (lane, bank = index mod 16) with slots as colours (k_recolor).  Random order costs 2.66 wavefronts per
+//     ideal one (ncu, profiles/r02_kcorr_ncu_before.txt); the colouring needs ~4 % more slots than the longest line and
+//     makes the gathers conflict free.  Unused slots point at 16 zero words behind the vector slice (one per bank), so
+//     the gather loop has no predicates and no per-line counts.
+// 2 bytes per missing value and side (+ padding ~40 % at 1 %), built once per handle from the SNP-major copy.  The matvec
 // kernels then always run in their no-missing mode.  Results equal the flag-plane path up to fp64 rounding of the last
 // combination (the sums themselves are exact integers).
 #include <stdint.h>
@@ -31,7 +37,12 @@ namespace naell {
 
 constexpr int CH = 4096;      // contraction indices per chunk (16-bit local index, 32 KB of int64 in shared memory)
 constexpr int GW = 4;         // line groups per warp and pass (register accumulators)
-constexpr int CORR_WARPS = 32;
+constexpr int CORR_WARPS = 16;  // two CTAs per SM
+constexpr int PAD0 = CH;      // unused slots: index CH + (lane & 15) -> 16 zero words, one per 64-bit bank
+constexpr int SLACK = 3;      // slots beyond the longest line of a block that the colouring may use
+constexpr int RC_MAX_ROWS = 32;  // blocks with more rows of 8 keep their arrival order (padding is still rewritten)
+constexpr int RC_WARPS = 4;
+constexpr int RC_WARP_SMEM = RC_MAX_ROWS * 8 * 32 * 3 + (32 + 32) * 4 * 8 + 2 * RC_MAX_ROWS * 8;  // see k_recolor
 
 __device__ __forceinline__ uint32_t na_flags(uint32_t x) { return x & (x >> 1) & 0x55555555u; }
 
@@ -80,7 +91,7 @@ __global__ void k_fill_lines(const uint8_t *__restrict__ A, int64_t stride, int 
       while (f) {
         const int b = __ffs(f) - 1;
         f &= f - 1;
-        dst[(int64_t)(t >> 3) * 256 + (t & 7)] = (uint16_t)((r * 32 + lane) * 16 + (b >> 1));
+        dst[(int64_t)(t >> 3) * 256 + (t & 7)] = (uint16_t)(((r * 32 + lane) * 16 + (b >> 1)) * 8);  // byte offset in the slice
         t++;
       }
       base += tot;
@@ -131,7 +142,7 @@ __global__ void __launch_bounds__(256) k_fill_samples(const uint8_t *__restrict_
         const int64_t i = (int64_t)wb * 512 + sl;
         if (i < n) {
           const unsigned int t = atomicAdd(&cur[sl], 1u);  // any order: the sums are integers
-          ent[((off[(i >> 5) * nchunks + c] + (t >> 3)) * 32 + (i & 31)) * 8 + (t & 7)] = (uint16_t)(j - c * CH);
+          ent[((off[(i >> 5) * nchunks + c] + (t >> 3)) * 32 + (i & 31)) * 8 + (t & 7)] = (uint16_t)((j - c * CH) * 8);
         }
       }
     }
@@ -144,71 +155,223 @@ __global__ void k_block_max(const uint16_t *__restrict__ cnt, int64_t nblocks, l
     int mx = 0;
     if (b < nblocks)
       for (int r = 0; r < 32; r++) mx = max(mx, (int)cnt[b * 32 + r]);
-    blk[b] = (mx + 7) >> 3;
+    blk[b] = mx ? (mx + SLACK + 7) >> 3 : 0;
+  }
+}
+
+__device__ __forceinline__ unsigned long long slot_mask(int S, int w4) {  // slots w4 * 64 .. w4 * 64 + 63 that exist (< S)
+  const int nb = S - w4 * 64;
+  return nb >= 64 ? ~0ull : (nb > 0 ? ((1ull << nb) - 1ull) : 0ull);
+}
+
+// Re-order the entries of every block (32 lines x one chunk), one warp per block: slot c of lane l gets an entry whose
+// bank (index mod 16: the 64-bit word's bank pair) differs from the banks the other 15 lanes of the half-warp use in slot c.
+// Greedy edge colouring: entries are taken line by line, k-th entry of lane 0, 1, .., 15 in turn (the two half-warps run
+// side by side), each takes the smallest slot free for its lane and its bank; if none is left below the block's slot
+// count, any slot free for the lane (a conflict, never an error).  Unused slots are rewritten to the zero words.
+__global__ void __launch_bounds__(RC_WARPS * 32)
+    k_recolor(const uint16_t *__restrict__ cnt, const long long *__restrict__ off, uint16_t *__restrict__ ent, int64_t nblocks,
+              int recolor) {
+  extern __shared__ __align__(16) unsigned char rc_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, half = lane >> 4, l16 = lane & 15;
+  // per warp: entries [RC_MAX_ROWS * 8][32] u16, slot of entry [RC_MAX_ROWS * 8][32] u8, masks lane_used[32][4],
+  // bank_used[2][16][4], free bank of every slot padf[2][RC_MAX_ROWS * 8] u8
+  constexpr int S_MAX = RC_MAX_ROWS * 8;
+  unsigned char *base = rc_smem + (size_t)warp * RC_WARP_SMEM;
+  uint16_t *e = reinterpret_cast<uint16_t *>(base);
+  uint8_t *col = base + S_MAX * 32 * 2;
+  unsigned long long *lane_used = reinterpret_cast<unsigned long long *>(base + S_MAX * 32 * 3);
+  unsigned long long *bank_used = lane_used + 32 * 4;
+  uint8_t *padf = reinterpret_cast<uint8_t *>(bank_used + 32 * 4);
+  for (int64_t b = (int64_t)blockIdx.x * RC_WARPS + warp; b < nblocks; b += (int64_t)gridDim.x * RC_WARPS) {
+    const long long o0 = off[b];
+    const int nrows = (int)(off[b + 1] - o0);
+    if (nrows == 0) continue;
+    const int S = nrows * 8, deg = cnt[b * 32 + lane];
+    uint4 *rows = reinterpret_cast<uint4 *>(ent) + o0 * 32 + lane;
+    if (nrows > RC_MAX_ROWS || !recolor) {  // too long for the staging buffers: arrival order, padding rewritten
+      for (int r = 0; r < nrows; r++) {
+        uint4 v = rows[(int64_t)r * 32];
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q8 = 0; q8 < 8; q8++)
+          if (r * 8 + q8 >= deg) {
+            const uint32_t m = 0xFFFFu << (16 * (q8 & 1));
+            w[q8 >> 1] = (w[q8 >> 1] & ~m) | ((uint32_t)((PAD0 + l16) * 8) << (16 * (q8 & 1)));
+          }
+        rows[(int64_t)r * 32] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      continue;
+    }
+    __syncwarp();
+    for (int r = 0; r < nrows; r++) {
+      const uint4 v = rows[(int64_t)r * 32];
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int q8 = 0; q8 < 8; q8++) e[(r * 8 + q8) * 32 + lane] = (uint16_t)((w[q8 >> 1] >> (16 * (q8 & 1))) & 0xFFFFu);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      lane_used[lane * 4 + k] = 0;
+      bank_used[lane * 4 + k] = 0;  // 2 halves x 16 banks = 32 mask rows
+    }
+    int maxdeg = deg;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) maxdeg = max(maxdeg, __shfl_xor_sync(0xffffffffu, maxdeg, o));
+    __syncwarp();
+    for (int k = 0; k < maxdeg; k++) {
+      for (int turn = 0; turn < 16; turn++) {
+        if (l16 == turn && k < deg) {
+          const int bank = (e[k * 32 + lane] >> 3) & 15;
+          unsigned long long *lu = lane_used + lane * 4, *bu = bank_used + (half * 16 + bank) * 4;
+          int c = -1;
+          for (int w4 = 0; w4 < 4 && c < 0; w4++) {
+            const unsigned long long freem = ~(lu[w4] | bu[w4]) & slot_mask(S, w4);
+            if (freem) c = w4 * 64 + __ffsll((long long)freem) - 1;
+          }
+          if (c < 0) {  // no conflict-free slot left: any slot of the lane (deg <= S - SLACK, so one exists)
+            for (int w4 = 0; w4 < 4 && c < 0; w4++) {
+              const unsigned long long freem = ~lu[w4] & slot_mask(S, w4);
+              if (freem) c = w4 * 64 + __ffsll((long long)freem) - 1;
+            }
+          }
+          lu[c >> 6] |= 1ull << (c & 63);
+          bu[c >> 6] |= 1ull << (c & 63);
+          col[k * 32 + lane] = (uint8_t)c;
+        }
+        __syncwarp();
+      }
+    }
+    // unused slots: all lanes of a half-warp that idle in slot c read the SAME zero word (a broadcast), the one of a bank no
+    // entry of the slot uses -- a slot with an idle lane has at most 15 entries, so a free bank exists
+    for (int c = l16; c < S; c += 16) {
+      int f = 0;
+      for (int bk = 0; bk < 16; bk++)
+        if (!((bank_used[(half * 16 + bk) * 4 + (c >> 6)] >> (c & 63)) & 1ull)) {
+          f = bk;
+          break;
+        }
+      padf[half * S_MAX + c] = (uint8_t)f;
+    }
+    __syncwarp();
+    for (int r = 0; r < nrows; r++) {
+      uint32_t w[4];
+#pragma unroll
+      for (int q8 = 0; q8 < 8; q8 += 2)
+        w[q8 >> 1] = (uint32_t)((PAD0 + padf[half * S_MAX + r * 8 + q8]) * 8) | ((uint32_t)((PAD0 + padf[half * S_MAX + r * 8 + q8 + 1]) * 8) << 16);
+      rows[(int64_t)r * 32] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    __syncwarp();
+    uint16_t *mine = ent + (o0 * 32 + lane) * 8;  // slot c of this lane: mine[(c >> 3) * 256 + (c & 7)]
+    for (int k = 0; k < deg; k++) {
+      const int c = col[k * 32 + lane];
+      mine[(int64_t)(c >> 3) * 256 + (c & 7)] = e[k * 32 + lane];
+    }
+    __syncwarp();
   }
 }
 
 // N[line] = sum of Q over the line's missing entries, as (low 32-bit halves, high halves) exact 64-bit sums.
-// grid = (group CTAs, chunk splits): a CTA of 32 warps walks its range of chunks -- per chunk one cooperative load of the
-// 32 KB vector slice into shared memory, then every warp consumes the block(s) of its line group(s).  The per-chunk phase
-// costs a few microseconds of latency whatever the work, so the chunks are split over several CTAs when there are few
-// groups (the partial sums are then combined with 64-bit integer atomics: exact, order free).
+// grid = (group CTAs, chunk splits), two CTAs of 16 warps per SM: a CTA walks its range of chunks -- the 32 KB vector slice
+// of chunk c + 1 streams into the second shared-memory buffer (cp.async) while every warp consumes the block(s) of its line
+// group(s) for chunk c; one barrier per chunk.  A warp's blocks of consecutive chunks are contiguous in memory, so it reads
+// one sequential stream of index rows and asks L2 for the next 4 KB ahead of use.  With few groups the chunks are split
+// over several CTAs (the partial sums are then combined with 64-bit integer atomics: exact, order free).
+// Every slot of a block is gathered (unused ones read a zero word): no per-line counts, no predicates.
+// dst_stride = 2: outN[line][2] (k_apply places them); dst_stride = 16: straight into part[line][8], part[line][12]
+// (identity line order, `part` zeroed by the matvec launcher), always with atomics.
+constexpr int SQ_WORDS = CH + 16;
+constexpr int CORR_SMEM = 2 * SQ_WORDS * (int)sizeof(long long);
+
 template <int GWT>
-__global__ void __launch_bounds__(CORR_WARPS * 32, 1)
-    k_corr(const uint16_t *__restrict__ cnt, const long long *__restrict__ off, const uint16_t *__restrict__ ent, int nchunks,
-           int ngroups, int gw, const long long *__restrict__ Q, int64_t qlen, long long *__restrict__ outN) {
-  __shared__ long long sq[CH];
+__global__ void __launch_bounds__(CORR_WARPS * 32, 2)
+    k_corr(const long long *__restrict__ off, const uint16_t *__restrict__ ent, int nchunks, int ngroups, int gw,
+           const long long *__restrict__ Q, int64_t qlen, long long *__restrict__ outN, int dst_stride, int dst_hi, int nlines) {
+  extern __shared__ __align__(16) long long sq_all[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t W = (int64_t)blockIdx.x * CORR_WARPS + warp, TW = (int64_t)gridDim.x * CORR_WARPS;
   const int cper = (nchunks + gridDim.y - 1) / gridDim.y;
   const int c0 = blockIdx.y * cper, c1 = min(nchunks, c0 + cper);
-  const bool atomic = gridDim.y > 1;
+  const bool atomic = gridDim.y > 1 || dst_stride != 2;
   const int npass = (int)((ngroups + TW * gw - 1) / (TW * gw));
+  if (threadIdx.x < 32) sq_all[(threadIdx.x >> 4) * SQ_WORDS + CH + (threadIdx.x & 15)] = 0;
+  const uint32_t sq_base = (uint32_t)__cvta_generic_to_shared(sq_all);
+  auto stage = [&](int c, int buf) {  // vector slice of chunk c -> buffer buf; entries past the end are zero-filled
+    if ((int64_t)(c + 1) * CH <= qlen) {  // whole chunk inside the vector: plain 16-byte copies
+      const long long *src = Q + (int64_t)c * CH + 2 * threadIdx.x;
+      const uint32_t dst = sq_base + (uint32_t)((buf * SQ_WORDS + 2 * threadIdx.x) * 8);
+#pragma unroll
+      for (int u = 0; u < CH / 2 / (CORR_WARPS * 32); u++)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + u * CORR_WARPS * 32 * 16), "l"(src + u * CORR_WARPS * 32 * 2)
+                     : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      return;
+    }
+    for (int t = threadIdx.x; t < CH / 2; t += CORR_WARPS * 32) {
+      const int64_t q = (int64_t)c * CH + 2 * t;
+      const int64_t left = (qlen - q) * 8;
+      const int bytes = left >= 16 ? 16 : (left > 0 ? (int)left : 0);
+      const long long *src = bytes > 0 ? Q + q : Q;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sq_base + (uint32_t)((buf * SQ_WORDS + 2 * t) * 8)), "l"(src),
+                   "r"(bytes)
+                   : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
   for (int pass = 0; pass < npass; pass++) {
     // groups are dealt round-robin over the warps of the grid: group (pass * gw + k) * TW + W
     long long lo[GWT], hi[GWT];
 #pragma unroll
     for (int k = 0; k < GWT; k++) lo[k] = hi[k] = 0;
+    __syncthreads();  // the buffers of the previous pass are no longer read
+    if (c0 < c1) stage(c0, 0);
     for (int c = c0; c < c1; c++) {
-      // GWT == 1 (few groups: the per-chunk phase latency dominates): the block's counts, offsets and first 8 rows are
-      // requested BEFORE the vector slice is staged, so their latency chain overlaps the cooperative load and its barriers
+      const int buf = (c - c0) & 1;
+      const unsigned char *sq = reinterpret_cast<const unsigned char *>(sq_all + buf * SQ_WORDS);
+      // entries are byte offsets into the slice.  |Q| < 2^60, so the 8 values of a row add up without overflow; the row
+      // sum is then split into its 32-bit halves (exact over any number of rows)
+      auto consume = [&](const uint4 &v, long long &l, long long &hh) {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        long long q[8];
+#pragma unroll
+        for (int q8 = 0; q8 < 8; q8++)
+          q[q8] = *reinterpret_cast<const long long *>(sq + ((q8 & 1) ? (w[q8 >> 1] >> 16) : (w[q8 >> 1] & 0xFFFFu)));
+        const long long rs = ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
+        l += (long long)(unsigned int)(rs & 0xFFFFFFFFll);
+        hh += rs >> 32;
+      };
+      // GWT == 1 (few groups): the block's offsets and first 8 rows are requested BEFORE the wait for the vector slice
       uint4 pre[GWT == 1 ? 8 : 1];
-      int pre_nme = 0, pre_nrows = 0;
+      int pre_nrows = 0;
       const uint4 *pre_e = nullptr;
       if (GWT == 1) {
         const int64_t g = (int64_t)pass * TW + W;
         if (g < ngroups) {
           const int64_t blk = g * nchunks + c;
-          pre_nme = cnt[blk * 32 + lane];
           const long long o0 = off[blk];
           pre_nrows = (int)(off[blk + 1] - o0);
           pre_e = reinterpret_cast<const uint4 *>(ent) + o0 * 32 + lane;
 #pragma unroll
           for (int u = 0; u < 8; u++) pre[u] = (u < pre_nrows) ? __ldg(pre_e + (int64_t)u * 32) : make_uint4(0, 0, 0, 0);
+          if (c + 1 < c1)  // the rows of the next chunk follow directly: 4 KB ahead into L2
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(ent) + (o0 + pre_nrows) * 512 + lane * 128));
         }
       }
-      __syncthreads();
-      for (int t = threadIdx.x; t < CH; t += CORR_WARPS * 32) {
-        const int64_t q = (int64_t)c * CH + t;
-        sq[t] = q < qlen ? Q[q] : 0;
-      }
-      __syncthreads();
-      auto consume = [&](const uint4 &v, int row, int nme, long long &l, long long &hh) {
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int q8 = 0; q8 < 8; q8++) {
-          if (row * 8 + q8 < nme) {
-            const long long q = sq[(w[q8 >> 1] >> (16 * (q8 & 1))) & 0xFFFFu];
-            l += (long long)(unsigned int)(q & 0xFFFFFFFFll);
-            hh += q >> 32;
-          }
-        }
-      };
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();  // slice c is complete for every thread, and nobody still reads the other buffer (slice c - 1)
+      if (c + 1 < c1) stage(c + 1, buf ^ 1);
       if (GWT == 1) {
 #pragma unroll
         for (int u = 0; u < 8; u++)
-          if (u < pre_nrows) consume(pre[u], u, pre_nme, lo[0], hi[0]);
-        for (int r = 8; r < pre_nrows; r++) consume(__ldg(pre_e + (int64_t)r * 32), r, pre_nme, lo[0], hi[0]);
+          if (u < pre_nrows) consume(pre[u], lo[0], hi[0]);
+        for (int r0 = 8; r0 < pre_nrows; r0 += 4) {
+          uint4 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) v[u] = (r0 + u < pre_nrows) ? __ldg(pre_e + (int64_t)(r0 + u) * 32) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+            if (r0 + u < pre_nrows) consume(v[u], lo[0], hi[0]);
+        }
         continue;
       }
 #pragma unroll
@@ -216,7 +379,6 @@ __global__ void __launch_bounds__(CORR_WARPS * 32, 1)
         const int64_t g = ((int64_t)pass * gw + k) * TW + W;
         if (k < gw && g < ngroups) {  // warp-uniform
           const int64_t blk = g * nchunks + c;
-          const int nme = cnt[blk * 32 + lane];
           const long long o0 = off[blk];
           const int nrows = (int)(off[blk + 1] - o0);  // rows of 8 entries per line (warp-uniform)
           const uint4 *e = reinterpret_cast<const uint4 *>(ent) + o0 * 32 + lane;
@@ -225,17 +387,8 @@ __global__ void __launch_bounds__(CORR_WARPS * 32, 1)
 #pragma unroll
             for (int u = 0; u < 4; u++) v[u] = (r0 + u < nrows) ? __ldg(e + (int64_t)(r0 + u) * 32) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-              const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-#pragma unroll
-              for (int q8 = 0; q8 < 8; q8++) {
-                if ((r0 + u) * 8 + q8 < nme) {
-                  const long long q = sq[(w[q8 >> 1] >> (16 * (q8 & 1))) & 0xFFFFu];
-                  lo[k] += (long long)(unsigned int)(q & 0xFFFFFFFFll);
-                  hi[k] += q >> 32;
-                }
-              }
-            }
+            for (int u = 0; u < 4; u++)
+              if (r0 + u < nrows) consume(v[u], lo[k], hi[k]);
           }
         }
       }
@@ -243,14 +396,14 @@ __global__ void __launch_bounds__(CORR_WARPS * 32, 1)
 #pragma unroll
     for (int k = 0; k < GWT; k++) {
       const int64_t g = ((int64_t)pass * gw + k) * TW + W;
-      if (k < gw && g < ngroups) {
-        long long *dst = outN + (g * 32 + lane) * 2;
+      if (k < gw && g < ngroups && g * 32 + lane < nlines) {
+        long long *dst = outN + (g * 32 + lane) * dst_stride;
         if (atomic) {
           if (lo[k]) atomicAdd(reinterpret_cast<unsigned long long *>(dst), (unsigned long long)lo[k]);
-          if (hi[k]) atomicAdd(reinterpret_cast<unsigned long long *>(dst + 1), (unsigned long long)hi[k]);
+          if (hi[k]) atomicAdd(reinterpret_cast<unsigned long long *>(dst + dst_hi), (unsigned long long)hi[k]);
         } else {
           dst[0] = lo[k];
-          dst[1] = hi[k];
+          dst[dst_hi] = hi[k];
         }
       }
     }
@@ -309,7 +462,7 @@ bool na_ell_ready(bsg_bed *h) {
       size_t fr = 0, tot = 0;
       cudaMemGetInfo(&fr, &tot);
       const size_t meta = (size_t)nblocks * 64 + (size_t)(nblocks + 1) * 16 + (size_t)ngroups * 32 * 16;
-      if (meta + (size_t)(2.8 * (double)nnz) + ((size_t)2 << 30) > fr) break;  // expected entries incl. padding
+      if (meta + (size_t)(3.2 * (double)nnz) + ((size_t)2 << 30) > fr) break;  // expected entries incl. padding
       if (cudaMalloc((void **)&cnt, (size_t)nblocks * 32 * sizeof(uint16_t)) != cudaSuccess ||
           cudaMalloc((void **)&blk, (size_t)(nblocks + 1) * sizeof(long long)) != cudaSuccess ||
           cudaMalloc((void **)&off, (size_t)(nblocks + 1) * sizeof(long long)) != cudaSuccess ||
@@ -333,7 +486,7 @@ bool na_ell_ready(bsg_bed *h) {
         break;
       cudaMemGetInfo(&fr, &tot);
       if ((size_t)rows * 512 + ((size_t)2 << 30) > fr) break;
-      if (cudaMalloc((void **)&ent, std::max<size_t>((size_t)rows * 512, 512)) != cudaSuccess) break;
+      if (cudaMalloc((void **)&ent, std::max<size_t>((size_t)rows * 512, 512) + 4096) != cudaSuccess) break;  // + the L2 look-ahead of k_corr
       if (cudaMemsetAsync(ent, 0, std::max<size_t>((size_t)rows * 512, 512), s) != cudaSuccess) break;
       if (side == 1) {
         k_fill_lines<<<grid_cap((int64_t)m * nchunks * 32, 256), 256, 0, s>>>(h->A, h->strideA, n, m, nchunks, off, ent);
@@ -341,7 +494,13 @@ bool na_ell_ready(bsg_bed *h) {
         dim3 grid((unsigned)nchunks, (unsigned)((h->strideA / 4 + 31) / 32));
         k_fill_samples<<<grid, 256, 0, s>>>(h->A, h->strideA, n, m, nchunks, off, ent);
       }
-      count_launch(4);
+      {
+        const char *er = getenv("BSG_NA_RECOLOR");  // 0: keep the arrival order (measurement switch); padding is rewritten either way
+        const size_t smem = (size_t)RC_WARPS * RC_WARP_SMEM;
+        if (cudaFuncSetAttribute(k_recolor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) break;
+        k_recolor<<<grid_cap(nblocks * 32, RC_WARPS * 32), RC_WARPS * 32, smem, s>>>(cnt, off, ent, nblocks, (er && er[0] == '0') ? 0 : 1);
+      }
+      count_launch(5);
       if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) break;
       ok = true;
     } while (0);
@@ -355,7 +514,8 @@ bool na_ell_ready(bsg_bed *h) {
       cudaFree(outN);
       break;
     }
-    h->ellCnt[side] = cnt;
+    cudaFree(cnt);  // only the build needs the per-line counts
+    h->ellCnt[side] = nullptr;
     h->ellOff[side] = off;
     h->ellEnt[side] = ent;
     h->ellOut[side] = outN;
@@ -388,22 +548,30 @@ int na_ell_correction(bsg_bed *h, int side, const int *lines, int nlines, const 
   int nsm = 148;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
   const int ngroups = h->ellGroups[side], nchunks = h->ellChunks[side];
-  // one CTA of 32 warps per SM: few groups -> one group per warp and the chunks split over several CTAs (about two waves,
-  // at least ~8 chunks each); many groups -> up to GW groups per warp, one wave
-  const int64_t warp_slots = (int64_t)nsm * CORR_WARPS;
+  // two CTAs of 16 warps per SM: few groups -> one group per warp and the chunks split over several CTAs (one resident
+  // wave, at least ~8 chunks each); many groups -> up to GW groups per warp
+  const int64_t cta_slots = 2 * (int64_t)nsm, warp_slots = cta_slots * CORR_WARPS;
   int gw = (int)std::min<int64_t>(GW, std::max<int64_t>(1, (ngroups + warp_slots - 1) / warp_slots));
-  int gctas = (int)std::min<int64_t>(nsm, ((int64_t)ngroups + (int64_t)CORR_WARPS * gw - 1) / ((int64_t)CORR_WARPS * gw));
+  int gctas = (int)std::min<int64_t>(cta_slots, ((int64_t)ngroups + (int64_t)CORR_WARPS * gw - 1) / ((int64_t)CORR_WARPS * gw));
   gctas = std::max(gctas, 1);
-  int nsplit = std::max(1, std::min(std::max(1, nchunks / 8), (2 * nsm) / gctas));
-  if (nsplit > 1) BSG_CUDA(cudaMemsetAsync(h->ellOut[side], 0, (size_t)ngroups * 32 * 2 * sizeof(long long), s));
+  int nsplit = std::max(1, std::min(std::max(1, nchunks / 8), (int)(cta_slots / gctas)));
+  BSG_CUDA(cudaFuncSetAttribute(k_corr<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CORR_SMEM));  // per device
+  BSG_CUDA(cudaFuncSetAttribute(k_corr<GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, CORR_SMEM));
+  // identity line order (X.y: every sample): the sums go straight into part[line][8] / [12] (zeroed by the launcher of the
+  // matvec kernel) with integer atomics; otherwise into outN and k_apply places the selected lines
+  const bool direct = lines == nullptr;
+  long long *dst = direct ? part + 8 : h->ellOut[side];
+  const int dst_stride = direct ? 16 : 2, dst_hi = direct ? 4 : 1;
+  const int dst_lines = direct ? nlines : ngroups * 32;
+  if (!direct && nsplit > 1) BSG_CUDA(cudaMemsetAsync(h->ellOut[side], 0, (size_t)ngroups * 32 * 2 * sizeof(long long), s));
   dim3 grid((unsigned)gctas, (unsigned)nsplit);
   if (gw == 1)
-    k_corr<1><<<grid, CORR_WARPS * 32, 0, s>>>(h->ellCnt[side], h->ellOff[side], h->ellEnt[side], nchunks, ngroups, gw, Q,
-                                               side == 0 ? h->m : h->n, h->ellOut[side]);
+    k_corr<1><<<grid, CORR_WARPS * 32, CORR_SMEM, s>>>(h->ellOff[side], h->ellEnt[side], nchunks, ngroups, gw, Q,
+                                               side == 0 ? h->m : h->n, dst, dst_stride, dst_hi, dst_lines);
   else
-    k_corr<GW><<<grid, CORR_WARPS * 32, 0, s>>>(h->ellCnt[side], h->ellOff[side], h->ellEnt[side], nchunks, ngroups, gw, Q,
-                                                side == 0 ? h->m : h->n, h->ellOut[side]);
-  k_apply<<<(nlines + 255) / 256, 256, 0, s>>>(h->ellOut[side], lines, nlines, part);
+    k_corr<GW><<<grid, CORR_WARPS * 32, CORR_SMEM, s>>>(h->ellOff[side], h->ellEnt[side], nchunks, ngroups, gw, Q,
+                                                side == 0 ? h->m : h->n, dst, dst_stride, dst_hi, dst_lines);
+  if (!direct) k_apply<<<(nlines + 255) / 256, 256, 0, s>>>(h->ellOut[side], lines, nlines, part);
   count_launch(2);
   BSG_CUDA(cudaGetLastError());
   return BSG_OK;

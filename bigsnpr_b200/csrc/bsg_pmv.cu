@@ -1296,6 +1296,61 @@ __global__ void k_finish_prod_pair(const long long *__restrict__ part, int nline
     out[l] = r;
   }
 }
+
+// Two vectors per pass through k_pmv (lines = SNP columns, vectors over the samples: multLinReg).  Digit layout of
+// k_digits, slices 0..3 = 30-bit vector 1 (Qa), 4..7 = vector 2 (Qb).
+__global__ void k_digits_pair(const long long *__restrict__ Qa, const long long *__restrict__ Qb, int len, int nchunks,
+                              uint8_t *__restrict__ dig) {
+  const int64_t total = (int64_t)nchunks * 256;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int chunk = (int)(t >> 8), unit = (int)(t & 255);
+    const int q = unit & 3, s = (unit >> 2) & 7, w = unit >> 5;
+    const long long *Q = s < 4 ? Qa : Qb;
+    const int sd = s & 3;
+    uint32_t out[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const int64_t k = (int64_t)chunk * pmv::CODES + (w < 4 ? 64 * q + 16 * w : 256 + 64 * q + 16 * (w - 4)) + 4 * r + c;
+        long long v = (Q && k < len) ? Q[k] : 0;
+        int d = 0;
+        for (int i = 0; i <= sd; i++) {
+          d = (int)(signed char)(v & 0xFF);
+          v = (v - d) >> 8;
+        }
+        out[c] |= (uint32_t)(d & 0xFF) << (8 * r);
+      }
+    }
+    reinterpret_cast<uint4 *>(dig)[t] = make_uint4(out[0], out[1], out[2], out[3]);
+  }
+}
+
+// per vector vv:  out_l = cR R_l + cP P_l,  outB_l = cRb R_l + cPb P_l   (R raw-plane sum, P missing-value plane sum of
+// the SAME vector: one digit block serves both planes)
+struct PairCoef {
+  double cR, cP, cRb, cPb;
+  double *out, *outB;
+};
+__global__ void k_finish_planes_pair(const long long *__restrict__ part, int nlines, const pmv::Scal *sc, int have_p,
+                                     PairCoef ca, PairCoef cb) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= nlines) return;
+#pragma unroll
+  for (int vv = 0; vv < 2; vv++) {
+    const PairCoef &c = vv ? cb : ca;
+    if (!c.out) continue;
+    if (sc[vv].nonfinite) {
+      c.out[l] = nan("");
+      if (c.outB) c.outB[l] = nan("");
+      continue;
+    }
+    const double R = combine4(part, l, vv, 1, 0, sc[vv].e[0]);
+    const double P = have_p ? combine4(part, l, vv, 0, 1, sc[vv].e[0]) : 0.0;
+    c.out[l] = c.cR * R + c.cP * P;
+    if (c.outB) c.outB[l] = c.cRb * R + c.cPb * P;
+  }
+}
 }  // namespace pmvt
 
 
@@ -1981,6 +2036,48 @@ static int view_planes_dev(bsg_view *v, int dir, const double *x1, const double 
   return BSG_OK;
 }
 
+
+// Xt-side plane sums of TWO vectors in one pass over the SNP-major copy (30-bit fixed point each, see k_pick_exp_pair):
+// per vector R_l = sum_t code(l, t) x[t] and, with plane == PLANE_NA, N_l = sum_t [missing(l, t)] x[t].
+static int view_planes_pair_dev(bsg_view *v, const double *xa, const double *xb, int plane, const pmvt::PairCoef &ca,
+                                const pmvt::PairCoef &cb, cudaStream_t s) {
+  using namespace pmv;
+  bsg_bed *h = v->h;
+  if (plane == PLANE_NA && !h->has_na) plane = PLANE_NONE;
+  Scal *sc = v->s_scal.as<Scal>();
+  const int L = h->n, len = v->nr;
+  const int hb = hb_bits(v->row_maxmult);
+  const int64_t stride = h->strideA;
+  const int nchunks = (int)(stride / SEG);
+  BSG_TRY(v->s_dig1.ensure((size_t)nchunks * DIG));
+  BSG_TRY(v->s_q0.ensure((size_t)L * sizeof(long long)));
+  BSG_TRY(v->s_q1.ensure((size_t)L * sizeof(long long)));
+  uint8_t *dig1 = v->s_dig1.as<uint8_t>();
+  long long *Q0 = v->s_q0.as<long long>(), *Q1 = v->s_q1.as<long long>();
+  const int *idx = v->row_identity ? nullptr : v->d_row;
+  k_scal_reset<<<1, 1, 0, s>>>(sc);
+  k_scal_reset<<<1, 1, 0, s>>>(sc + 1);
+  k_maxabs<<<launch_cap(len, 256, 592), 256, 0, s>>>(0, xa, nullptr, nullptr, len, sc);
+  if (xb) k_maxabs<<<launch_cap(len, 256, 592), 256, 0, s>>>(0, xb, nullptr, nullptr, len, sc + 1);
+  pmvt::k_pick_exp_pair<<<1, 32, 0, s>>>(sc, hb);
+  if (idx) {
+    BSG_CUDA(cudaMemsetAsync(Q0, 0, (size_t)L * sizeof(long long), s));
+    BSG_CUDA(cudaMemsetAsync(Q1, 0, (size_t)L * sizeof(long long), s));
+  }
+  k_quantise<<<launch_cap(len, 256, 592), 256, 0, s>>>(0, xa, nullptr, nullptr, len, idx, sc, Q0, nullptr);
+  if (xb) k_quantise<<<launch_cap(len, 256, 592), 256, 0, s>>>(0, xb, nullptr, nullptr, len, idx, sc + 1, Q1, nullptr);
+  pmvt::k_digits_pair<<<launch_cap((int64_t)nchunks * 256, 256, 1184), 256, 0, s>>>(Q0, xb ? Q1 : nullptr, idx ? L : len, nchunks,
+                                                                                  dig1);
+  count_launch(6 + (xb ? 2 : 0));
+  Args a;
+  const int nlines = v->nc;
+  BSG_TRY(run_pmv(v, h->A, stride, L, v->d_col, nlines, dig1, nullptr, h->naA, plane != PLANE_NONE, &a, s, false));
+  pmvt::k_finish_planes_pair<<<(nlines + 255) / 256, 256, 0, s>>>(a.part, nlines, sc, plane != PLANE_NONE, ca, cb);
+  count_launch();
+  BSG_CUDA(cudaGetLastError());
+  return BSG_OK;
+}
+
 // per selected column: a = (1 - 2c)/s^2, w = 1/s^2, nv = (5 - 6c + c^2)/s^2 and block partials of T = sum c^2/s^2
 __global__ void k_rss_weights(const double *__restrict__ center, const double *__restrict__ scale, int nc,
                               double *__restrict__ a, double *__restrict__ w, double *__restrict__ nv,
@@ -2246,14 +2343,37 @@ int bsg_multlinreg(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, i
     k_square<<<launch_cap_pub((int64_t)nr * K), 256, 0, s>>>(dU, (int64_t)nr * K, dUU);
     count_launch();
   }
-  for (int k = 0; k < K; k++) {
-    const double *u = dU + (size_t)k * nr;
-    PlaneOut o1{1.0, na ? -3.0 : 0.0, 0.0, dG + (size_t)k * nc, 0.0, 1.0, na ? dNu + (size_t)k * nc : nullptr};
-    BSG_TRY(view_planes_dev(v, 1, u, u, na ? PLANE_NA : PLANE_NONE, o1, s));
-    if (na) {
-      const double *uu = dUU + (size_t)k * nr;
-      PlaneOut o2{0.0, 1.0, 0.0, dNuu + (size_t)k * nc, 0, 0, nullptr};
-      BSG_TRY(view_planes_dev(v, 1, uu, uu, PLANE_NA, o2, s));
+  static int pair_mode = -1;
+  if (pair_mode < 0) {
+    const char *ev = getenv("BSG_MLR_PAIR");
+    pair_mode = (ev && ev[0] == '0') ? 0 : 1;
+  }
+  if (pair_mode && K >= 2) {
+    // two columns of U per pass over the matrix (30-bit fixed point per vector: ~1e-9 of the sums)
+    for (int k = 0; k < K; k += 2) {
+      const bool both = k + 1 < K;
+      const double *ua = dU + (size_t)k * nr, *ub = both ? dU + (size_t)(k + 1) * nr : nullptr;
+      pmvt::PairCoef ca{1.0, na ? -3.0 : 0.0, 0.0, 1.0, dG + (size_t)k * nc, na ? dNu + (size_t)k * nc : nullptr};
+      pmvt::PairCoef cb{1.0, na ? -3.0 : 0.0, 0.0, 1.0, both ? dG + (size_t)(k + 1) * nc : nullptr,
+                        (na && both) ? dNu + (size_t)(k + 1) * nc : nullptr};
+      BSG_TRY(view_planes_pair_dev(v, ua, ub, na ? PLANE_NA : PLANE_NONE, ca, cb, s));
+      if (na) {
+        const double *uua = dUU + (size_t)k * nr, *uub = both ? dUU + (size_t)(k + 1) * nr : nullptr;
+        pmvt::PairCoef da{0.0, 1.0, 0.0, 0.0, dNuu + (size_t)k * nc, nullptr};
+        pmvt::PairCoef db{0.0, 1.0, 0.0, 0.0, both ? dNuu + (size_t)(k + 1) * nc : nullptr, nullptr};
+        BSG_TRY(view_planes_pair_dev(v, uua, uub, PLANE_NA, da, db, s));
+      }
+    }
+  } else {
+    for (int k = 0; k < K; k++) {
+      const double *u = dU + (size_t)k * nr;
+      PlaneOut o1{1.0, na ? -3.0 : 0.0, 0.0, dG + (size_t)k * nc, 0.0, 1.0, na ? dNu + (size_t)k * nc : nullptr};
+      BSG_TRY(view_planes_dev(v, 1, u, u, na ? PLANE_NA : PLANE_NONE, o1, s));
+      if (na) {
+        const double *uu = dUU + (size_t)k * nr;
+        PlaneOut o2{0.0, 1.0, 0.0, dNuu + (size_t)k * nc, 0, 0, nullptr};
+        BSG_TRY(view_planes_dev(v, 1, uu, uu, PLANE_NA, o2, s));
+      }
     }
   }
   BSG_CUDA(cudaStreamSynchronize(s));  // the counts helper stages its index upload from host memory

@@ -468,7 +468,8 @@ def test_multLinReg_pcadapt(B, gbed, gbed_na, oracle, obed, obed_na, rng):
             to = oracle.multLinReg(o, ir, ic, U, ncores=2)
             assert np.array_equal(np.isnan(t), np.isnan(to))
             ok = ~np.isnan(to)
-            assert np.max(np.abs(t[ok] - to[ok]) / (1.0 + np.abs(to[ok]))) < 1e-9
+            # K >= 2: two columns of U per pass, 30-bit fixed point each (bsg_pmv.cu view_planes_pair_dev); K = 1: 61 bits
+            assert np.max(np.abs(t[ok] - to[ok]) / (1.0 + np.abs(to[ok]))) < (1e-7 if K >= 2 else 1e-9)
     # FBM.code256 handle == bed handle; constant column -> NA (deno == 0)
     G = rng.integers(0, 4, size=(120, 40)).astype(np.uint8)
     G[:, 5] = 1
@@ -483,7 +484,7 @@ def test_multLinReg_pcadapt(B, gbed, gbed_na, oracle, obed, obed_na, rng):
     t[7] = to[7] = np.nan
     assert np.array_equal(np.isnan(t), np.isnan(to))
     ok = ~np.isnan(to)
-    assert np.max(np.abs(t[ok] - to[ok]) / (1.0 + np.abs(to[ok]))) < 1e-9
+    assert np.max(np.abs(t[ok] - to[ok]) / (1.0 + np.abs(to[ok]))) < 1e-7
     res = B.bed_pcadapt(gbed, U_row=np.linalg.qr(rng.normal(size=(obed.nrow, 1)))[0][:, 0])
     assert res["tscores"].shape == (obed.ncol, 1) and res["score"].shape == (obed.ncol,)
     with pytest.raises(ValueError, match="Incompatibility between dimensions."):

