@@ -1174,8 +1174,13 @@ __global__ void __launch_bounds__(TWARPS * 32, 2) k_pmvT2(const TArgs a, const u
 __global__ void k_quantT(int mode, const double *__restrict__ x, const double *__restrict__ center,
                          const double *__restrict__ scale, int len, int len_pad, const pmv::Scal *sc,
                          uint8_t *__restrict__ dig1, uint8_t *__restrict__ dig2, const int *__restrict__ lines = nullptr,
-                         long long *__restrict__ qna_full = nullptr, int na_second = 0) {
-  const int e0 = sc->e[0], e1 = sc->e[1];
+                         long long *__restrict__ qna_full = nullptr, int na_second = 0, pmv::Scal *pick = nullptr) {
+  // pick: the exponents are derived here from the maxima k_prep1 left in *sc (and published for the finish kernels)
+  const int e0 = pick ? pmv::pick_e(sc->maxabs[0], sc->hb) : sc->e[0], e1 = pick ? pmv::pick_e(sc->maxabs[1], sc->hb) : sc->e[1];
+  if (pick && blockIdx.x == 0 && threadIdx.x == 0) {
+    pick->e[0] = e0;
+    pick->e[1] = e1;
+  }
   const bool bad = sc->nonfinite != 0;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < len_pad; t += gridDim.x * blockDim.x) {
     long long q0 = 0, q1 = 0;
@@ -1649,13 +1654,14 @@ static int prep_T(bsg_view *v, int mode, const double *x, const double *p1, cons
   const int nsteps = (nc + TLINES - 1) / TLINES;
   BSG_TRY(v->s_dig1.ensure((size_t)std::max(nsteps, 1) * 256));
   if (two) BSG_TRY(v->s_dig2.ensure((size_t)std::max(nsteps, 1) * 256));
-  k_scal_reset<<<1, 1, 0, s>>>(sc);
-  k_maxabs<<<launch_cap(nc, 256, 592), 256, 0, s>>>(mode, x, p1, p2, nc, sc);
-  k_pick_exp<<<1, 1, 0, s>>>(sc, 0);
+  // memset + 2 kernels: maxima, finiteness and (mode 1) the block partials of C = sum c z in one pass over the vector,
+  // then quantisation + digits with the exponents picked per block from the maxima
+  BSG_CUDA(cudaMemsetAsync(sc, 0, sizeof(Scal), s));
+  k_prep1<<<SUMCZ_BLOCKS, 256, 0, s>>>(mode, x, p1, p2, nc, 0, sc);
   k_quantT<<<launch_cap((int64_t)std::max(nsteps, 1) * TLINES, 256, 1184), 256, 0, s>>>(
       mode, x, p1, p2, nc, nsteps * TLINES, sc, v->s_dig1.as<uint8_t>(), two ? v->s_dig2.as<uint8_t>() : nullptr, v->d_col,
-      qna_full, na_second);
-  count_launch(4);
+      qna_full, na_second, sc);
+  count_launch(2);
   return BSG_OK;
 }
 
@@ -1675,11 +1681,7 @@ static int prodvec_T(bsg_view *v, const double *x_dev, double *out_dev, cudaStre
     qna = v->s_q1.as<long long>();
     BSG_CUDA(cudaMemsetAsync(qna, 0, (size_t)h->m * sizeof(long long), s));
   }
-  BSG_TRY(prep_T(v, mode, x_dev, v->d_center, v->d_scale, two, s, qna, v->has_scaling ? 1 : 0));
-  if (v->has_scaling) {
-    k_sum_cz<<<SUMCZ_BLOCKS, 256, 0, s>>>(x_dev, v->d_center, v->d_scale, nc, sc->cpart);
-    count_launch();
-  }
+  BSG_TRY(prep_T(v, mode, x_dev, v->d_center, v->d_scale, two, s, qna, v->has_scaling ? 1 : 0));  // incl. the partials of C
   long long *part = nullptr;
   BSG_TRY(run_pmvT(v, v->s_dig1.as<uint8_t>(), (h->has_na && !lists) ? 1 : 0,
                    two ? v->s_dig2.as<uint8_t>() : v->s_dig1.as<uint8_t>(), &part, s));
