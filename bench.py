@@ -338,6 +338,15 @@ def run_workload(args, wl_key, torch, dist, B, L, rank, world, local, with_cpu, 
                 "kernel": kernel, "kernel_ms": kern_ms, "launches_timed": cnt.value,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "kernel_share_of_step": (kern_ms * args.steps / ms) if ms > 0 else None}
+    if world > 1:
+        # the step ends in a collective, so it runs at the pace of the slowest GPU: show every rank's kernel time and clock
+        mine = torch.tensor([kern_ms, float(clocks.get("sm_mhz") or 0.0)], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        roofline["kernel_ms_per_rank"] = [round(float(t[0]), 4) for t in allr]
+        roofline["kernel_ms_max_over_ranks"] = max(float(t[0]) for t in allr)
+        roofline["sm_mhz_per_rank"] = [float(t[1]) for t in allr]
+        roofline["kernel_share_of_step"] = (roofline["kernel_ms_max_over_ranks"] * args.steps / ms) if ms > 0 else None
 
     # ---------------- e2e: the 9-argument C-ABI call with HOST buffers (H2D / D2H inside the timed region) --------
     e2e_steps = max(3, min(args.steps, 50))

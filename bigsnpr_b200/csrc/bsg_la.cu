@@ -16,6 +16,7 @@
 //                   bsg_tcrossprod_dev leaves K in the caller's device buffer (sharded GRM: one all-reduce).
 #include <cublas_v2.h>
 #include <math.h>
+#include <cmath>
 #include <string.h>
 
 #include <algorithm>
@@ -591,11 +592,18 @@ int lanczos_svd(std::vector<SvdShard> &sh, const int *ind_row, int nr, int ncol_
       BSG_CUDA(cudaMemcpyAsync(sc2, rep[0].W.scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, rep[0].s));
       BSG_CUDA(cudaStreamSynchronize(rep[0].s));
       beta_last = sc2[0];
+      bool finite = std::isfinite(beta_last);
       for (int j = have; j < ncv; j++)
         for (int i = 0; i <= j; i++) {
-          T[(size_t)j * ncv + i] = Td[(size_t)j * ncv + i];
-          T[(size_t)i * ncv + j] = Td[(size_t)j * ncv + i];
+          const double t = Td[(size_t)j * ncv + i];
+          finite = finite && std::isfinite(t);
+          T[(size_t)j * ncv + i] = t;
+          T[(size_t)i * ncv + j] = t;
         }
+      // the device-vector products turn a zero / non-finite scale or center into an all-NaN result (include/bsgpu.h):
+      // stop here instead of iterating on NaNs (RSpectra fails on such an operator too)
+      if (!finite)
+        return fail(BSG_ERR_ARG, "non-finite values in the scaled matrix-vector products (zero or non-finite scale / center?).");
     }
     have = ncv;
     // ---- Ritz pairs of the projected matrix

@@ -104,7 +104,11 @@ void bsg_view_destroy(bsg_view *v);
 int bsg_view_prodvec(bsg_view *v, const double *x, double *out);   /* host vectors */
 int bsg_view_cprodvec(bsg_view *v, const double *x, double *out);  /* host vectors */
 /* device-resident vectors, enqueued on `stream` (a cudaStream_t; NULL = the legacy default stream, i.e. ordered with
- * everything the caller enqueued on stream 0 -- torch's default stream included); no sync */
+ * everything the caller enqueued on stream 0 -- torch's default stream included); no sync.
+ * Non-finite input: the host-vector forms above reproduce the reference's per-element Inf / NaN propagation (a zero scale
+ * makes only that column's Xt.y entry NaN, src/bed-acc.h:98-111) by re-running through the accessor kernels.  The _dev
+ * forms cannot look at their result: ANY non-finite x, center or 1/scale entry makes the WHOLE output NaN.  The SVD
+ * drivers built on them return BSG_ERR_ARG in that case instead of iterating on NaNs. */
 int bsg_view_prodvec_dev(bsg_view *v, const double *x_dev, double *out_dev, void *stream);
 int bsg_view_cprodvec_dev(bsg_view *v, const double *x_dev, double *out_dev, void *stream);
 

@@ -388,6 +388,19 @@ def test_clumping_identical_to_oracle(B, gbed, gbed_na, oracle, obed, obed_na, r
         B.bed_clumping(gbed, ind_row=None)
 
 
+def test_randomSVD_degenerate_scaling_fails_loudly(B, gbed):
+    # the device-vector products turn a zero scale into an all-NaN result; the SVD built on them must not
+    # iterate on NaNs and hand back garbage -- it reports the degenerate operator (RSpectra fails on it as well)
+    def zero_scale(obj, ind_row=None, ind_col=None, **kw):
+        m = len(ind_col)
+        return {"center": np.zeros(m), "scale": np.r_[0.0, np.ones(m - 1)]}
+
+    with pytest.raises(B.BsgError, match="non-finite"):
+        B.bed_randomSVD(gbed, fun_scaling=zero_scale, k=3)
+    # and the handle is still usable afterwards
+    assert B.bed_randomSVD(gbed, k=2)["d"].shape == (2,)
+
+
 def test_clumping_against_reference_rds_golden(B, gbed, oracle, obed, golden_dir):
     # tests/testthat/test-6-PRS.R:25-31: the reference's stored snp_clumping result (testdata/clumping.rds) with the priority
     # order recovered from testdata/pval.rds (p-value = decreasing function of abs(gwas$score); only the order of S matters).
