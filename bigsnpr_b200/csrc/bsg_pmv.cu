@@ -846,7 +846,7 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   return r;
 }
 
-template <int PLANE, bool LINES>
+template <int PLANE, bool LINES, bool WHOLE = false>
 __global__ void __launch_bounds__(TWARPS * 32, 2) k_pmvT(const TArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
@@ -939,7 +939,10 @@ __global__ void __launch_bounds__(TWARPS * 32, 2) k_pmvT(const TArgs a) {
       mma_u8s8(acc[j][0], wa & 0x03030303u, wb & 0x03030303u, wc2 & 0x03030303u, wd & 0x03030303u, b0, b1);
       mma_u8s8(acc[j][1], wa & 0x0C0C0C0Cu, wb & 0x0C0C0C0Cu, wc2 & 0x0C0C0C0Cu, wd & 0x0C0C0C0Cu, b0, b1);
       mma_u8s8(acc[j][2], wa & 0x30303030u, wb & 0x30303030u, wc2 & 0x30303030u, wd & 0x30303030u, b0, b1);
-      mma_u8s8(acc[j][3], wa & 0xC0C0C0C0u, wb & 0xC0C0C0C0u, wc2 & 0xC0C0C0C0u, wd & 0xC0C0C0C0u, b0, b1);
+      if (WHOLE)  // experiment (BSG_PMVT_WHOLE=1): the whole byte (<= 255: 255 x 128 x 2^16 lines fits int32); the epilogue
+        mma_u8s8(acc[j][3], wa, wb, wc2, wd, b0, b1);  // recovers field 3 as whole - fields 0..2
+      else
+        mma_u8s8(acc[j][3], wa & 0xC0C0C0C0u, wb & 0xC0C0C0C0u, wc2 & 0xC0C0C0C0u, wd & 0xC0C0C0C0u, b0, b1);
     }
   };
 
@@ -991,6 +994,12 @@ __global__ void __launch_bounds__(TWARPS * 32, 2) k_pmvT(const TArgs a) {
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   // epilogue: D rows = samples (slot g / g + 8), D columns = slices 2q, 2q + 1
+  if (WHOLE) {
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+      for (int k = 0; k < 4; k++) acc[j][3][k] -= acc[j][0][k] + acc[j][1][k] + acc[j][2][k];
+  }
 #pragma unroll
   for (int j = 0; j < 4; j++)
 #pragma unroll
@@ -1615,7 +1624,18 @@ static int run_pmvT(bsg_view *v, const uint8_t *dig_raw, int plane, const uint8_
     if (lines)
       k_pmvT<0, true><<<grid, thr, TSMEM, s>>>(a);
     else
-      k_pmvT<0, false><<<grid, thr, TSMEM, s>>>(a);
+    {
+      static int whole = -1;
+      if (whole < 0) {
+        const char *ev = getenv("BSG_PMVT_WHOLE");
+        whole = (ev && ev[0] == '1') ? 1 : 0;
+        if (whole) BSG_CUDA(cudaFuncSetAttribute(k_pmvT<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TSMEM));
+      }
+      if (whole)
+        k_pmvT<0, false, true><<<grid, thr, TSMEM, s>>>(a);
+      else
+        k_pmvT<0, false><<<grid, thr, TSMEM, s>>>(a);
+    }
   } else {
     // both planes in one pass: 32-byte strips per warp, twice the sample blocks
     a.nblocks = (int)((nbytes + T2BYTES - 1) / T2BYTES);
