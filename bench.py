@@ -331,7 +331,9 @@ def run_workload(args, wl_key, torch, dist, B, L, rank, world, local, with_cpu, 
     kern_ms = tot.value / max(cnt.value, 1)
     peak, peak_src = measured_peaks()
     achieved = alg_bytes / (kern_ms / 1e3) / 1e9 if kern_ms > 0 else None
-    kernel = ("bsg::pmvt::k_pmvT2" if g.has_na else ("bsg::pmv::k_pmv" if (layouts & 2) else "bsg::pmvt::k_pmvT"))
+    # with missing values the product kernel runs in its no-missing mode and bsg::naell::k_corr adds the list sums
+    # (bigsnpr_b200/csrc/bsg_naell.cu); kernel_ms is the product kernel alone, ms_per_step the whole step
+    kernel = "bsg::pmv::k_pmv" if (layouts & 2) else "bsg::pmvt::k_pmvT"
     traffic, traffic_src = traffic_for(kernel, alg_bytes)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,

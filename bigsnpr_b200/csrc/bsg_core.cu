@@ -694,6 +694,9 @@ void bsg_close(bsg_bed *h) {
   for (DevBuf &b : h->w_proj) b.release();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  for (cudaEvent_t &e : h->copy_ev)
+    if (e) cudaEventDestroy(e);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }

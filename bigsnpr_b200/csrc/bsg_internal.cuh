@@ -99,6 +99,8 @@ struct bsg_bed {
   double *d_code = nullptr;  // generic FBM: code256 on the device [0,256) and the same with NA -> 3 [256,512)
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t copy_stream = nullptr;  // created on first use: host -> device uploads that run under the kernels of `stream`
+  cudaEvent_t copy_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // view cached for the 9-argument drop-in matvec calls (bsg_prodvec / bsg_cprodvec)
   struct bsg_view *cv = nullptr;
   std::vector<int> cv_row, cv_col;

@@ -846,7 +846,7 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   return r;
 }
 
-template <int PLANE, bool LINES, bool WHOLE = false>
+template <int PLANE, bool LINES>
 __global__ void __launch_bounds__(TWARPS * 32, 2) k_pmvT(const TArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
@@ -939,10 +939,7 @@ __global__ void __launch_bounds__(TWARPS * 32, 2) k_pmvT(const TArgs a) {
       mma_u8s8(acc[j][0], wa & 0x03030303u, wb & 0x03030303u, wc2 & 0x03030303u, wd & 0x03030303u, b0, b1);
       mma_u8s8(acc[j][1], wa & 0x0C0C0C0Cu, wb & 0x0C0C0C0Cu, wc2 & 0x0C0C0C0Cu, wd & 0x0C0C0C0Cu, b0, b1);
       mma_u8s8(acc[j][2], wa & 0x30303030u, wb & 0x30303030u, wc2 & 0x30303030u, wd & 0x30303030u, b0, b1);
-      if (WHOLE)  // experiment (BSG_PMVT_WHOLE=1): the whole byte (<= 255: 255 x 128 x 2^16 lines fits int32); the epilogue
-        mma_u8s8(acc[j][3], wa, wb, wc2, wd, b0, b1);  // recovers field 3 as whole - fields 0..2
-      else
-        mma_u8s8(acc[j][3], wa & 0xC0C0C0C0u, wb & 0xC0C0C0C0u, wc2 & 0xC0C0C0C0u, wd & 0xC0C0C0C0u, b0, b1);
+      mma_u8s8(acc[j][3], wa & 0xC0C0C0C0u, wb & 0xC0C0C0C0u, wc2 & 0xC0C0C0C0u, wd & 0xC0C0C0C0u, b0, b1);
     }
   };
 
@@ -994,12 +991,6 @@ __global__ void __launch_bounds__(TWARPS * 32, 2) k_pmvT(const TArgs a) {
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   // epilogue: D rows = samples (slot g / g + 8), D columns = slices 2q, 2q + 1
-  if (WHOLE) {
-#pragma unroll
-    for (int j = 0; j < 4; j++)
-#pragma unroll
-      for (int k = 0; k < 4; k++) acc[j][3][k] -= acc[j][0][k] + acc[j][1][k] + acc[j][2][k];
-  }
 #pragma unroll
   for (int j = 0; j < 4; j++)
 #pragma unroll
@@ -1624,18 +1615,7 @@ static int run_pmvT(bsg_view *v, const uint8_t *dig_raw, int plane, const uint8_
     if (lines)
       k_pmvT<0, true><<<grid, thr, TSMEM, s>>>(a);
     else
-    {
-      static int whole = -1;
-      if (whole < 0) {
-        const char *ev = getenv("BSG_PMVT_WHOLE");
-        whole = (ev && ev[0] == '1') ? 1 : 0;
-        if (whole) BSG_CUDA(cudaFuncSetAttribute(k_pmvT<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TSMEM));
-      }
-      if (whole)
-        k_pmvT<0, false, true><<<grid, thr, TSMEM, s>>>(a);
-      else
-        k_pmvT<0, false><<<grid, thr, TSMEM, s>>>(a);
-    }
+      k_pmvT<0, false><<<grid, thr, TSMEM, s>>>(a);
   } else {
     // both planes in one pass: 32-byte strips per warp, twice the sample blocks
     a.nblocks = (int)((nbytes + T2BYTES - 1) / T2BYTES);
@@ -2244,13 +2224,27 @@ int bsg_prod_and_rowsumssq(bsg_bed *h, const int *ind_row, int nr, const int *in
   BSG_TRY(mem.alloc(&d_cols, 3 * (size_t)nc + NP + 2));   // a | w | nv | partials of T | flag
   double *d_rs = d_rows;
   if (nr == 0) return BSG_OK;
-  BSG_CUDA(cudaMemcpyAsync(dV, V, (size_t)nc * K * sizeof(double), cudaMemcpyHostToDevice, s));
   if (nc == 0) {
     BSG_CUDA(cudaStreamSynchronize(s));
     memset(XV, 0, (size_t)nr * K * sizeof(double));
     memset(rowSumsSq, 0, (size_t)nr * sizeof(double));
     return BSG_OK;
   }
+  // V (nc x K doubles, configs[1]: 40 MB, usually pageable R memory) goes up in pieces of two columns on a second stream:
+  // the host stages piece p + 1 while the kernels of piece p run, instead of 3-4 ms of upload in front of everything
+  if (!h->copy_stream) BSG_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (cudaEvent_t &e : h->copy_ev)
+    if (!e) BSG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  BSG_CUDA(cudaEventRecord(h->copy_ev[7], s));  // dV may still be read by work enqueued earlier on s
+  BSG_CUDA(cudaStreamWaitEvent(h->copy_stream, h->copy_ev[7], 0));
+  auto upload = [&](int k0, int k1) -> int {  // columns [k0, k1) of V; afterwards s waits for them
+    BSG_CUDA(cudaMemcpyAsync(dV + (size_t)k0 * nc, V + (size_t)k0 * nc, (size_t)(k1 - k0) * nc * sizeof(double),
+                             cudaMemcpyHostToDevice, h->copy_stream));
+    cudaEvent_t ev = h->copy_ev[(k0 / 2) % 7];
+    BSG_CUDA(cudaEventRecord(ev, h->copy_stream));
+    BSG_CUDA(cudaStreamWaitEvent(s, ev, 0));
+    return BSG_OK;
+  };
   int *d_bad = reinterpret_cast<int *>(d_cols + 3 * (size_t)nc + NP);  // any pass saw a non-finite quantity
   BSG_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), s));
   static int pair_mode = -1;
@@ -2262,6 +2256,7 @@ int bsg_prod_and_rowsumssq(bsg_bed *h, const int *ind_row, int nr, const int *in
     // two columns of V per pass over the matrix (30-bit fixed point per vector, see k_quantT_pair)
     for (int k = 0; k < K; k += 2) {
       const bool both = k + 1 < K;
+      BSG_TRY(upload(k, std::min(K, k + 2)));
       BSG_TRY(prodvec_T_pair(v, dV + (size_t)k * nc, both ? dV + (size_t)(k + 1) * nc : nullptr, dXV + (size_t)k * nr,
                              both ? dXV + (size_t)(k + 1) * nr : nullptr, s));
       k_or_flag<<<1, 1, 0, s>>>(v->s_scal.as<pmv::Scal>(), d_bad);
@@ -2269,6 +2264,7 @@ int bsg_prod_and_rowsumssq(bsg_bed *h, const int *ind_row, int nr, const int *in
       count_launch(2);
     }
   } else {
+    if (K > 0) BSG_TRY(upload(0, K));
     for (int k = 0; k < K; k++) {
       BSG_TRY(bsg_view_prodvec_dev(v, dV + (size_t)k * nc, dXV + (size_t)k * nr, s));
       k_or_flag<<<1, 1, 0, s>>>(v->s_scal.as<pmv::Scal>(), d_bad);
@@ -2371,7 +2367,22 @@ int bsg_multlinreg(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, i
     pair_mode = (ev && ev[0] == '0') ? 0 : 1;
   }
   if (pair_mode && K >= 2) {
-    // two columns of U per pass over the matrix (30-bit fixed point per vector: ~1e-9 of the sums)
+    // two columns of U per pass over the matrix (30-bit fixed point per vector: ~1e-9 of the sums).  The t-scores of a pair
+    // are evaluated right after its passes and fetched (nc x 2 doubles into usually pageable, untouched host memory: the
+    // fetch blocks the host) while the passes of the NEXT pair run.
+    BSG_CUDA(cudaStreamSynchronize(s));  // the counts helper stages its index upload from host memory
+    int32_t *d_cnt0 = nullptr;
+    BSG_TRY(col_counts_dev(h, ind_row, nr, ind_col, nc, &d_cnt0));
+    if (!h->copy_stream) BSG_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t &e : h->copy_ev)
+      if (!e) BSG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    auto fetch = [&](int k0) -> int {
+      const int k1 = std::min(K, k0 + 2);
+      BSG_CUDA(cudaStreamWaitEvent(h->copy_stream, h->copy_ev[(k0 / 2) % 7], 0));
+      BSG_CUDA(cudaMemcpyAsync(tscores + (size_t)k0 * nc, dOut + (size_t)k0 * nc, (size_t)(k1 - k0) * nc * sizeof(double),
+                               cudaMemcpyDeviceToHost, h->copy_stream));
+      return BSG_OK;
+    };
     for (int k = 0; k < K; k += 2) {
       const bool both = k + 1 < K;
       const double *ua = dU + (size_t)k * nr, *ub = both ? dU + (size_t)(k + 1) * nr : nullptr;
@@ -2385,7 +2396,19 @@ int bsg_multlinreg(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, i
         pmvt::PairCoef db{0.0, 1.0, 0.0, 0.0, both ? dNuu + (size_t)(k + 1) * nc : nullptr, nullptr};
         BSG_TRY(view_planes_pair_dev(v, uua, uub, PLANE_NA, da, db, s));
       }
+      const int kp = both ? 2 : 1;
+      k_tscores<<<launch_cap_pub((int64_t)nc * kp), 256, 0, s>>>(nc, kp, d_cnt0, dG + (size_t)k * nc, na ? dNu + (size_t)k * nc : nullptr,
+                                                                na ? dNuu + (size_t)k * nc : nullptr, dY + k, dY + K + k,
+                                                                dOut + (size_t)k * nc);
+      count_launch();
+      BSG_CUDA(cudaEventRecord(h->copy_ev[(k / 2) % 7], s));
+      if (k >= 2) BSG_TRY(fetch(k - 2));
     }
+    BSG_TRY(fetch(((K - 1) / 2) * 2));
+    BSG_CUDA(cudaGetLastError());
+    BSG_CUDA(cudaStreamSynchronize(h->copy_stream));
+    BSG_CUDA(cudaStreamSynchronize(s));
+    return BSG_OK;
   } else {
     for (int k = 0; k < K; k++) {
       const double *u = dU + (size_t)k * nr;

@@ -8,3 +8,5 @@ for w in 0 1; do
 done
 done
 cat gpurun_out/r02_whole_ab.log
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_shim.py -x -q -m gpu -k "proj or rowSums or shim or pcadapt" > gpurun_out/r02_pytest18.log 2>&1; tail -3 gpurun_out/r02_pytest18.log
+timeout 300 python tools/bench_proj.py > gpurun_out/r02h_bench_proj.log 2>&1; grep "prod_and_rowSumsSq\|multLinReg" gpurun_out/r02h_bench_proj.log | cut -c1-200
