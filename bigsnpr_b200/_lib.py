@@ -60,6 +60,7 @@ SIGNATURES = {
     "bsg_readbina2": (C.c_int, [vp, c_int_p, C.c_int, c_int_p, C.c_int, C.POINTER(C.c_uint8)]),
     "bsg_writebina": (C.c_int, [vp, C.c_char_p, c_int_p, C.c_int, c_int_p, C.c_int]),
     "bsg_set_prodvec_path": (C.c_int, [C.c_int]),
+    "bsg_set_scaling_reuse": (C.c_int, [C.c_int]),
     "bsg_prod_and_rowsumssq": (C.c_int, [vp, c_int_p, C.c_int, c_int_p, C.c_int, c_dbl_p, c_dbl_p, c_dbl_p, C.c_int,
                                          c_dbl_p, c_dbl_p]),
     "bsg_multlinreg": (C.c_int, [vp, c_int_p, C.c_int, c_int_p, C.c_int, c_dbl_p, C.c_int, c_dbl_p]),

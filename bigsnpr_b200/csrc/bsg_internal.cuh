@@ -104,6 +104,10 @@ struct bsg_bed {
   // view cached for the 9-argument drop-in matvec calls (bsg_prodvec / bsg_cprodvec)
   struct bsg_view *cv = nullptr;
   std::vector<int> cv_row, cv_col;
+  // fingerprint of the center / scale vectors last uploaded into the cached view (address, length, strided sample of the
+  // values): an unchanged scaling is not uploaded again by the next 9-argument call
+  const double *cv_center_ptr = nullptr, *cv_scale_ptr = nullptr;
+  std::vector<double> cv_scal_sample;
   // scratch reused across calls
   bsg::DevBuf w_idx_row, w_idx_col, w_center, w_scale, w_x, w_out, w_tmp0, w_tmp1, w_tmp2, w_tmp3,
       w_part, w_dig1, w_dig2, w_misc;

@@ -1875,6 +1875,26 @@ int bsg_view_cprodvec(bsg_view *v, const double *x, double *out) { return view_h
 // (src/bed-prod-vec.cpp:22-23); here the accessor state lives in a view cached on the handle: it is
 // reused while the index vectors are unchanged (compared by content), and only center / scale / x are
 // re-uploaded, so a Lanczos loop calling through the old interface does no per-call allocation.
+// Strided sample of (center, scale): every element when nc <= 2048, else 2048 evenly spaced ones of each + the last.  A
+// different scaling differs (practically) everywhere, so address + length + this sample identify "the same vectors as in
+// the previous call" -- what a Lanczos loop through the old interface passes ~1,000 times (R/autoSVD.R:216-218).
+// It is OPT-IN (bsg_set_scaling_reuse(1) or BSG_SCALING_REUSE=1): a vector edited in place at a position the sample
+// does not cover would go unnoticed, and the reference re-reads center / scale on every call.  Default: upload every call.
+static int g_scaling_reuse = -1;
+static void scaling_sample(const double *center, const double *scale, int nc, std::vector<double> &out) {
+  out.clear();
+  if (!center || !scale || nc <= 0) return;
+  const int ns = std::min(nc, 2048);
+  out.reserve(2 * (size_t)ns + 2);
+  for (int t = 0; t < ns; t++) {
+    const size_t j = (size_t)((int64_t)t * nc / ns);
+    out.push_back(center[j]);
+    out.push_back(scale[j]);
+  }
+  out.push_back(center[nc - 1]);
+  out.push_back(scale[nc - 1]);
+}
+
 static int cached_view(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, const double *center,
                        const double *scale, bsg_view **out) {
   if (!h) return fail(BSG_ERR_ARG, "null handle");
@@ -1900,10 +1920,27 @@ static int cached_view(bsg_bed *h, const int *ind_row, int nr, const int *ind_co
     h->cv = v;
     h->cv_row.assign(ind_row ? ind_row : nullptr, ind_row ? ind_row + nr : nullptr);
     h->cv_col.assign(ind_col ? ind_col : nullptr, ind_col ? ind_col + nc : nullptr);
+    h->cv_center_ptr = center;
+    h->cv_scale_ptr = scale;
+    scaling_sample(center, scale, nc, h->cv_scal_sample);
   } else if (center) {
     BSG_TRY(bind_device(h));
-    BSG_CUDA(cudaMemcpyAsync(h->cv->d_center, center, (size_t)nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    BSG_CUDA(cudaMemcpyAsync(h->cv->d_scale, scale, (size_t)nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (g_scaling_reuse < 0) {
+      const char *ev = getenv("BSG_SCALING_REUSE");
+      g_scaling_reuse = (ev && ev[0] == '1') ? 1 : 0;
+    }
+    std::vector<double> smp;
+    scaling_sample(center, scale, nc, smp);
+    const bool same = g_scaling_reuse == 1 && center == h->cv_center_ptr && scale == h->cv_scale_ptr &&
+                      smp.size() == h->cv_scal_sample.size() &&
+                      memcmp(smp.data(), h->cv_scal_sample.data(), smp.size() * sizeof(double)) == 0;
+    if (!same) {
+      BSG_CUDA(cudaMemcpyAsync(h->cv->d_center, center, (size_t)nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      BSG_CUDA(cudaMemcpyAsync(h->cv->d_scale, scale, (size_t)nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      h->cv_center_ptr = center;
+      h->cv_scale_ptr = scale;
+      h->cv_scal_sample.swap(smp);
+    }
   }
   *out = h->cv;
   return BSG_OK;
@@ -2434,6 +2471,14 @@ int bsg_multlinreg(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, i
 
 // 0: automatic (sample-major kernel when that copy is resident, else the SNP-major kernel); 1: always the
 // SNP-major kernel (k_pmvT) for the X-side products.  Process-wide; for tests and measurements.
+// 1: the 9-argument calls skip the upload of center / scale when address, length and a strided sample of the values equal
+// those of the previous call on the handle (see scaling_sample); 0 (default): always upload.  Process-wide.
+int bsg_set_scaling_reuse(int on) {
+  if (on != 0 && on != 1) return fail(BSG_ERR_ARG, "on must be 0 or 1");
+  g_scaling_reuse = on;
+  return BSG_OK;
+}
+
 int bsg_set_prodvec_path(int path) {
   if (path != 0 && path != 1) return fail(BSG_ERR_ARG, "path must be 0 or 1");
   g_force_t = path;

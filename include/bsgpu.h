@@ -89,6 +89,13 @@ int64_t bsg_packed_bytes(const bsg_bed *h);
 int bsg_export_packed(const bsg_bed *h, uint8_t *out);
 
 /* ---- X.y and Xt.y ---------------------------------------------------------------------------- */
+/* The accessor state of a call (index vectors, center, scale) is cached on the handle: a following call with the same
+ * index vectors (compared by content) re-uses it; center / scale are uploaded with every call, like the reference
+ * re-reads them (src/bed-prod-vec.cpp:22-23).  bsg_set_scaling_reuse(1) (or BSG_SCALING_REUSE=1) lets a call skip that
+ * upload when address, length and a strided sample of 2,048 values of each vector equal the previous call's -- the shape
+ * of big_randomSVD's closures (R/autoSVD.R:216-218: ~1,000 calls with identical scaling vectors).  Opt-in because a vector
+ * edited in place at an unsampled position would go unnoticed. */
+int bsg_set_scaling_reuse(int on);
 /* bed_pMatVec4: src/bed-prod-vec.cpp:15-54.  out[nr] = X~[ind_row, ind_col] %*% x[nc] */
 int bsg_prodvec(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc,
                 const double *center, const double *scale, const double *x, double *out);

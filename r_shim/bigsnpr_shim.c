@@ -46,6 +46,13 @@ static int gpu_device(void) {
   return (o == R_NilValue) ? 0 : Rf_asInteger(o);
 }
 
+/* options(bigsnpr.gpu.scaling.reuse = TRUE): an unchanged center / scale pair (same R vectors as in the previous call,
+ * the pattern of big_randomSVD's closures) is not uploaded again -- include/bsgpu.h, bsg_set_scaling_reuse.  Default off. */
+static void apply_scaling_option(void) {
+  SEXP o = Rf_GetOption1(Rf_install("bigsnpr.gpu.scaling.reuse"));
+  chk(bsg_set_scaling_reuse((o == R_NilValue) ? 0 : (Rf_asInteger(o) != 0)));
+}
+
 /* _bigsnpr_bedXPtr(path, n, p): src/bed-acc-xptr.cpp:40-55.  Validation + staging to HBM. */
 SEXP _bigsnpr_bedXPtr(SEXP path, SEXP n, SEXP p) {
   bsg_bed *h = NULL;
@@ -67,6 +74,7 @@ static bsg_bed *handle_of(SEXP obj_bed) {
 /* _bigsnpr_bed_pMatVec4: src/bed-prod-vec.cpp:15-54 */
 SEXP _bigsnpr_bed_pMatVec4(SEXP obj_bed, SEXP ind_row, SEXP ind_col, SEXP center, SEXP scale, SEXP x, SEXP ncores) {
   bsg_bed *h = handle_of(obj_bed);
+  apply_scaling_option();
   int nr = LENGTH(ind_row), nc = LENGTH(ind_col);
   if (LENGTH(center) != nc || LENGTH(scale) != nc) Rf_error("Incompatibility between dimensions.");
   SEXP out = PROTECT(Rf_allocVector(REALSXP, nr));
@@ -78,6 +86,7 @@ SEXP _bigsnpr_bed_pMatVec4(SEXP obj_bed, SEXP ind_row, SEXP ind_col, SEXP center
 /* _bigsnpr_bed_cpMatVec4: src/bed-prod-vec.cpp:59-97 */
 SEXP _bigsnpr_bed_cpMatVec4(SEXP obj_bed, SEXP ind_row, SEXP ind_col, SEXP center, SEXP scale, SEXP x, SEXP ncores) {
   bsg_bed *h = handle_of(obj_bed);
+  apply_scaling_option();
   int nr = LENGTH(ind_row), nc = LENGTH(ind_col);
   if (LENGTH(center) != nc || LENGTH(scale) != nc) Rf_error("Incompatibility between dimensions.");
   SEXP out = PROTECT(Rf_allocVector(REALSXP, nc));

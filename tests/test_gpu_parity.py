@@ -388,6 +388,42 @@ def test_clumping_identical_to_oracle(B, gbed, gbed_na, oracle, obed, obed_na, r
         B.bed_clumping(gbed, ind_row=None)
 
 
+def test_scaling_reuse_shortcut_is_opt_in_and_tracks_changes(B, gbed, oracle, obed, rng):
+    # include/bsgpu.h: the 9-argument calls upload center / scale every time (like the reference re-reads them); with
+    # bsg_set_scaling_reuse(1) an unchanged scaling (same address, length and sampled values) is not uploaded again.
+    from bigsnpr_b200 import _lib
+
+    L = _lib.lib()
+    m = obed.ncol
+    y = rng.normal(size=m)
+    sc = oracle.bed_scaleBinom(obed)
+    c, s = sc["center"].copy(), sc["scale"].copy()
+    want = oracle.bed_prodVec(obed, y, center=c, scale=s)
+    tol = 1e-12 * np.max(np.abs(want))
+    for mode in (0, 1):
+        _lib.check(L.bsg_set_scaling_reuse(mode))
+        try:
+            a1 = B.bed_prodVec(gbed, y, center=c, scale=s)
+            a2 = B.bed_prodVec(gbed, y, center=c, scale=s)          # same vectors again
+            assert np.array_equal(a1, a2) and np.max(np.abs(a1 - want)) < tol
+            s2 = 2.0 * s                                            # a different vector (new address)
+            assert np.max(np.abs(B.bed_prodVec(gbed, y, center=c, scale=s2) - want / 2)) < tol
+            s *= 4.0                                                # the SAME buffer rewritten in place
+            assert np.max(np.abs(B.bed_prodVec(gbed, y, center=c, scale=s) - want / 4)) < tol
+            s /= 4.0
+            if mode == 0:                                           # default: even a one-element edit in place is seen
+                j = 1234                                            # (not one of the 2,048 + 1 sampled positions of 4,542)
+                assert j not in set((np.arange(2048) * m // 2048).tolist()) | {m - 1}
+                keep = s[j]
+                s[j] = 7.0 * keep
+                got = B.bed_prodVec(gbed, y, center=c, scale=s)
+                assert np.max(np.abs(got - oracle.bed_prodVec(obed, y, center=c, scale=s))) < tol
+                s[j] = keep
+                B.bed_prodVec(gbed, y, center=c, scale=s)           # uploads the restored vector (mode 1 would not notice)
+        finally:
+            _lib.check(L.bsg_set_scaling_reuse(0))
+
+
 def test_randomSVD_degenerate_scaling_fails_loudly(B, gbed):
     # the device-vector products turn a zero scale into an all-NaN result; the SVD built on them must not
     # iterate on NaNs and hand back garbage -- it reports the degenerate operator (RSpectra fails on it as well)
