@@ -855,11 +855,73 @@ int bsg_ld_scores(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, in
 
 }  // extern "C"
 
+// One round of the greedy clumping pass, all undecided variants in parallel (one warp each).  The sequential pass
+// (src/clumping-bed.cpp:37-88) visits the variants by decreasing priority and keeps j0 unless an ALREADY KEPT variant of
+// its window is correlated with it above the threshold.  Only higher-priority neighbours matter, so j0's fate is known as
+// soon as theirs is:  REMOVED if one of its conflicting higher-priority neighbours is KEPT, KEPT if all of them are REMOVED
+// (or there is none), otherwise undecided for this round.  By induction on the rank this gives the sequential result; the
+// highest-ranked undecided variant is decided in every round, dense LD blocks resolve in two or three rounds.
+// Neighbour ranges follow which_to_check (src/clumping-utils.h:12-43) literally: left while pos[j] >= pos[j0] - size, right
+// while pos[j] <= pos[j0] + size, each scan stopping at the first failure like the `break` of the sequential loops.
+__global__ void k_clump_round(const uint8_t *__restrict__ conflict, const long long *__restrict__ boff, const int *__restrict__ wlen,
+                              const double *__restrict__ pos, const int *__restrict__ rank, double size, int nc, int *state,
+                              int *n_undecided) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t j0l = warp; j0l < nc; j0l += nw) {
+    const int j0 = (int)j0l;
+    if (state[j0] != -1) continue;  // warp-uniform
+    const int k = rank[j0];
+    const double pos_min = pos[j0] - size, pos_max = pos[j0] + size;
+    int kept = 0, undec = 0;
+    const int wl = wlen[j0];
+    const long long b0 = boff[j0];
+    for (int t0 = 0; t0 < wl; t0 += 32) {  // left neighbours: the pairs of j0's own window
+      const int t = t0 + lane;
+      bool ok = t < wl;
+      int j = j0 - 1 - t;
+      if (ok) ok = pos[j] >= pos_min;
+      const unsigned stop = __ballot_sync(0xffffffffu, !ok);
+      const bool live = stop ? lane < __ffs(stop) - 1 : true;
+      if (live && conflict[b0 + t] && rank[j] < k) {
+        const int st = state[j];
+        kept |= st == 1;
+        undec |= st == -1;
+      }
+      if (stop) break;
+    }
+    for (int j1 = j0 + 1; j1 < nc; j1 += 32) {  // right neighbours: j0 sits in the window of j
+      const int j = j1 + lane, t = j - 1 - j0;
+      bool ok = j < nc;
+      if (ok) ok = pos[j] <= pos_max && t < wlen[j];
+      const unsigned stop = __ballot_sync(0xffffffffu, !ok);
+      const bool live = stop ? lane < __ffs(stop) - 1 : true;
+      if (live && conflict[boff[j] + t] && rank[j] < k) {
+        const int st = state[j];
+        kept |= st == 1;
+        undec |= st == -1;
+      }
+      if (stop) break;
+    }
+    kept = __any_sync(0xffffffffu, kept);
+    undec = __any_sync(0xffffffffu, undec);
+    if (lane == 0) {
+      if (kept)
+        state[j0] = 0;
+      else if (!undec)
+        state[j0] = 1;
+      else
+        atomicAdd(n_undecided, 1);
+    }
+  }
+}
+
 extern "C" {
 
 // bed_clumping_chr: src/clumping-bed.cpp:11-91 (+ which_to_check, src/clumping-utils.h:12-43).
 // ordInd: 1-based column positions by decreasing priority (R: order(S, decreasing = TRUE)); keep[nc] receives 0 / 1.
-// All pair statistics inside the window come from the Gram tiles; the greedy pass in rank order runs on the host.
+// All pair statistics inside the window come from the Gram tiles; the greedy pass is resolved on the device in rounds
+// (k_clump_round; BSG_CLUMP_HOST=1: the literal sequential pass on the host over the downloaded flags).
 static int clumping_common(bsg_bed *h, const int *ind_row, int nr, const int *ind_col, int nc, const double *a1,
                            const double *a2, const int *ordInd, const double *pos, double size, double thr, int *keep,
                            bool fbm) {
@@ -875,6 +937,58 @@ static int clumping_common(bsg_bed *h, const int *ind_row, int nr, const int *in
   cp.thr = thr;
   cp.fbm = fbm;
   BSG_TRY(cor_common(h, ind_row, nr, ind_col, nc, size, pos, nullptr, false, w, sc, &cp));
+  static int host_sweep = -1;
+  if (host_sweep < 0) {
+    const char *ev = getenv("BSG_CLUMP_HOST");
+    host_sweep = (ev && ev[0] == '1') ? 1 : 0;
+  }
+  if (!host_sweep) {
+    std::vector<int> rank(nc);
+    for (int k = 0; k < nc; k++) {
+      int j = ordInd[k] - 1;
+      if (j < 0 || j >= nc) return fail(BSG_ERR_BOUNDS, "Tested subscript out of bounds (ordInd).");
+      rank[j] = k;
+    }
+    if (nc == 0) return BSG_OK;
+    cudaStream_t s = h->stream;
+    int *d_rank = nullptr, *d_state = nullptr, *d_cnt = nullptr;
+    double *d_pos = nullptr;
+    struct G {
+      void *p[4];
+      ~G() {
+        for (void *q : p)
+          if (q) cudaFree(q);
+      }
+    } guard{{nullptr, nullptr, nullptr, nullptr}};
+    BSG_CUDA(pool_alloc((void **)&d_rank, (size_t)nc * sizeof(int), h->device, s));
+    guard.p[0] = d_rank;
+    BSG_CUDA(pool_alloc((void **)&d_state, (size_t)nc * sizeof(int), h->device, s));
+    guard.p[1] = d_state;
+    BSG_CUDA(pool_alloc((void **)&d_pos, (size_t)nc * sizeof(double), h->device, s));
+    guard.p[2] = d_pos;
+    BSG_CUDA(pool_alloc((void **)&d_cnt, 64 * sizeof(int), h->device, s));
+    guard.p[3] = d_cnt;
+    BSG_CUDA(cudaMemcpyAsync(d_rank, rank.data(), (size_t)nc * sizeof(int), cudaMemcpyHostToDevice, s));
+    BSG_CUDA(cudaMemcpyAsync(d_pos, pos, (size_t)nc * sizeof(double), cudaMemcpyHostToDevice, s));
+    BSG_CUDA(cudaMemsetAsync(d_state, 0xFF, (size_t)nc * sizeof(int), s));  // -1: undecided
+    const int grid = (int)std::min<int64_t>(((int64_t)nc * 32 + 255) / 256, 148 * 16);
+    const int BATCH = 4;  // rounds per host round trip
+    int left[BATCH];
+    for (int64_t round = 0; round < (int64_t)nc + BATCH; round += BATCH) {
+      BSG_CUDA(cudaMemsetAsync(d_cnt, 0, BATCH * sizeof(int), s));
+      for (int b = 0; b < BATCH; b++)
+        k_clump_round<<<grid, 256, 0, s>>>(sc.keep, sc.boff, sc.wlen, d_pos, d_rank, size, nc, d_state, d_cnt + b);
+      count_launch(BATCH);
+      BSG_CUDA(cudaMemcpyAsync(left, d_cnt, BATCH * sizeof(int), cudaMemcpyDeviceToHost, s));
+      BSG_CUDA(cudaStreamSynchronize(s));
+      if (left[BATCH - 1] == 0) break;
+    }
+    BSG_CUDA(cudaMemcpyAsync(keep, d_state, (size_t)nc * sizeof(int), cudaMemcpyDeviceToHost, s));
+    BSG_CUDA(cudaStreamSynchronize(s));
+    for (int j = 0; j < nc; j++)
+      if (keep[j] != 0 && keep[j] != 1) return fail(BSG_ERR_CUDA, "clumping rounds did not converge.");
+    return BSG_OK;
+  }
   std::vector<uint8_t> conflict((size_t)w.total);
   if (w.total)
     BSG_CUDA(cudaMemcpyAsync(conflict.data(), sc.keep, (size_t)w.total, cudaMemcpyDeviceToHost, h->stream));
