@@ -719,6 +719,7 @@ int bsg_group_tcrossprod(bsg_group *g, const int *ind_row, int nr, const int *in
   }
   if (!rc) {
     cudaSetDevice(g->devices[0]);
+    prefault_pages(K, (size_t)nr * nr * sizeof(double));  // while the devices reduce
     cudaError_t e = cudaMemcpyAsync(K, dK[0], (size_t)nr * nr * sizeof(double), cudaMemcpyDeviceToHost, g->shard[0]->stream);
     if (e != cudaSuccess) rc = cuda_fail(e, "GRM download");
   }

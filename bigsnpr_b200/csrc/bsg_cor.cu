@@ -20,24 +20,6 @@
 #include "bsg_gram.cuh"
 #include "bsg_internal.cuh"
 
-// first touch of a fresh host allocation from several threads (one write per 4 KB page)
-static void prefault_pages(void *p, size_t bytes) {
-  if (bytes < ((size_t)64 << 20)) return;
-  unsigned hw = std::thread::hardware_concurrency();
-  const int nt = (int)std::max(1u, std::min(hw ? hw : 1u, 16u));
-  std::vector<std::thread> th;
-  const size_t per = (bytes / nt + 4095) & ~(size_t)4095;
-  for (int t = 0; t < nt; t++) {
-    const size_t b0 = (size_t)t * per, b1 = std::min(bytes, b0 + per);
-    if (b0 >= b1) break;
-    th.emplace_back([=]() {
-      volatile char *q = static_cast<volatile char *>(p);
-      for (size_t o = b0; o < b1; o += 4096) q[o] = 0;
-      q[b1 - 1] = 0;
-    });
-  }
-  for (auto &x : th) x.join();
-}
 
 namespace bsg {
 

@@ -120,6 +120,7 @@ namespace bsg {
 int stage_finish(bsg_bed *h);  // counts and NA flags from copy A; copy B only when requested
 int build_copy_B(bsg_bed *h);  // sample-major copy on demand (no-op when resident)
 int bind_device(const bsg_bed *h);
+void prefault_pages(void *p, size_t bytes);  // parallel first touch of a host output buffer (bsg_core.cu)
 cudaError_t pool_alloc(void **p, size_t bytes, int device, cudaStream_t s);  // stream-ordered pool, freed with cudaFree
 
 // ---- index helpers (bsg_core.cu) -------------------------------------------------------------

@@ -803,6 +803,7 @@ static int tcrossprod_dsyrk(bsg_bed *h, const int *ind_row, int nr, const int *i
     k_mirror_lower<<<(int)std::min<int64_t>(((int64_t)nr * nr + 255) / 256, 148 * 32), 256, 0, s>>>(dK, nr);
     count_launch();
     cudaError_t e2 = cudaGetLastError();
+    if (K) prefault_pages(K, (size_t)nr * nr * sizeof(double));
     if (e2 == cudaSuccess && K) e2 = cudaMemcpyAsync(K, dK, (size_t)nr * nr * sizeof(double), cudaMemcpyDeviceToHost, s);
     if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(s);
     if (e2 != cudaSuccess) rc = cuda_fail(e2, "GRM download");
@@ -1021,6 +1022,7 @@ static int tcrossprod_impl(bsg_bed *h, const int *ind_row, int nr, const int *in
     k_grm_finish<<<(int)std::min<int64_t>(((int64_t)nr * nr + 255) / 256, 148 * 32), 256, 0, s>>>(dK, nr, nr, d_r, d_q, sumW3);
     count_launch();
     cudaError_t e2 = cudaGetLastError();
+    if (K) prefault_pages(K, (size_t)nr * nr * sizeof(double));  // 800 MB at configs[3], while the device still computes
     if (e2 == cudaSuccess && K) e2 = cudaMemcpyAsync(K, dK, (size_t)nr * nr * sizeof(double), cudaMemcpyDeviceToHost, s);
     if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(s);
     if (e2 != cudaSuccess) rc = cuda_fail(e2, "GRM download");
