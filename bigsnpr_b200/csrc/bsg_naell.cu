@@ -8,19 +8,23 @@
 //
 // Here the positions are stored so that the gather runs out of SHARED memory with coalesced index loads:
 //   * the contraction index is cut into chunks of 4096; the quantised vector of one chunk (4096 x int64 = 32 KB) sits in
-//     shared memory while every line group consumes its entries of that chunk;
+//     shared memory while every line group consumes its entries of that chunk (double-buffered: the next chunk's slice
+//     streams in with cp.async meanwhile);
 //   * lines are grouped by 32; a block (group g, chunk c) stores its entries ELL style in rows of 8 entries per line -- row r
-//     holds entries 8r..8r+7 of the 32 lines, lane after lane, 16-bit chunk-local indices, padded to the longest line of the
-//     block -- so one warp load is 512 contiguous bytes (a uint4 = 8 indices per lane), all rows of a block are in flight
-//     together, and each lane adds shared[idx] to its own line's exact 64-bit sum (32-bit halves: no overflow, order free);
-//   * a warp keeps the sums of its groups in registers across all chunks: one plain store per line at the end, no atomics;
+//     holds slots 8r..8r+7 of the 32 lines, lane after lane, 16-bit byte offsets into the chunk's slice, padded to the block's
+//     slot count -- so one warp load is 512 contiguous bytes (a uint4 = 8 entries per lane) and each lane adds the gathered
+//     values to its own line's exact sum (row sums in int64, |Q| < 2^60, then split into 32-bit halves: no overflow, order
+//     free);
+//   * a warp keeps the sums of its group(s) in registers across its chunks; with few groups the chunks are split over CTAs and
+//     the partial sums are combined with 64-bit integer atomics (exact, order free), for X.y straight into `part`;
 //   * the ORDER of a line's entries is free (integer sums), so each block is re-ordered once at build time such that the 16
-//     lanes of a half-warp hit 16 different shared-memory banks in every slot: a greedy edge colouring of the bipartite
-//     multigraph (lane, bank = index mod 16) with slots as colours (k_recolor).  Random order costs 2.66 wavefronts per
+//     lanes of a half-warp hit 16 different shared-memory bank pairs in every slot: a greedy edge colouring of the bipartite
+//     multigraph (lane, bank = index mod 16) with slots as colours (k_recolor).  Arrival order costs 2.66 wavefronts per
 //     ideal one (ncu, profiles/r02_kcorr_ncu_before.txt); the colouring needs ~4 % more slots than the longest line and
-//     makes the gathers conflict free.  Unused slots point at 16 zero words behind the vector slice (one per bank), so
-//     the gather loop has no predicates and no per-line counts.
-// 2 bytes per missing value and side (+ padding ~40 % at 1 %), built once per handle from the SNP-major copy.  The matvec
+//     makes the gathers conflict free (1.01, profiles/r02_kcorr_ncu_after.txt).  The idle slots of a half-warp all read ONE
+//     zero word behind the slice, the one of a bank no entry of that slot uses, so the gather loop has no predicates and no
+//     per-line counts.
+// ~3.1 bytes per missing value and side including padding, built once per handle from the SNP-major copy.  The matvec
 // kernels then always run in their no-missing mode.  Results equal the flag-plane path up to fp64 rounding of the last
 // combination (the sums themselves are exact integers).
 #include <stdint.h>
